@@ -1,0 +1,285 @@
+/*
+ * sopht_b200.h — C ABI of libsopht_b200.so
+ *
+ * B200 (sm_100a) implementation of the SophT Eulerian flow time step.  Every
+ * entry point replaces one kernel (or kernel family) that the reference builds
+ * at run time with pystencils / pyFFTW / numba; the citation after each
+ * declaration names the reference interface it stands in for
+ * (paths relative to the SophT source tree, sopht/numeric/...).
+ *
+ * Conventions
+ *  - plain C: pointers + sizes only, no torch / C++ types.
+ *  - all pointers in sopht_field_t are DEVICE pointers; the caller owns the
+ *    memory.  Work is enqueued on `stream` (a cudaStream_t passed as void*)
+ *    and the call returns without synchronising.
+ *  - fields are strided views: shape/stride are in ELEMENTS of the dtype
+ *    (for complex fields: in complex elements), slowest axis first, x last.
+ *    Scalar fields are (nz, ny, nx) / (ny, nx); vector fields (dim, nz, ny, nx).
+ *  - scalars travel as double and are rounded to the kernel dtype inside.
+ *  - return value: 0 on success, negative sopht_status_t otherwise; a text
+ *    description of the last failure is available from sopht_last_error().
+ *    Nothing throws or aborts across this boundary.
+ */
+#ifndef SOPHT_B200_H
+#define SOPHT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOPHT_MAX_DIMS 5
+
+typedef enum {
+  SOPHT_F32 = 0,
+  SOPHT_F64 = 1
+} sopht_dtype_t;
+
+typedef enum {
+  SOPHT_OK = 0,
+  SOPHT_ERR_DTYPE = -1,   /* dtype is neither SOPHT_F32 nor SOPHT_F64            */
+  SOPHT_ERR_SHAPE = -2,   /* operand shapes / ndim inconsistent                   */
+  SOPHT_ERR_STRIDE = -3,  /* stride pattern not supported by this entry point     */
+  SOPHT_ERR_ARG = -4,     /* bad scalar argument (width, order, axis, ...)        */
+  SOPHT_ERR_CUDA = -5,    /* a CUDA runtime call or kernel launch failed          */
+  SOPHT_ERR_CUFFT = -6,   /* a cuFFT call failed                                  */
+  SOPHT_ERR_ALLOC = -7,   /* device allocation failed                             */
+  SOPHT_ERR_HANDLE = -8   /* null / stale handle                                  */
+} sopht_status_t;
+
+typedef struct {
+  void *data;                      /* device pointer to element [0,...,0]          */
+  int32_t ndim;                    /* 1..SOPHT_MAX_DIMS                            */
+  int64_t shape[SOPHT_MAX_DIMS];   /* slowest axis first                           */
+  int64_t stride[SOPHT_MAX_DIMS];  /* element strides (may be any sign-positive)   */
+} sopht_field_t;
+
+const char *sopht_last_error(void);
+int sopht_version(void);
+/* number of kernel launches issued through this library since load (for bench accounting) */
+int64_t sopht_launch_count(void);
+
+/* ------------------------------------------------------------------------ */
+/* Elementwise operations on strided views (1..4-D, 2D and 3D grids alike)   */
+/* ------------------------------------------------------------------------ */
+
+/* field[...] = fixed_val
+ * ref: eulerian_grid_ops/stencil_ops_3d/elementwise_ops_3d.py:60-119 (gen_set_fixed_val_pyst_kernel_3d),
+ *      stencil_ops_2d/elementwise_ops_2d.py:60-114 */
+int sopht_set_fixed_val(int dtype, const sopht_field_t *field, double fixed_val, void *stream);
+
+/* vector_field[c, ...] = fixed_vals[c]  (leading axis = component)
+ * ref: elementwise_ops_3d.py:95-115 (vector closure) */
+int sopht_set_fixed_vals_vector(int dtype, const sopht_field_t *vector_field,
+                                const double *fixed_vals, int n_vals, void *stream);
+
+/* field[...] = rhs_field[...]
+ * ref: elementwise_ops_3d.py:122-143 (gen_elementwise_copy_pyst_kernel_3d) */
+int sopht_elementwise_copy(int dtype, const sopht_field_t *field, const sopht_field_t *rhs_field,
+                           void *stream);
+
+/* sum_field = field_1 + field_2 (aliasing sum_field == field_k allowed)
+ * ref: elementwise_ops_3d.py:13-57 (gen_elementwise_sum_pyst_kernel_3d) */
+int sopht_elementwise_sum(int dtype, const sopht_field_t *sum_field, const sopht_field_t *field_1,
+                          const sopht_field_t *field_2, void *stream);
+
+/* sum_field = field_1_prefac * field_1 + field_2_prefac * field_2
+ * ref: elementwise_ops_3d.py:337-387 (gen_elementwise_saxpby_pyst_kernel_3d) */
+int sopht_elementwise_saxpby(int dtype, const sopht_field_t *sum_field,
+                             const sopht_field_t *field_1, const sopht_field_t *field_2,
+                             double field_1_prefac, double field_2_prefac, void *stream);
+
+/* sum_field = field + fixed_val
+ * ref: elementwise_ops_3d.py:271-334 (gen_add_fixed_val_pyst_kernel_3d) */
+int sopht_add_fixed_val(int dtype, const sopht_field_t *sum_field, const sopht_field_t *field,
+                        double fixed_val, void *stream);
+
+/* sum_field[c] = vector_field[c] + fixed_vals[c]
+ * ref: elementwise_ops_3d.py:305-329 */
+int sopht_add_fixed_vals_vector(int dtype, const sopht_field_t *sum_field,
+                                const sopht_field_t *vector_field, const double *fixed_vals,
+                                int n_vals, void *stream);
+
+/* product = field_1 * field_2 on complex fields (interleaved re/im; strides in complex elements)
+ * ref: elementwise_ops_3d.py:146-197 (gen_elementwise_complex_product_pyst_kernel_3d) */
+int sopht_elementwise_complex_product(int dtype, const sopht_field_t *product_field,
+                                      const sopht_field_t *field_1, const sopht_field_t *field_2,
+                                      void *stream);
+
+/* result = field_1 x field_2, (3, nz, ny, nx) operands
+ * ref: elementwise_ops_3d.py:390-449 (gen_elementwise_cross_product_pyst_kernel_3d) */
+int sopht_elementwise_cross_product_3d(int dtype, const sopht_field_t *result_field,
+                                       const sopht_field_t *field_1, const sopht_field_t *field_2,
+                                       void *stream);
+
+/* ring of `width` cells on every grid face <- fixed value(s).  `field` is a scalar grid field
+ * (2-D / 3-D) when is_vector == 0, a vector field (dim leading) when is_vector == 1.
+ * ref: elementwise_ops_3d.py:200-268, elementwise_ops_2d.py:193-253 */
+int sopht_set_fixed_val_at_boundaries(int dtype, const sopht_field_t *field, int width,
+                                      const double *fixed_vals, int is_vector, void *stream);
+
+/* penalised = (field + f*chi*penalty) / (1 + f*chi)
+ * ref: stencil_ops_3d/brinkmann_penalise_3d.py:13-83, stencil_ops_2d/brinkmann_penalise_2d.py:13-76 */
+int sopht_brinkmann_penalise(int dtype, const sopht_field_t *penalised_field,
+                             const sopht_field_t *field, const sopht_field_t *char_field,
+                             const sopht_field_t *penalty_field, double penalty_factor,
+                             void *stream);
+
+/* same with a spatially constant penalty value
+ * ref: stencil_ops_2d/brinkmann_penalise_2d.py:79-141 */
+int sopht_brinkmann_penalise_vs_fixed_val(int dtype, const sopht_field_t *penalised_field,
+                                          const sopht_field_t *field,
+                                          const sopht_field_t *char_field, double penalty_val,
+                                          double penalty_factor, void *stream);
+
+/* smooth sine Heaviside of a level set
+ * ref: stencil_ops_3d/char_func_from_level_set_3d.py:12-51, stencil_ops_2d/char_func_from_level_set_2d.py:12-51 */
+int sopht_char_func_from_level_set(int dtype, const sopht_field_t *char_func_field,
+                                   const sopht_field_t *level_set_field, double blend_width,
+                                   void *stream);
+
+/* velocity_magnitude = sum_c |velocity[c]| (written, as the reference does) and the device scalar
+ * *max_out = max over cells (max_out: device pointer to one element of dtype).
+ * ref: simulator/flow/passive_transport_flow_simulators.py:139-155 */
+int sopht_abs_sum_max(int dtype, const sopht_field_t *velocity_magnitude_field,
+                      const sopht_field_t *velocity_field, void *max_out, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* 3D stencils (pystencils ghost-ring rule: only cells whose whole stencil   */
+/* is in bounds are written; `reset_ghost_zone` zeroes the ring afterwards)  */
+/* ------------------------------------------------------------------------ */
+
+/* flux = prefactor * (sum of 6 neighbours - 6 f); scalar (nz,ny,nx) or vector (3,nz,ny,nx)
+ * ref: stencil_ops_3d/diffusion_flux_3d.py:14-115 */
+int sopht_diffusion_flux_3d(int dtype, const sopht_field_t *diffusion_flux,
+                            const sopht_field_t *field, double prefactor, int reset_ghost_zone,
+                            void *stream);
+
+/* curl = prefactor * centred-difference curl (no 1/(2dx))
+ * ref: stencil_ops_3d/curl_3d.py:13-132 */
+int sopht_curl_3d(int dtype, const sopht_field_t *curl, const sopht_field_t *field,
+                  double prefactor, int reset_ghost_zone, void *stream);
+
+/* divergence = 0.5 * inv_dx * centred-difference divergence
+ * ref: stencil_ops_3d/divergence_3d.py:13-96 */
+int sopht_divergence_3d(int dtype, const sopht_field_t *divergence, const sopht_field_t *field,
+                        double inv_dx, int reset_ghost_zone, void *stream);
+
+/* vorticity += prefactor * curl_c(velocity_forcing) on the ring-1 interior
+ * ref: stencil_ops_3d/update_vorticity_from_velocity_forcing_3d.py:12-132 */
+int sopht_update_vorticity_from_velocity_forcing_3d(int dtype, const sopht_field_t *vorticity_field,
+                                                    const sopht_field_t *velocity_forcing_field,
+                                                    double prefactor, void *stream);
+
+/* vorticity += prefactor * curl_c(penalised_velocity - velocity)
+ * ref: update_vorticity_from_velocity_forcing_3d.py:135-291 */
+int sopht_update_vorticity_from_penalised_velocity_3d(int dtype,
+                                                      const sopht_field_t *vorticity_field,
+                                                      const sopht_field_t *penalised_velocity_field,
+                                                      const sopht_field_t *velocity_field,
+                                                      double prefactor, void *stream);
+
+/* flux_c = prefactor * (omega . grad_c) u_c, ring <- 0
+ * ref: stencil_ops_3d/vorticity_stretching_flux_3d.py:13-107 */
+int sopht_vorticity_stretching_flux_3d(int dtype, const sopht_field_t *flux_field,
+                                       const sopht_field_t *vorticity_field,
+                                       const sopht_field_t *velocity_field, double prefactor,
+                                       void *stream);
+
+/* advection_flux += conservative ENO3 flux divergence (six face terms), ring-2 interior
+ * ref: stencil_ops_3d/advection_flux_3d.py:12-233 */
+int sopht_advection_flux_eno3_3d(int dtype, const sopht_field_t *advection_flux,
+                                 const sopht_field_t *field, const sopht_field_t *velocity,
+                                 double inv_dx, void *stream);
+
+/* filter_flux = 0.25 * (-f[-1] + 2 f - f[+1]) along `axis` (0 = x, 1 = y, 2 = z), ring-1 interior
+ * ref: stencil_ops_3d/laplacian_filter_3d.py:58-77 */
+int sopht_laplacian_filter_flux_3d(int dtype, const sopht_field_t *filter_flux,
+                                   const sopht_field_t *field, int axis, void *stream);
+
+/* sine-ramp penalisation of a `width`-cell ring, applied x then y then z.
+ * ramp_{x,y,z}: HOST arrays of 2*width factors each (front ramp then back ramp), in the kernel dtype's
+ * value range, precomputed by the caller from the grid coordinates exactly as the reference does.
+ * ref: stencil_ops_3d/penalise_field_boundary_3d.py:13-240 */
+int sopht_penalise_field_boundary_3d(int dtype, const sopht_field_t *field, int width,
+                                     const double *ramp_x, const double *ramp_y,
+                                     const double *ramp_z, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* 2D stencils                                                               */
+/* ------------------------------------------------------------------------ */
+
+/* ref: stencil_ops_2d/diffusion_flux_2d.py:13-72 */
+int sopht_diffusion_flux_2d(int dtype, const sopht_field_t *diffusion_flux,
+                            const sopht_field_t *field, double prefactor, int reset_ghost_zone,
+                            void *stream);
+/* ref: stencil_ops_2d/advection_flux_2d.py:12-165 */
+int sopht_advection_flux_eno3_2d(int dtype, const sopht_field_t *advection_flux,
+                                 const sopht_field_t *field, const sopht_field_t *velocity,
+                                 double inv_dx, void *stream);
+/* curl (2,ny,nx) of a scalar stream function: u_x = p dpsi/dy, u_y = -p dpsi/dx
+ * ref: stencil_ops_2d/outplane_field_curl_2d.py:13-100 */
+int sopht_outplane_field_curl_2d(int dtype, const sopht_field_t *curl, const sopht_field_t *field,
+                                 double prefactor, int reset_ghost_zone, void *stream);
+/* scalar curl of a (2,ny,nx) field, no ring reset
+ * ref: stencil_ops_2d/inplane_field_curl_2d.py:10-50 */
+int sopht_inplane_field_curl_2d(int dtype, const sopht_field_t *curl, const sopht_field_t *field,
+                                double prefactor, void *stream);
+/* ref: stencil_ops_2d/update_vorticity_from_velocity_forcing_2d.py:12-71 */
+int sopht_update_vorticity_from_velocity_forcing_2d(int dtype, const sopht_field_t *vorticity_field,
+                                                    const sopht_field_t *velocity_forcing_field,
+                                                    double prefactor, void *stream);
+/* ref: stencil_ops_2d/update_vorticity_from_velocity_forcing_2d.py:74-147 */
+int sopht_update_vorticity_from_penalised_velocity_2d(int dtype,
+                                                      const sopht_field_t *vorticity_field,
+                                                      const sopht_field_t *penalised_velocity_field,
+                                                      const sopht_field_t *velocity_field,
+                                                      double prefactor, void *stream);
+/* ref: stencil_ops_2d/penalise_field_boundary_2d.py:12-142 */
+int sopht_penalise_field_boundary_2d(int dtype, const sopht_field_t *field, int width,
+                                     const double *ramp_x, const double *ramp_y, void *stream);
+
+/* ------------------------------------------------------------------------ */
+/* Unbounded Poisson solver (Hockney-Eastwood doubled domain, FFT)           */
+/* ------------------------------------------------------------------------ */
+
+typedef struct sopht_poisson *sopht_poisson_t;
+
+#define SOPHT_POISSON_AUTO 0          /* fused power-of-two path when eligible, else generic */
+#define SOPHT_POISSON_FORCE_GENERIC 1 /* cuFFT batched 2-D + strided 1-D path (any size, f32/f64) */
+
+/* Builds plans, workspaces and the Green's function spectrum G_hat * dx^dim on the doubled grid.
+ * dim = 2: (ny, nx) grids (nz ignored); dim = 3: (nz, ny, nx).
+ * mz/my/mx: HOST arrays (2nz / 2ny / 2nx doubles) holding min(x, 2X - x) of the doubled-axis
+ * coordinates, and origin_value the regularised G at r = 0, both computed by the caller with the
+ * reference's expressions; pass NULL arrays to have them derived from x_range and dx.
+ * The library owns everything behind the handle; solve() allocates nothing.
+ * ref: poisson_solver_3d/UnboundedPoissonSolverPYFFTW3D.py:12-83 (ctor + Green's function),
+ *      poisson_solver_2d/UnboundedPoissonSolverPYFFTW2D.py:11-68,
+ *      poisson_solver_3d/FFTPyFFTW3D.py:28-56 (plans and buffers) */
+int sopht_poisson_create(sopht_poisson_t *handle, int dtype, int dim, int nz, int ny, int nx,
+                         double x_range, double dx, const double *mz, const double *my,
+                         const double *mx, double origin_value, int flags, void *stream);
+
+/* -laplacian(solution) = rhs on the unbounded domain. Fields: scalar grid fields, or vector fields
+ * with a leading component axis (each component solved independently).
+ * ref: UnboundedPoissonSolverPYFFTW3D.py:111-172 (solve, vector_field_solve),
+ *      UnboundedPoissonSolverPYFFTW2D.py:95-129 */
+int sopht_poisson_solve(sopht_poisson_t handle, const sopht_field_t *solution_field,
+                        const sopht_field_t *rhs_field, void *stream);
+
+/* device pointer to Re(G_hat) * dx^dim / (doubled cell count), natural (kz, ky, kx<=nx) order, of the
+ * handle's dtype (NULL if the active path does not keep it in that layout).
+ * ref: UnboundedPoissonSolverPYFFTW3D.py:47-49 (fourier_greens_function_times_dx_cubed) */
+int sopht_poisson_green_hat(sopht_poisson_t handle, const void **device_ptr);
+
+/* "generic" or "pow2" */
+const char *sopht_poisson_path(sopht_poisson_t handle);
+
+int sopht_poisson_destroy(sopht_poisson_t handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOPHT_B200_H */

@@ -1,0 +1,86 @@
+"""CPU ORACLE (test infrastructure): unbounded Poisson solve, scipy.fft restatement.
+
+Follows sopht/numeric/eulerian_grid_ops/poisson_solver_3d/UnboundedPoissonSolverPYFFTW3D.py:51-149 and
+poisson_solver_2d/UnboundedPoissonSolverPYFFTW2D.py:47-129 with scipy's rfftn/irfftn standing in for
+the two pyFFTW plans — exactly the substitution the reference's own tests make
+(tests/.../test_unbounded_poisson_solver_3d.py:55-90, SophT's scipy_fft_3d.py:7-15).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+from scipy.fft import irfftn, rfftn
+
+
+class UnboundedPoissonSolver3D:
+    def __init__(self, grid_size_z, grid_size_y, grid_size_x, x_range=1.0, real_t=np.float64, workers=1):
+        self.nz, self.ny, self.nx = grid_size_z, grid_size_y, grid_size_x
+        self.real_t = real_t
+        self.workers = workers
+        self.x_range = x_range
+        self.y_range = x_range * (grid_size_y / grid_size_x)
+        self.z_range = x_range * (grid_size_z / grid_size_x)
+        self.dx = real_t(x_range / grid_size_x)
+        self.domain_doubled_buffer = np.zeros((2 * self.nz, 2 * self.ny, 2 * self.nx), dtype=real_t)
+        self.fourier_greens_function_times_dx_cubed = self._greens() * (self.dx**3)
+
+    def _greens(self):  # UnboundedPoissonSolverPYFFTW3D.py:51-83
+        real_t = self.real_t
+        x = np.linspace(0, 2 * self.x_range - self.dx, 2 * self.nx).astype(real_t)
+        y = np.linspace(0, 2 * self.y_range - self.dx, 2 * self.ny).astype(real_t)
+        z = np.linspace(0, 2 * self.z_range - self.dx, 2 * self.nz).astype(real_t)
+        zg, yg, xg = np.meshgrid(z, y, x, indexing="ij")
+        r = np.sqrt(
+            np.minimum(xg, 2 * self.x_range - xg) ** 2
+            + np.minimum(yg, 2 * self.y_range - yg) ** 2
+            + np.minimum(zg, 2 * self.z_range - zg) ** 2
+        )
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            g = (1 / r) / (4 * np.pi)
+        g[0, 0, 0] = 1 / (4 * np.pi * self.dx)
+        return rfftn(g, workers=self.workers)
+
+    def solve(self, solution_field, rhs_field):  # :111-149
+        buf = self.domain_doubled_buffer
+        buf[...] = 0
+        buf[: self.nz, : self.ny, : self.nx] = rhs_field
+        spec = rfftn(buf, workers=self.workers)
+        spec = spec * self.fourier_greens_function_times_dx_cubed
+        solution_field[...] = irfftn(spec, s=buf.shape, workers=self.workers)[: self.nz, : self.ny, : self.nx]
+
+    def vector_field_solve(self, solution_vector_field, rhs_vector_field):  # :151-172
+        for c in range(3):
+            self.solve(solution_vector_field[c], rhs_vector_field[c])
+
+
+class UnboundedPoissonSolver2D:
+    def __init__(self, grid_size_y, grid_size_x, x_range=1.0, real_t=np.float64, workers=1):
+        self.ny, self.nx = grid_size_y, grid_size_x
+        self.real_t = real_t
+        self.workers = workers
+        self.x_range = x_range
+        self.y_range = x_range * (grid_size_y / grid_size_x)
+        self.dx = real_t(x_range / grid_size_x)
+        self.domain_doubled_buffer = np.zeros((2 * self.ny, 2 * self.nx), dtype=real_t)
+        self.fourier_greens_function_times_dx_squared = self._greens() * (self.dx**2)
+
+    def _greens(self):  # UnboundedPoissonSolverPYFFTW2D.py:47-68
+        real_t = self.real_t
+        x = np.linspace(0, 2 * self.x_range - self.dx, 2 * self.nx).astype(real_t)
+        y = np.linspace(0, 2 * self.y_range - self.dx, 2 * self.ny).astype(real_t)
+        xg, yg = np.meshgrid(x, y)
+        r = np.sqrt(
+            np.minimum(xg, 2 * self.x_range - xg) ** 2 + np.minimum(yg, 2 * self.y_range - yg) ** 2
+        )
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            g = -np.log(r) / (2 * np.pi)
+        g[0, 0] = -(2 * np.log(self.dx / np.sqrt(np.pi)) - 1) / (4 * np.pi)
+        return rfftn(g, workers=self.workers)
+
+    def solve(self, solution_field, rhs_field):  # :95-129
+        buf = self.domain_doubled_buffer
+        buf[...] = 0
+        buf[: self.ny, : self.nx] = rhs_field
+        spec = rfftn(buf, workers=self.workers)
+        spec = spec * self.fourier_greens_function_times_dx_squared
+        solution_field[...] = irfftn(spec, s=buf.shape, workers=self.workers)[: self.ny, : self.nx]

@@ -1,0 +1,150 @@
+// Shared helpers for libsopht_b200: view descriptors, argument checks, launch accounting.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "sopht_b200.h"
+
+namespace sopht {
+
+// ---- error reporting (thread-local text for sopht_last_error) -------------------------------
+void set_error(const char* fmt, ...);
+extern int64_t g_launch_count;
+
+#define SOPHT_FAIL(code, ...)      \
+  do {                             \
+    ::sopht::set_error(__VA_ARGS__); \
+    return (code);                 \
+  } while (0)
+
+#define SOPHT_CHECK_DTYPE(dtype)                                          \
+  do {                                                                    \
+    if ((dtype) != SOPHT_F32 && (dtype) != SOPHT_F64)                     \
+      SOPHT_FAIL(SOPHT_ERR_DTYPE, "%s: invalid dtype %d", __func__, (int)(dtype)); \
+  } while (0)
+
+#define SOPHT_CHECK_LAUNCH()                                                          \
+  do {                                                                                \
+    ::sopht::g_launch_count++;                                                        \
+    cudaError_t e__ = cudaGetLastError();                                             \
+    if (e__ != cudaSuccess)                                                           \
+      SOPHT_FAIL(SOPHT_ERR_CUDA, "%s: kernel launch failed: %s", __func__,            \
+                 cudaGetErrorString(e__));                                            \
+  } while (0)
+
+#define SOPHT_CUDA(call)                                                              \
+  do {                                                                                \
+    cudaError_t e__ = (call);                                                         \
+    if (e__ != cudaSuccess)                                                           \
+      SOPHT_FAIL(SOPHT_ERR_CUDA, "%s: %s failed: %s", __func__, #call,                \
+                 cudaGetErrorString(e__));                                            \
+  } while (0)
+
+// ---- device-side views ----------------------------------------------------------------------
+// 3-D scalar view (z, y, x); strides in elements.
+template <typename T>
+struct View3 {
+  T* p;
+  int64_t sz, sy, sx;
+  __host__ __device__ __forceinline__ T& operator()(int k, int j, int i) const {
+    return p[k * sz + j * sy + i * sx];
+  }
+  __host__ __device__ __forceinline__ T* at(int k, int j, int i) const {
+    return p + (k * sz + j * sy + i * sx);
+  }
+};
+
+// 2-D scalar view (y, x)
+template <typename T>
+struct View2 {
+  T* p;
+  int64_t sy, sx;
+  __host__ __device__ __forceinline__ T& operator()(int j, int i) const {
+    return p[j * sy + i * sx];
+  }
+};
+
+// ---- host-side helpers on sopht_field_t --------------------------------------------------------
+inline bool same_shape(const sopht_field_t* a, const sopht_field_t* b) {
+  if (a->ndim != b->ndim) return false;
+  for (int d = 0; d < a->ndim; ++d)
+    if (a->shape[d] != b->shape[d]) return false;
+  return true;
+}
+
+inline int64_t numel(const sopht_field_t* a) {
+  int64_t n = 1;
+  for (int d = 0; d < a->ndim; ++d) n *= a->shape[d];
+  return n;
+}
+
+inline bool is_contiguous(const sopht_field_t* a) {
+  int64_t expect = 1;
+  for (int d = a->ndim - 1; d >= 0; --d) {
+    if (a->shape[d] != 1 && a->stride[d] != expect) return false;
+    expect *= a->shape[d];
+  }
+  return true;
+}
+
+inline bool valid_field(const sopht_field_t* a, int min_dim, int max_dim) {
+  if (!a || !a->data) return false;
+  if (a->ndim < min_dim || a->ndim > max_dim) return false;
+  for (int d = 0; d < a->ndim; ++d)
+    if (a->shape[d] < 0 || a->stride[d] < 0) return false;
+  return true;
+}
+
+// component `c` of a vector field as a 3-D view (drops the leading axis)
+template <typename T>
+inline View3<T> comp3(const sopht_field_t* f, int c) {
+  View3<T> v;
+  v.p = reinterpret_cast<T*>(f->data) + c * f->stride[0];
+  v.sz = f->stride[1];
+  v.sy = f->stride[2];
+  v.sx = f->stride[3];
+  return v;
+}
+template <typename T>
+inline View3<T> scalar3(const sopht_field_t* f) {
+  View3<T> v;
+  v.p = reinterpret_cast<T*>(f->data);
+  v.sz = f->stride[0];
+  v.sy = f->stride[1];
+  v.sx = f->stride[2];
+  return v;
+}
+template <typename T>
+inline View2<T> comp2(const sopht_field_t* f, int c) {
+  View2<T> v;
+  v.p = reinterpret_cast<T*>(f->data) + c * f->stride[0];
+  v.sy = f->stride[1];
+  v.sx = f->stride[2];
+  return v;
+}
+template <typename T>
+inline View2<T> scalar2(const sopht_field_t* f) {
+  View2<T> v;
+  v.p = reinterpret_cast<T*>(f->data);
+  v.sy = f->stride[0];
+  v.sx = f->stride[1];
+  return v;
+}
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// grid for "one thread per cell, x fastest" kernels
+struct Grid3 {
+  dim3 grid, block;
+};
+inline Grid3 cell_grid(int nz, int ny, int nx) {
+  Grid3 g;
+  int bx = nx >= 128 ? 128 : (nx >= 64 ? 64 : 32);
+  int by = 256 / bx;
+  g.block = dim3(bx, by, 1);
+  g.grid = dim3((nx + bx - 1) / bx, (ny + by - 1) / by, nz);
+  return g;
+}
+
+}  // namespace sopht

@@ -1,0 +1,20 @@
+// Internal interface shared by the Poisson solver implementations.
+#pragma once
+#include "common.cuh"
+
+namespace sopht {
+
+struct PoissonImpl {
+  virtual ~PoissonImpl() {}
+  // solution / rhs: scalar (grid dims) or vector (leading component axis) fields of the handle's dtype
+  virtual int solve(const sopht_field_t* sol, const sopht_field_t* rhs, cudaStream_t st) = 0;
+  // device pointer to Re(G_hat)*dx^dim/(doubled cell count) on (n2z, n2y, nx+1), natural order (or null)
+  virtual const void* green_hat() const { return nullptr; }
+  virtual const char* path_name() const { return "generic"; }
+};
+
+PoissonImpl* make_generic_poisson(int dtype, int dim, int nz, int ny, int nx, double dx,
+                                  const double* mz, const double* my, const double* mx,
+                                  double origin, cudaStream_t st, int* rc);
+
+}  // namespace sopht

@@ -1,0 +1,154 @@
+"""Unbounded Poisson solver classes (2-D and 3-D).
+
+Drop-in counterparts of UnboundedPoissonSolverPYFFTW{2,3}D
+(sopht/numeric/eulerian_grid_ops/poisson_solver_3d/UnboundedPoissonSolverPYFFTW3D.py:9-172,
+poisson_solver_2d/UnboundedPoissonSolverPYFFTW2D.py:8-129): same constructor arguments and
+``solve`` / ``vector_field_solve`` keywords. Plans, workspaces and the Green's function spectrum live
+behind an opaque C handle (sopht_poisson_create); fields stay caller-owned torch CUDA tensors (numpy
+arrays are staged through the device).
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Any
+
+import numpy as np
+import torch
+
+from sopht_b200 import _lib
+
+POISSON_AUTO = 0
+POISSON_FORCE_GENERIC = 1
+
+
+def _reflected_axis(axis_range: float, dx: Any, grid_size: int, real_t: type) -> np.ndarray:
+    """min(x, 2X - x) on the doubled axis, with the reference's numpy expressions and dtypes
+    (UnboundedPoissonSolverPYFFTW3D.py:58-75)."""
+    x_double = np.linspace(0, 2 * axis_range - dx, 2 * grid_size).astype(real_t)
+    return np.minimum(x_double, 2 * axis_range - x_double)
+
+
+class _UnboundedPoissonSolverBase:
+    _dim: int
+
+    def _create(self, flags: int) -> None:
+        lib = _lib.load()
+        dt = _lib.dtype_code(self.real_t)
+        real_t = self.real_t
+        mx = _reflected_axis(self.x_range, self.dx, self.grid_size_x, real_t)
+        my = _reflected_axis(self.y_range, self.dx, self.grid_size_y, real_t)
+        if self._dim == 3:
+            mz = _reflected_axis(self.z_range, self.dx, self.grid_size_z, real_t)
+            # Regularization term (straight from PPM), UnboundedPoissonSolverPYFFTW3D.py:79
+            origin = real_t(1 / (4 * np.pi * self.dx))
+            nz = self.grid_size_z
+        else:
+            mz = None
+            # UnboundedPoissonSolverPYFFTW2D.py:64
+            origin = real_t(-(2 * np.log(self.dx / np.sqrt(np.pi)) - 1) / (4 * np.pi))
+            nz = 1
+        if not torch.cuda.is_available():
+            msg = "sopht_b200 Poisson solver needs a CUDA device (no CPU fallback)"
+            raise _lib.SophtLibraryError(msg)
+        handle = ctypes.c_void_p()
+        _lib.check(
+            lib.sopht_poisson_create(
+                ctypes.byref(handle),
+                dt,
+                self._dim,
+                nz,
+                self.grid_size_y,
+                self.grid_size_x,
+                float(self.x_range),
+                float(self.dx),
+                _lib.double_array(mz) if mz is not None else None,
+                _lib.double_array(my),
+                _lib.double_array(mx),
+                float(origin),
+                flags,
+                _lib.current_stream(),
+            )
+        )
+        self._handle = handle
+        self._dt = dt
+        self.path = lib.sopht_poisson_path(handle).decode()
+
+    def __del__(self) -> None:
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                _lib.load().sopht_poisson_destroy(h)
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+            self._handle = None
+
+    def _solve(self, solution: Any, rhs: Any) -> None:
+        with _lib.Staging() as s:
+            r, o = s.inp(rhs), s.out(solution)
+            fo, fr = _lib.field_desc(o, self._dt), _lib.field_desc(r, self._dt)
+            _lib.check(
+                _lib.load().sopht_poisson_solve(
+                    self._handle, ctypes.byref(fo), ctypes.byref(fr), _lib.current_stream()
+                )
+            )
+
+    def solve(self, solution_field: Any, rhs_field: Any) -> None:
+        """Solve -del^2(solution_field) = rhs_field on the unbounded domain (Hockney-Eastwood)."""
+        self._solve(solution_field, rhs_field)
+
+
+class UnboundedPoissonSolverPYFFTW3D(_UnboundedPoissonSolverBase):
+    """3-D unbounded Poisson solver (same ctor as the reference class of this name)."""
+
+    _dim = 3
+
+    def __init__(
+        self,
+        grid_size_z: int,
+        grid_size_y: int,
+        grid_size_x: int,
+        x_range: float = 1.0,
+        num_threads: int = 1,
+        real_t: type = np.float64,
+        flags: int = POISSON_AUTO,
+    ) -> None:
+        self.grid_size_z = grid_size_z
+        self.grid_size_y = grid_size_y
+        self.grid_size_x = grid_size_x
+        self.x_range = x_range
+        self.y_range = x_range * (grid_size_y / grid_size_x)
+        self.z_range = x_range * (grid_size_z / grid_size_x)
+        self.dx = real_t(x_range / grid_size_x)
+        self.num_threads = num_threads
+        self.real_t = real_t
+        self.x_axis_idx, self.y_axis_idx, self.z_axis_idx = 0, 1, 2
+        self._create(flags)
+
+    def vector_field_solve(self, solution_vector_field: Any, rhs_vector_field: Any) -> None:
+        """Three component solves, -del^2(solution_vector_field) = rhs_vector_field."""
+        self._solve(solution_vector_field, rhs_vector_field)
+
+
+class UnboundedPoissonSolverPYFFTW2D(_UnboundedPoissonSolverBase):
+    """2-D unbounded Poisson solver (same ctor as the reference class of this name)."""
+
+    _dim = 2
+
+    def __init__(
+        self,
+        grid_size_y: int,
+        grid_size_x: int,
+        x_range: float = 1.0,
+        num_threads: int = 1,
+        real_t: type = np.float64,
+        flags: int = POISSON_AUTO,
+    ) -> None:
+        self.grid_size_y = grid_size_y
+        self.grid_size_x = grid_size_x
+        self.x_range = x_range
+        self.y_range = x_range * (grid_size_y / grid_size_x)
+        self.dx = real_t(x_range / grid_size_x)
+        self.num_threads = num_threads
+        self.real_t = real_t
+        self._create(flags)

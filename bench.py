@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py — 3D unbounded flow step throughput (Gcell-updates/s) on N B200s, one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Workloads (grid tuples are (nz, ny, nx) like the reference):
+  c2      3D flow past rigid sphere, unbounded Poisson, 128x128x256 fp32, IB forcing (BASELINE configs[1])  [default]
+  u256    3D unbounded flow step 256^3 fp32 (no body)
+  u512    3D unbounded flow step 512^3 fp32 (no body; the north-star single-GPU target size)
+A "step" is one pass of the hot path: [IB gather + forcing + spread] -> vorticity update (rotational
+advection + diffusion + boundary penalisation) -> unbounded FFT Poisson solve -> velocity = curl(psi) + U_inf.
+
+`value`       device-resident fields, fixed dt, no host sync inside the timed region.
+`e2e`         the loop a user of the reference writes (examples/3d_examples/FlowPastSphereCase/
+              flow_past_sphere_case.py:191-197): every step copies that step's host inputs (Lagrangian
+              body positions / velocities, pinned float64) to the device, runs the coupled step through
+              the public simulator API, and reads the step's results (stable dt, Lagrangian forces) back.
+`roofline`    dominant kernel, algorithmic bytes / CUDA-event time (a second K-step region with the
+              library's per-phase event timers switched on), against MEASURED_PEAKS.json.
+`cpu_baseline` the CPU oracle (numpy + scipy.fft restatement of the reference's dataflow) on the
+              box's host cores, bounded sample, rank 0 at N=1 only.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "c2": dict(grid=(128, 128, 256), body="sphere", desc="3D flow past rigid sphere, unbounded Poisson, 128x128x256 fp32"),
+    "u256": dict(grid=(256, 256, 256), body=None, desc="3D unbounded flow step 256^3 fp32"),
+    "u512": dict(grid=(512, 512, 512), body=None, desc="3D unbounded flow step 512^3 fp32"),
+}
+NU = 1e-3
+X_RANGE = 1.0
+U_INF = (1.0, 0.0, 0.0)
+
+
+def algorithmic_bytes_per_cell(with_forcing: bool) -> int:
+    """SURVEY.md §8(d) / BASELINE.md §2: 3D unbounded NS step, fp32."""
+    return 408 if with_forcing else 384
+
+
+def hill_vortex_vorticity(grid, x_range, real_t=np.float32):
+    """Smooth band-limited initial vorticity: Hill's spherical vortex (R = 0.25 x_range, U = 1) centred
+    in the domain (analogue of examples/3d_examples/HillSphericalVortexCase)."""
+    nz, ny, nx = grid
+    dx = x_range / nx
+    z = (np.arange(nz) + 0.5) * dx
+    y = (np.arange(ny) + 0.5) * dx
+    x = (np.arange(nx) + 0.5) * dx
+    zc, yc, xc = z.mean(), y.mean(), x.mean()
+    Z, Y, X = np.meshgrid(z - zc, y - yc, x - xc, indexing="ij")
+    R = 0.25 * min(nz, ny, nx) * dx
+    r2 = X * X + Y * Y + Z * Z
+    inside = r2 <= R * R
+    # omega = (15 U / 2 R^2) * rho * e_phi about the z axis
+    pref = 7.5 / (R * R)
+    w = np.zeros((3, nz, ny, nx), dtype=real_t)
+    w[0] = np.where(inside, -pref * Y, 0.0)
+    w[1] = np.where(inside, pref * X, 0.0)
+    return w
+
+
+def sphere_lag_grid(n_eq=96, diameter=0.2, centre=(0.25, 0.25, 0.25)):
+    """Forcing points on a sphere surface, equal-area latitude rings
+    (rigid_body_forcing_grids.py:236-300 analogue; ~2914 points for n_eq = 96)."""
+    r = diameter / 2
+    n_lat = n_eq // 2
+    pts = []
+    for i in range(n_lat + 1):
+        polar = np.pi * i / n_lat
+        n_ring = max(1, int(round(n_eq * np.sin(polar))))
+        az = 2 * np.pi * (np.arange(n_ring) + 0.5 * (i % 2)) / n_ring
+        pts.append(np.stack([r * np.sin(polar) * np.cos(az) + centre[0],
+                             r * np.sin(polar) * np.sin(az) + centre[1],
+                             np.full(n_ring, r * np.cos(polar)) + centre[2]]))
+    return np.concatenate(pts, axis=1)  # (3, N) float64
+
+
+class ClockSampler:
+    """Samples SM clock and throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.1) -> None:
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self._nv = None
+        self._period = period
+
+    def _run(self) -> None:
+        nv = self._nv
+        names = {
+            nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+            nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+            nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self._period)
+
+    def __enter__(self):
+        if self._nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+
+    def summary(self) -> dict:
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's restatement of the reference step (numpy stencils + scipy.fft + IB loops)
+# ---------------------------------------------------------------------------------------------------------
+def build_cpu_case(wl, cores):
+    from oracle import flow as oflow
+
+    grid = wl["grid"]
+    forcing = wl["body"] is not None
+    sim = oflow.UnboundedNavierStokesFlowSimulator3D(
+        grid_size=grid, x_range=X_RANGE, kinematic_viscosity=NU, real_t=np.float32,
+        with_forcing=forcing, with_free_stream_flow=True, workers=cores)
+    sim.vorticity_field[...] = hill_vortex_vorticity(grid, X_RANGE)
+    sim._poisson.vector_field_solve(sim.stream_func_field, sim.vorticity_field)
+    from oracle import stencils as ost
+
+    ost.curl_3d(sim.velocity_field, sim.stream_func_field, np.float32(0.5 / sim.dx))
+    vb = None
+    if forcing:
+        from oracle import ib as oib
+
+        pos = sphere_lag_grid()
+        ds = np.pi * 0.2 / 96  # ~ lagrangian spacing
+        vb = (oib.VirtualBoundaryForcing(-1.5e5 * ds * ds, -87.5 * ds * ds, 3, sim.dx, pos.shape[1], np.float32),
+              pos, np.zeros_like(pos))
+    return sim, vb
+
+
+def cpu_step(sim, vb, dt):
+    if vb is not None:
+        f, pos, vel = vb
+        f.time_step(dt)
+        f.compute_interaction_force_on_eul_and_lag_grid(
+            sim.eul_grid_forcing_field, sim.velocity_field, pos, vel)
+    sim.time_step(dt, free_stream_velocity=U_INF)
+
+
+def time_cpu(wl, steps, warmup):
+    cores = len(os.sched_getaffinity(0))
+    sim, vb = build_cpu_case(wl, cores)
+    dt = float(0.1 * sim.dx)
+    for _ in range(warmup):
+        cpu_step(sim, vb, dt)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_step(sim, vb, dt)
+    el = time.perf_counter() - t0
+    cells = int(np.prod(wl["grid"]))
+    return cells * steps / el / 1e9, el / steps * 1e3, cores
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 8))
+    warm = 1 if args.warmup > 0 else 0
+    # bound the sample: big grids run fewer steps
+    cells = int(np.prod(wl["grid"]))
+    if cells > 2**24:
+        steps = min(steps, 2)
+    val, ms, cores = time_cpu(wl, steps, warm)
+    sample = f"{steps} full steps of {wl['desc']} (numpy/scipy.fft oracle, scipy workers={cores})"
+    line = {
+        "impl": "reference", "metric": "3D flow step Gcell-updates/s", "value": val, "unit": "Gcell/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["desc"], "grid": list(wl["grid"]), "timing": "host perf_counter (CPU arm)"},
+        "cpu_baseline": {"value": val, "unit": "Gcell/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "Gcell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+
+    from sopht_b200 import _lib
+    from sopht_b200.simulator import UnboundedNavierStokesFlowSimulator3D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.load()
+
+    grid = wl["grid"]
+    forcing = wl["body"] is not None
+    sim = UnboundedNavierStokesFlowSimulator3D(
+        grid_size=grid, x_range=X_RANGE, kinematic_viscosity=NU, real_t=np.float32,
+        with_forcing=forcing, with_free_stream_flow=True, step_mode=args.step_mode)
+    sim.vorticity_field[...] = torch.from_numpy(hill_vortex_vorticity(grid, X_RANGE)).cuda()
+    sim._unbounded_poisson_solver.vector_field_solve(
+        solution_vector_field=sim.stream_func_field, rhs_vector_field=sim.vorticity_field)
+    sim._curl(curl=sim.velocity_field, field=sim.stream_func_field, prefactor=np.float32(0.5 / sim.dx))
+    dt = float(0.1 * sim.dx)
+    cells = int(np.prod(grid))
+
+    interactor = None
+    if forcing:
+        from sopht_b200.numeric.immersed_boundary_ops import VirtualBoundaryForcing
+
+        pos_h = torch.from_numpy(sphere_lag_grid()).pin_memory()
+        vel_h = torch.zeros_like(pos_h).pin_memory()
+        ds = np.pi * 0.2 / 96
+        interactor = VirtualBoundaryForcing(
+            virtual_boundary_stiffness_coeff=-1.5e5 * ds * ds, virtual_boundary_damping_coeff=-87.5 * ds * ds,
+            grid_dim=3, dx=sim.dx, num_lag_nodes=pos_h.shape[1], real_t=np.float32)
+        pos_d, vel_d = pos_h.cuda(), vel_h.cuda()
+        force_h = torch.zeros(3, pos_h.shape[1], dtype=torch.float32).pin_memory()
+
+    def device_step():
+        if interactor is not None:
+            interactor.time_step(dt)
+            interactor.compute_interaction_force_on_eul_and_lag_grid(
+                sim.eul_grid_forcing_field, sim.velocity_field, pos_d, vel_d)
+        sim.time_step(dt=dt, free_stream_velocity=U_INF)
+
+    h2d = d2h = 0
+
+    def e2e_step():
+        nonlocal h2d, d2h
+        step_dt = sim.compute_stable_timestep(dt_prefac=0.5)  # device reduction + D2H scalar
+        d2h_n = 4
+        h2d_n = 0
+        if interactor is not None:
+            p = pos_h.to("cuda", non_blocking=True)
+            v = vel_h.to("cuda", non_blocking=True)
+            h2d_n += pos_h.numel() * 8 + vel_h.numel() * 8
+            interactor.time_step(step_dt)
+            interactor.compute_interaction_force_on_eul_and_lag_grid(
+                sim.eul_grid_forcing_field, sim.velocity_field, p, v)
+            force_h.copy_(interactor.lag_grid_forcing_field, non_blocking=True)
+            d2h_n += force_h.numel() * 4
+        sim.time_step(dt=step_dt, free_stream_velocity=U_INF)
+        h2d, d2h = h2d_n, d2h_n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    n0 = _lib.launch_count()
+    with ClockSampler(local) as clk:
+        ms = timed(device_step, args.steps)
+    launches = _lib.launch_count() - n0
+    value = cells * world * args.steps / (ms * 1e-3) / 1e9
+
+    # end-to-end through the public API with host-side per-step inputs/outputs
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_val = cells * world * args.steps / (ms_e2e * 1e-3) / 1e9
+
+    # roofline of the dominant kernel: per-phase CUDA-event timers inside the library
+    peak, peak_src = measured_peak_hbm()
+    roof = None
+    if hasattr(_lib, "phase_timing"):
+        roof = _lib.phase_timing(device_step, args.steps, cells, peak, peak_src)
+    if roof is None:
+        bpc = algorithmic_bytes_per_cell(forcing)
+        ach = bpc * cells * args.steps / (ms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "kernel": "whole step (no per-phase timers in this build)",
+                "algorithmic_bytes_per_cell": bpc, "peak_source": peak_src}
+
+    if rank != 0:
+        return
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        csteps = 8 if cells <= 2**23 else 2
+        cval, cms, cores = time_cpu(wl, csteps, 1)
+        cpu = {"value": cval, "unit": "Gcell/s", "cores": cores, "kind": "port",
+               "sample": f"{csteps} full steps of the same workload, numpy/scipy.fft oracle, {cms:.0f} ms/step"}
+    line = {
+        "metric": "3D flow step Gcell-updates/s", "value": value, "unit": "Gcell/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": wl["desc"], "grid": list(grid), "cells_per_gpu": cells,
+                   "lagrangian_nodes": int(pos_h.shape[1]) if forcing else 0,
+                   "step_mode": sim.step_mode, "poisson_path": sim._unbounded_poisson_solver.path,
+                   "l2": "working set per step exceeds L2 (fields + FFT workspace > 126 MB)"
+                   if cells * 4 * 15 > 126e6 else "L2 flushed between steps"},
+        "e2e": {"value": e2e_val, "unit": "Gcell/s", "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": roof,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--step-mode", default="auto", choices=["auto", "fused", "unfused"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        run_ours(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -279,6 +279,57 @@ const char *sopht_poisson_path(sopht_poisson_t handle);
 
 int sopht_poisson_destroy(sopht_poisson_t handle);
 
+/* ------------------------------------------------------------------------ */
+/* Immersed boundary: Eulerian <-> Lagrangian transfer, 4-point delta kernels */
+/* Lagrangian arrays are (dim, N) with N contiguous; nearest_index is int64;  */
+/* lag_positions / body velocities are of pos_dtype (SOPHT_F32 / SOPHT_F64),  */
+/* all other arrays of `dtype`. dim = 2 or 3.                                 */
+/* ------------------------------------------------------------------------ */
+
+/* nearest_index = floor((X - shift)/dx); local_support[d, taps, i] = (idx_d + off_d) dx + shift - X_d
+ * ref: immersed_boundary_ops/EulerianLagrangianGridCommunicator3D.py:69-135, ...2D.py:70-134 */
+int sopht_ib_local_support(int dtype, int dim, const sopht_field_t *local_support,
+                           const sopht_field_t *nearest_index, const sopht_field_t *lag_positions,
+                           int pos_dtype, double dx, double eul_grid_coord_shift, void *stream);
+
+/* kernel_type 0: cosine (3D.py:387-412), 1: Peskin 2002 (3D.py:415-518). Mutates local_support as the
+ * reference does (/= dx, or |.|/dx). prefactor = (0.25/dx)^dim or (0.125/dx)^dim, evaluated by the caller. */
+int sopht_ib_interpolation_weights(int dtype, int dim, int kernel_type,
+                                   const sopht_field_t *interp_weights,
+                                   const sopht_field_t *local_support, double dx, double prefactor,
+                                   void *stream);
+
+/* lag[c, i] = dx^dim * sum_taps eul[c, taps(i)] * w[taps, i]; scalar (N,) or vector (dim, N)
+ * ref: EulerianLagrangianGridCommunicator3D.py:180-295, ...2D.py */
+int sopht_ib_eulerian_to_lagrangian(int dtype, int dim, const sopht_field_t *lag_grid_field,
+                                    const sopht_field_t *eul_grid_field,
+                                    const sopht_field_t *interp_weights,
+                                    const sopht_field_t *nearest_index, double dx_pow_dim, void *stream);
+
+/* eul[c, taps(i)] += lag[c, i] * w[taps, i] (accumulates; caller zeroes)
+ * ref: EulerianLagrangianGridCommunicator3D.py:298-380, ...2D.py */
+int sopht_ib_lagrangian_to_eulerian(int dtype, int dim, const sopht_field_t *eul_grid_field,
+                                    const sopht_field_t *lag_grid_field,
+                                    const sopht_field_t *interp_weights,
+                                    const sopht_field_t *nearest_index, void *stream);
+
+/* One launch for the whole virtual-boundary interaction (cosine kernel): support, weights, velocity
+ * gather, dv = U - V_body, F = k dX + c dv, spread of F (eul_grid_forcing_field may be NULL: Lagrangian
+ * part only). ref: immersed_boundary_ops/VirtualBoundaryForcing.py:187-253 */
+int sopht_ib_virtual_boundary_forcing(int dtype, int dim, const sopht_field_t *eul_grid_forcing_field,
+                                      const sopht_field_t *eul_grid_velocity_field,
+                                      const sopht_field_t *lag_positions,
+                                      const sopht_field_t *lag_body_velocity, int pos_dtype,
+                                      const sopht_field_t *local_support,
+                                      const sopht_field_t *interp_weights,
+                                      const sopht_field_t *nearest_index,
+                                      const sopht_field_t *lag_flow_velocity,
+                                      const sopht_field_t *lag_velocity_mismatch,
+                                      const sopht_field_t *lag_position_mismatch,
+                                      const sopht_field_t *lag_forcing, double dx,
+                                      double eul_grid_coord_shift, double weight_prefactor,
+                                      double dx_pow_dim, double stiffness, double damping, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

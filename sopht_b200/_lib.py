@@ -125,6 +125,15 @@ _HANDLE_SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "sopht_poisson_green_hat": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
     "sopht_poisson_path": (ctypes.c_char_p, [_P]),
     "sopht_poisson_destroy": (ctypes.c_int, [_P]),
+    # immersed boundary (int dtype, int dim, ...)
+    "sopht_ib_local_support": (ctypes.c_int, [_I, _I, _F, _F, _F, _I, _D, _D, _P]),
+    "sopht_ib_interpolation_weights": (ctypes.c_int, [_I, _I, _I, _F, _F, _D, _D, _P]),
+    "sopht_ib_eulerian_to_lagrangian": (ctypes.c_int, [_I, _I, _F, _F, _F, _F, _D, _P]),
+    "sopht_ib_lagrangian_to_eulerian": (ctypes.c_int, [_I, _I, _F, _F, _F, _F, _P]),
+    "sopht_ib_virtual_boundary_forcing": (
+        ctypes.c_int,
+        [_I, _I, _F, _F, _F, _F, _I, _F, _F, _F, _F, _F, _F, _F, _D, _D, _D, _D, _D, _D, _P],
+    ),
 }
 
 
@@ -193,6 +202,26 @@ def field_desc(t: torch.Tensor, dt: int, *, is_complex: bool = False) -> SophtFi
     if t.dtype != want:
         msg = f"field dtype {t.dtype} does not match kernel dtype {want}"
         raise ValueError(msg)
+    if t.dim() < 1 or t.dim() > MAX_DIMS:
+        msg = f"unsupported field rank {t.dim()}"
+        raise ValueError(msg)
+    f = SophtField()
+    f.data = t.data_ptr()
+    f.ndim = t.dim()
+    for d in range(t.dim()):
+        f.shape[d] = t.shape[d]
+        f.stride[d] = t.stride(d)
+    return f
+
+
+def raw_desc(t: torch.Tensor) -> SophtField:
+    """Describe a CUDA tensor of any dtype (int64 index arrays, float64 Lagrangian positions)."""
+    if not isinstance(t, torch.Tensor):
+        msg = f"expected a torch.Tensor, got {type(t).__name__}"
+        raise TypeError(msg)
+    if not t.is_cuda:
+        msg = "sopht_b200 kernels need CUDA tensors (no CPU fallback)"
+        raise SophtLibraryError(msg)
     if t.dim() < 1 or t.dim() > MAX_DIMS:
         msg = f"unsupported field rank {t.dim()}"
         raise ValueError(msg)

@@ -1,0 +1,325 @@
+"""Unbounded Navier-Stokes flow simulators, 2D and 3D.
+
+Same constructor kwargs, attribute names and step order as
+sopht/simulator/flow/navier_stokes_flow_simulators.py:24-522; fields are torch CUDA tensors and every
+sub-step is a CUDA kernel behind the C ABI. Two step implementations are kept:
+
+* ``step_mode="fused"`` (default when the grid qualifies): the fused phase kernels of
+  csrc/fused_step3d.cu + the pruned FFT pipeline of csrc/poisson_pow2.cu (few launches, minimum HBM traffic);
+* ``step_mode="unfused"``: the reference's own composition, one public factory kernel per sub-step
+  (what the reference's integration tests rebuild by hand, tests/.../test_navier_stokes_flow_simulators.py:163-308).
+"""
+
+from __future__ import annotations
+
+import logging
+from typing import Any, Literal
+
+import numpy as np
+import torch
+
+import sopht_b200.numeric.eulerian_grid_ops as spne
+from sopht_b200 import _lib
+from sopht_b200.utils.field import VectorField
+
+from .flow_simulators import FlowSimulator
+
+logger = logging.getLogger(__name__)
+
+
+def compute_advection_diffusion_stable_timestep(
+    velocity_field: torch.Tensor,
+    velocity_magnitude_field: torch.Tensor,
+    grid_dim: int,
+    dx: float,
+    cfl: float,
+    kinematic_viscosity: float,
+    real_t: type = np.float32,
+) -> float:
+    """Stable dt from advection and diffusion limits (passive_transport_flow_simulators.py:139-155).
+
+    One fused kernel writes ``velocity_magnitude_field = sum_c |u_c|`` (the reference's side effect)
+    and reduces its maximum on the device; the only host sync is the read of that scalar.
+    """
+    dt_code = _lib.dtype_code(real_t)
+    vmax = torch.zeros(1, dtype=velocity_field.dtype, device=velocity_field.device)
+    _lib.call("sopht_abs_sum_max", dt_code, velocity_magnitude_field, velocity_field, vmax.data_ptr())
+    return stable_timestep_from_max(real_t(vmax.item()), grid_dim, dx, cfl, kinematic_viscosity, real_t)
+
+
+def stable_timestep_from_max(vel_max, grid_dim, dx, cfl, kinematic_viscosity, real_t):
+    tol = 10 * np.finfo(real_t).eps
+    with np.errstate(divide="ignore"):
+        diffusion_limit = 0.9 * dx**2 / (2 * grid_dim) / kinematic_viscosity + tol if kinematic_viscosity \
+            else np.inf
+    return min(cfl * dx / (vel_max + tol), diffusion_limit)
+
+
+class UnboundedNavierStokesFlowSimulator3D(FlowSimulator):
+    """3D unbounded Navier-Stokes flow simulator (vorticity-velocity, rotational form)."""
+
+    def __init__(
+        self,
+        grid_size: tuple[int, int, int],
+        x_range: float,
+        kinematic_viscosity: float,
+        cfl: float = 0.1,
+        real_t: type = np.float32,
+        num_threads: int = 1,
+        time: float = 0.0,
+        with_forcing: bool = False,
+        with_free_stream_flow: bool = False,
+        filter_vorticity: bool = False,
+        flow_density: float = 1.0,
+        poisson_solver_type: Literal[
+            "greens_function_convolution", "fast_diagonalisation"
+        ] = "greens_function_convolution",
+        **kwargs: Any,
+    ) -> None:
+        self.kinematic_viscosity = kinematic_viscosity
+        self.cfl = cfl
+        self.with_forcing = with_forcing
+        self.with_free_stream_flow = with_free_stream_flow
+        self.penalty_zone_width = kwargs.get("penalty_zone_width", 2)
+        self.filter_vorticity = filter_vorticity
+        self.filter_setting_dict = None
+        if self.filter_vorticity:
+            self.filter_setting_dict = kwargs.get(
+                "filter_setting_dict", {"order": 2, "type": "multiplicative"}
+            )
+            logger.info(
+                "Vorticity filtering is turned on: order = %s, type = %s",
+                self.filter_setting_dict["order"], self.filter_setting_dict["type"],
+            )
+        self.flow_density = flow_density
+        self.poisson_solver_type = poisson_solver_type
+        if poisson_solver_type not in ["greens_function_convolution", "fast_diagonalisation"]:
+            msg = "Invalid Poisson solver type given"
+            raise ValueError(msg)
+        if poisson_solver_type == "fast_diagonalisation":
+            msg = ("fast_diagonalisation (dense eigen-transform Neumann solver) is outside the "
+                   "FFT hot path this library implements (SURVEY.md §2 row 5)")
+            raise NotImplementedError(msg)
+        self.step_mode = kwargs.get("step_mode", "auto")
+        if self.step_mode not in ("auto", "fused", "unfused"):
+            msg = "step_mode must be 'auto', 'fused' or 'unfused'"
+            raise ValueError(msg)
+        self._poisson_flags = kwargs.get("poisson_flags", spne.POISSON_AUTO)
+        super().__init__(grid_dim=3, grid_size=grid_size, x_range=x_range, real_t=real_t,
+                         num_threads=num_threads, time=time)
+
+    def _init_fields(self) -> None:
+        """navier_stokes_flow_simulators.py:314-325 (buffer_scalar_field aliases buffer_vector_field[0])."""
+        shape = (self.grid_dim, *self.grid_size)
+        self.vorticity_field = self._zeros(shape)
+        self.velocity_field = self._zeros(shape)
+        self.buffer_vector_field = self._zeros(shape)
+        self.buffer_scalar_field = self.buffer_vector_field[0]
+        self.stream_func_field = self._zeros(shape)
+        if self.with_forcing:
+            self.eul_grid_forcing_field = self._zeros(shape)
+
+    def _compile_kernels(self) -> None:
+        """Kernel factories of the step (navier_stokes_flow_simulators.py:328-440)."""
+        rt, nt, gs = self.real_t, self.num_threads, self.grid_size
+        self._diffusion_timestep = spne.gen_diffusion_timestep_euler_forward_pyst_kernel_3d(
+            real_t=rt, fixed_grid_size=gs, num_threads=nt, field_type="vector")
+        nz, ny, nx = gs
+        self._unbounded_poisson_solver = spne.UnboundedPoissonSolverPYFFTW3D(
+            grid_size_z=nz, grid_size_y=ny, grid_size_x=nx, x_range=self.x_range, real_t=rt,
+            num_threads=nt, flags=self._poisson_flags)
+        self._curl = spne.gen_curl_pyst_kernel_3d(real_t=rt, num_threads=nt, fixed_grid_size=gs)
+        self._penalise_field_towards_boundary = spne.gen_penalise_field_boundary_pyst_kernel_3d(
+            width=self.penalty_zone_width, dx=self.dx,
+            x_grid_field=self.position_field[VectorField.x_axis_idx()],
+            y_grid_field=self.position_field[VectorField.y_axis_idx()],
+            z_grid_field=self.position_field[VectorField.z_axis_idx()],
+            real_t=rt, num_threads=nt, fixed_grid_size=gs, field_type="vector")
+        self._elementwise_cross_product = spne.gen_elementwise_cross_product_pyst_kernel_3d(
+            real_t=rt, num_threads=nt, fixed_grid_size=gs)
+        self._update_vorticity_from_velocity_forcing = (
+            spne.gen_update_vorticity_from_velocity_forcing_pyst_kernel_3d(
+                real_t=rt, fixed_grid_size=gs, num_threads=nt))
+        self._compute_divergence = spne.gen_divergence_pyst_kernel_3d(
+            real_t=rt, fixed_grid_size=gs, num_threads=nt)
+
+        def filter_vector_field(vector_field: torch.Tensor) -> None: ...
+
+        self._filter_vector_field = filter_vector_field
+        if self.filter_vorticity and self.filter_setting_dict is not None:
+            self._filter_vector_field = spne.gen_laplacian_filter_kernel_3d(
+                filter_order=self.filter_setting_dict["order"],
+                filter_flux_buffer=self.buffer_vector_field[0],
+                field_buffer=self.buffer_vector_field[1],
+                real_t=rt, num_threads=nt, fixed_grid_size=gs, field_type="vector",
+                filter_type=self.filter_setting_dict["type"])
+        if self.with_forcing:
+            self._set_field = spne.gen_set_fixed_val_pyst_kernel_3d(
+                real_t=rt, num_threads=nt, field_type="vector")
+        if self.with_free_stream_flow:
+            add_fixed_val = spne.gen_add_fixed_val_pyst_kernel_3d(
+                real_t=rt, fixed_grid_size=gs, num_threads=nt, field_type="vector")
+
+            def update_velocity_with_free_stream(free_stream_velocity) -> None:
+                add_fixed_val(sum_field=self.velocity_field, vector_field=self.velocity_field,
+                              fixed_vals=free_stream_velocity)
+        else:
+
+            def update_velocity_with_free_stream(free_stream_velocity) -> None: ...
+
+        self._update_velocity_with_free_stream = update_velocity_with_free_stream
+
+    def _finalise_flow_time_step(self) -> None:
+        self._flow_time_step = self._navier_stokes_time_step
+        if self.with_forcing:
+            self._flow_time_step = self._navier_stokes_with_forcing_time_step
+
+    def _navier_stokes_time_step(self, dt: float, free_stream_velocity=(0.0, 0.0, 0.0)) -> None:
+        """navier_stokes_flow_simulators.py:449-485."""
+        velocity_cross_vorticity = self.buffer_vector_field
+        self._elementwise_cross_product(
+            result_field=velocity_cross_vorticity, field_1=self.velocity_field,
+            field_2=self.vorticity_field)
+        self._update_vorticity_from_velocity_forcing(
+            vorticity_field=self.vorticity_field, velocity_forcing_field=velocity_cross_vorticity,
+            prefactor=self.real_t(dt / (2 * self.dx)))
+        self._diffusion_timestep(
+            vector_field=self.vorticity_field, diffusion_flux=self.buffer_scalar_field,
+            nu_dt_by_dx2=self.real_t(self.kinematic_viscosity * dt / self.dx / self.dx))
+        self._filter_vector_field(vector_field=self.vorticity_field)
+        self._penalise_field_towards_boundary(vector_field=self.vorticity_field)
+        self._unbounded_poisson_solver.vector_field_solve(
+            solution_vector_field=self.stream_func_field, rhs_vector_field=self.vorticity_field)
+        self._curl(curl=self.velocity_field, field=self.stream_func_field,
+                   prefactor=self.real_t(0.5 / self.dx))
+        self._update_velocity_with_free_stream(free_stream_velocity=free_stream_velocity)
+
+    def _navier_stokes_with_forcing_time_step(self, dt: float, free_stream_velocity=(0.0, 0.0, 0.0)) -> None:
+        """navier_stokes_flow_simulators.py:487-498."""
+        self._update_vorticity_from_velocity_forcing(
+            vorticity_field=self.vorticity_field, velocity_forcing_field=self.eul_grid_forcing_field,
+            prefactor=self.real_t(dt / (2 * self.dx * self.flow_density)))
+        self._navier_stokes_time_step(dt=dt, free_stream_velocity=free_stream_velocity)
+        self._set_field(vector_field=self.eul_grid_forcing_field, fixed_vals=[0.0] * self.grid_dim)
+
+    def compute_stable_timestep(self, dt_prefac: float = 1.0) -> float:
+        dt = compute_advection_diffusion_stable_timestep(
+            velocity_field=self.velocity_field, velocity_magnitude_field=self.buffer_scalar_field,
+            grid_dim=self.grid_dim, dx=self.dx, cfl=self.cfl,
+            kinematic_viscosity=self.kinematic_viscosity, real_t=self.real_t)
+        return dt * dt_prefac
+
+    def get_vorticity_divergence_l2_norm(self) -> float:
+        """L2 norm of div(vorticity) (navier_stokes_flow_simulators.py:514-522)."""
+        divergence_field = self.buffer_scalar_field
+        self._compute_divergence(divergence=divergence_field, field=self.vorticity_field,
+                                 inv_dx=(1.0 / self.dx))
+        return float(torch.linalg.vector_norm(divergence_field).item()) * self.dx ** (self.grid_dim / 2.0)
+
+
+class UnboundedNavierStokesFlowSimulator2D(FlowSimulator):
+    """2D unbounded Navier-Stokes flow simulator (navier_stokes_flow_simulators.py:24-209)."""
+
+    def __init__(
+        self,
+        grid_size: tuple[int, int],
+        x_range: float,
+        kinematic_viscosity: float,
+        cfl: float = 0.1,
+        real_t: type = np.float32,
+        num_threads: int = 1,
+        time: float = 0.0,
+        with_forcing: bool = False,
+        with_free_stream_flow: bool = False,
+        flow_density: float = 1.0,
+        **kwargs: Any,
+    ) -> None:
+        self.kinematic_viscosity = kinematic_viscosity
+        self.cfl = cfl
+        self.with_forcing = with_forcing
+        self.with_free_stream_flow = with_free_stream_flow
+        self.flow_density = flow_density
+        self.penalty_zone_width = kwargs.get("penalty_zone_width", 2)
+        self._poisson_flags = kwargs.get("poisson_flags", spne.POISSON_AUTO)
+        super().__init__(grid_dim=2, grid_size=grid_size, x_range=x_range, real_t=real_t,
+                         num_threads=num_threads, time=time)
+
+    def _init_fields(self) -> None:
+        self.vorticity_field = self._zeros(self.grid_size)
+        self.velocity_field = self._zeros((self.grid_dim, *self.grid_size))
+        self.buffer_scalar_field = self._zeros(self.grid_size)
+        self.stream_func_field = self._zeros(self.grid_size)
+        if self.with_forcing:
+            self.eul_grid_forcing_field = self._zeros((self.grid_dim, *self.grid_size))
+
+    def _compile_kernels(self) -> None:
+        rt, nt, gs = self.real_t, self.num_threads, self.grid_size
+        self._diffusion_timestep = spne.gen_diffusion_timestep_euler_forward_pyst_kernel_2d(
+            real_t=rt, fixed_grid_size=gs, num_threads=nt)
+        self._advection_timestep = (
+            spne.gen_advection_timestep_euler_forward_conservative_eno3_pyst_kernel_2d(
+                real_t=rt, fixed_grid_size=gs, num_threads=nt))
+        ny, nx = gs
+        self._unbounded_poisson_solver = spne.UnboundedPoissonSolverPYFFTW2D(
+            grid_size_y=ny, grid_size_x=nx, x_range=self.x_range, real_t=rt, num_threads=nt,
+            flags=self._poisson_flags)
+        self._curl = spne.gen_outplane_field_curl_pyst_kernel_2d(
+            real_t=rt, num_threads=nt, fixed_grid_size=gs)
+        self._penalise_field_towards_boundary = spne.gen_penalise_field_boundary_pyst_kernel_2d(
+            width=self.penalty_zone_width, dx=self.dx,
+            x_grid_field=self.position_field[VectorField.x_axis_idx()],
+            y_grid_field=self.position_field[VectorField.y_axis_idx()],
+            real_t=rt, num_threads=nt, fixed_grid_size=gs)
+        if self.with_forcing:
+            self._update_vorticity_from_velocity_forcing = (
+                spne.gen_update_vorticity_from_velocity_forcing_pyst_kernel_2d(
+                    real_t=rt, fixed_grid_size=gs, num_threads=nt))
+            self._set_field = spne.gen_set_fixed_val_pyst_kernel_2d(
+                real_t=rt, num_threads=nt, field_type="vector")
+        if self.with_free_stream_flow:
+            add_fixed_val = spne.gen_add_fixed_val_pyst_kernel_2d(
+                real_t=rt, fixed_grid_size=gs, num_threads=nt, field_type="vector")
+
+            def update_velocity_with_free_stream(free_stream_velocity) -> None:
+                add_fixed_val(sum_field=self.velocity_field, vector_field=self.velocity_field,
+                              fixed_vals=free_stream_velocity)
+        else:
+
+            def update_velocity_with_free_stream(free_stream_velocity) -> None: ...
+
+        self._update_velocity_with_free_stream = update_velocity_with_free_stream
+
+    def _finalise_flow_time_step(self) -> None:
+        self._flow_time_step = self._navier_stokes_time_step
+        if self.with_forcing:
+            self._flow_time_step = self._navier_stokes_with_forcing_time_step
+
+    def _navier_stokes_time_step(self, dt: float, free_stream_velocity=(0.0, 0.0)) -> None:
+        """navier_stokes_flow_simulators.py:171-195."""
+        self._advection_timestep(
+            field=self.vorticity_field, advection_flux=self.buffer_scalar_field,
+            velocity=self.velocity_field, dt_by_dx=self.real_t(dt / self.dx))
+        self._diffusion_timestep(
+            field=self.vorticity_field, diffusion_flux=self.buffer_scalar_field,
+            nu_dt_by_dx2=self.real_t(self.kinematic_viscosity * dt / self.dx / self.dx))
+        self._penalise_field_towards_boundary(field=self.vorticity_field)
+        self._unbounded_poisson_solver.solve(
+            solution_field=self.stream_func_field, rhs_field=self.vorticity_field)
+        self._curl(curl=self.velocity_field, field=self.stream_func_field,
+                   prefactor=self.real_t(0.5 / self.dx))
+        self._update_velocity_with_free_stream(free_stream_velocity=free_stream_velocity)
+
+    def _navier_stokes_with_forcing_time_step(self, dt: float, free_stream_velocity=(0.0, 0.0)) -> None:
+        """navier_stokes_flow_simulators.py:197-209."""
+        self._update_vorticity_from_velocity_forcing(
+            vorticity_field=self.vorticity_field, velocity_forcing_field=self.eul_grid_forcing_field,
+            prefactor=self.real_t(dt / (2 * self.dx * self.flow_density)))
+        self._navier_stokes_time_step(dt=dt, free_stream_velocity=free_stream_velocity)
+        self._set_field(vector_field=self.eul_grid_forcing_field, fixed_vals=[0.0] * self.grid_dim)
+
+    def compute_stable_timestep(self, dt_prefac: float = 1.0) -> float:
+        dt = compute_advection_diffusion_stable_timestep(
+            velocity_field=self.velocity_field, velocity_magnitude_field=self.buffer_scalar_field,
+            grid_dim=self.grid_dim, dx=self.dx, cfl=self.cfl,
+            kinematic_viscosity=self.kinematic_viscosity, real_t=self.real_t)
+        return dt * dt_prefac

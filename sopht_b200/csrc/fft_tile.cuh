@@ -1,0 +1,328 @@
+// CTA-level power-of-two complex FFT building blocks for the pruned Poisson pipeline (poisson_pow2.cu).
+//
+// A sequence of length L = R1*R2*R3 lives in shared memory (one "column" per sequence); T = L/E threads
+// per column each own E elements per pass. Forward transforms are decimation-in-frequency, inverse
+// transforms decimation-in-time with the mirrored pass order, so the spectrum a forward last pass leaves in
+// REGISTERS is exactly the input of the inverse first pass (used by the fused z-pass: forward -> x G_hat ->
+// inverse with no reordering and only two shared-memory exchanges for L <= 1024).
+//
+// Position/ordering conventions (all passes are in place):
+//   pass p works on blocks of length Sprev_p (Sprev_0 = L, Sprev_1 = L/R1, Sprev_2 = L/(R1 R2)); inside a
+//   block, butterfly j (0 <= j < S = Sprev/R) touches positions blk*Sprev + n*S + j, n = 0..R-1.
+//   After the forward last pass, position blk*Rlast + klast holds X[rev(blk) + (L/Rlast)*klast], where rev()
+//   reverses the (k1[,k2]) digits of blk:  two passes: rev = blk;  three passes: blk = k1*R2 + k2 -> k1 + R1*k2.
+//
+// Everything is __host__ __device__ so that the exact index arithmetic is unit-tested on the CPU
+// (tests/host/fft_emul.cu emulates the thread/phase structure) before it runs on the GPU.
+#pragma once
+#include <cuda_runtime.h>
+
+#ifdef __CUDACC__
+#define FFT_HD __host__ __device__ __forceinline__
+#else
+#define FFT_HD inline
+#endif
+
+namespace sopht {
+namespace fft {
+
+FFT_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+FFT_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+FFT_HD float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+FFT_HD float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
+  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+FFT_HD float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+
+// w32(j) = exp(-2 pi i j / 32); j is a compile-time constant after unrolling.
+FFT_HD float2 w32(int j) {
+  constexpr float c[32] = {
+      1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654757f,
+      0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f, 0.f, -0.19509032201612819f,
+      -0.38268343236508973f, -0.55557023301960196f, -0.70710678118654746f, -0.83146961230254535f,
+      -0.92387953251128674f, -0.98078528040323043f, -1.f, -0.98078528040323043f, -0.92387953251128685f,
+      -0.83146961230254546f, -0.70710678118654768f, -0.55557023301960218f, -0.38268343236509034f,
+      -0.19509032201612866f, 0.f, 0.1950903220161283f, 0.38268343236509f, 0.55557023301960184f,
+      0.70710678118654735f, 0.83146961230254524f, 0.92387953251128652f, 0.98078528040323032f};
+  constexpr float s[32] = {
+      0.f, -0.19509032201612825f, -0.38268343236508978f, -0.55557023301960218f, -0.70710678118654746f,
+      -0.83146961230254524f, -0.92387953251128674f, -0.98078528040323043f, -1.f, -0.98078528040323043f,
+      -0.92387953251128674f, -0.83146961230254546f, -0.70710678118654757f, -0.55557023301960218f,
+      -0.38268343236508989f, -0.19509032201612861f, 0.f, 0.19509032201612836f, 0.38268343236508967f,
+      0.55557023301960196f, 0.70710678118654746f, 0.83146961230254524f, 0.92387953251128652f,
+      0.98078528040323032f, 1.f, 0.98078528040323043f, 0.92387953251128663f, 0.83146961230254546f,
+      0.70710678118654768f, 0.55557023301960218f, 0.38268343236509039f, 0.19509032201612872f};
+  return make_float2(c[j & 31], s[j & 31]);
+}
+
+// a * exp(-2 pi i j / 32) with the trivial rotations done without multiplies
+FFT_HD float2 rot32(float2 a, int j) {
+  j &= 31;
+  if (j == 0) return a;
+  if (j == 8) return make_float2(a.y, -a.x);
+  if (j == 16) return make_float2(-a.x, -a.y);
+  if (j == 24) return make_float2(-a.y, a.x);
+  return cmul(a, w32(j));
+}
+
+// ---- in-register DFTs, natural order in and out: v[k] <- sum_n v[n] exp(-2 pi i n k / R) ----------------
+template <int R>
+struct Dft;
+
+template <>
+struct Dft<1> {
+  FFT_HD static void run(float2*) {}
+};
+template <>
+struct Dft<2> {
+  FFT_HD static void run(float2* v) {
+    const float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  }
+};
+template <>
+struct Dft<4> {
+  FFT_HD static void run(float2* v) {
+    const float2 a = cadd(v[0], v[2]), b = csub(v[0], v[2]);
+    const float2 c = cadd(v[1], v[3]), d = mul_mi(csub(v[1], v[3]));
+    v[0] = cadd(a, c);
+    v[1] = cadd(b, d);
+    v[2] = csub(a, c);
+    v[3] = csub(b, d);
+  }
+};
+
+// R = RA*RB: n = RB*a + b, k = ka + RA*kb
+template <int RA, int RB>
+FFT_HD void dft_composite(float2* v) {
+  constexpr int R = RA * RB;
+  float2 u[RB][RA];
+#pragma unroll
+  for (int b = 0; b < RB; ++b) {
+#pragma unroll
+    for (int a = 0; a < RA; ++a) u[b][a] = v[RB * a + b];
+    Dft<RA>::run(u[b]);
+#pragma unroll
+    for (int ka = 1; ka < RA; ++ka)
+      if (b > 0) u[b][ka] = rot32(u[b][ka], (32 / R) * b * ka);
+  }
+#pragma unroll
+  for (int ka = 0; ka < RA; ++ka) {
+    float2 w[RB];
+#pragma unroll
+    for (int b = 0; b < RB; ++b) w[b] = u[b][ka];
+    Dft<RB>::run(w);
+#pragma unroll
+    for (int kb = 0; kb < RB; ++kb) v[ka + RA * kb] = w[kb];
+  }
+}
+template <>
+struct Dft<8> {
+  FFT_HD static void run(float2* v) { dft_composite<4, 2>(v); }
+};
+template <>
+struct Dft<16> {
+  FFT_HD static void run(float2* v) { dft_composite<4, 4>(v); }
+};
+template <>
+struct Dft<32> {
+  FFT_HD static void run(float2* v) { dft_composite<8, 4>(v); }
+};
+
+template <int R>
+FFT_HD void swap_xy(float2* v) {
+#pragma unroll
+  for (int i = 0; i < R; ++i) v[i] = make_float2(v[i].y, v[i].x);
+}
+// inverse DFT (unnormalised) through the swap identity: IDFT(x) = swap(DFT(swap(x)))
+template <int R, bool INV>
+FFT_HD void dft(float2* v) {
+  if (INV) swap_xy<R>(v);
+  Dft<R>::run(v);
+  if (INV) swap_xy<R>(v);
+}
+
+// ---- decomposition table --------------------------------------------------------------------------------
+template <int L>
+struct Cfg;
+#define SOPHT_FFT_CFG(L_, R1_, R2_, R3_, E_)                      \
+  template <>                                                     \
+  struct Cfg<L_> {                                                \
+    static constexpr int R1 = R1_, R2 = R2_, R3 = R3_, E = E_;    \
+    static constexpr int T = L_ / E_;                             \
+    static constexpr int NP = R3_ > 1 ? 3 : 2;                    \
+    static constexpr int RLAST = R3_ > 1 ? R3_ : R2_;             \
+  };
+SOPHT_FFT_CFG(16, 4, 4, 1, 4)
+SOPHT_FFT_CFG(32, 8, 4, 1, 8)
+SOPHT_FFT_CFG(64, 8, 8, 1, 8)
+SOPHT_FFT_CFG(128, 16, 8, 1, 16)
+SOPHT_FFT_CFG(256, 16, 16, 1, 16)
+SOPHT_FFT_CFG(512, 32, 16, 1, 32)
+SOPHT_FFT_CFG(1024, 32, 32, 1, 32)
+SOPHT_FFT_CFG(2048, 16, 16, 8, 16)
+#undef SOPHT_FFT_CFG
+
+// spectrum index held at position blk*RLAST + klast after the forward last pass
+template <int L>
+FFT_HD int spectrum_index(int blk, int klast) {
+  using C = Cfg<L>;
+  if (C::NP == 2) return blk + C::R1 * klast;
+  const int k1 = blk / C::R2, k2 = blk % C::R2;
+  return k1 + C::R1 * k2 + C::R1 * C::R2 * klast;
+}
+// position of spectrum index k after the forward last pass (inverse of the above)
+template <int L>
+FFT_HD int spectrum_position(int k) {
+  using C = Cfg<L>;
+  if (C::NP == 2) return (k % C::R1) * C::R2 + k / C::R1;
+  const int k1 = k % C::R1, k2 = (k / C::R1) % C::R2, k3 = k / (C::R1 * C::R2);
+  return (k1 * C::R2 + k2) * C::R3 + k3;
+}
+
+// ---- passes. `Acc` maps a logical position (0..L-1) of THIS thread's column to a float2& in smem ---------
+// tw: forward twiddles of length L, tw[j] = exp(-2 pi i j / L)
+
+// forward first pass: global (pruned: positions >= L/2 are zero) -> butterfly R1 -> twiddle -> smem
+template <int L, class Load, class Acc>
+FFT_HD void fwd_first(Load ld, Acc sm, int t, const float2* __restrict__ tw) {
+  using C = Cfg<L>;
+  constexpr int R = C::R1, S = L / R, NB = C::E / R;
+  float2 v[NB][R];
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int j = t + q * C::T;
+#pragma unroll
+    for (int n = 0; n < R; ++n) v[q][n] = n < R / 2 ? ld(n * S + j) : make_float2(0.f, 0.f);
+  }
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int j = t + q * C::T;
+    dft<R, false>(v[q]);
+    sm(j) = v[q][0];
+#pragma unroll
+    for (int k = 1; k < R; ++k) sm(k * S + j) = cmul(v[q][k], tw[j * k]);
+  }
+}
+
+// forward middle pass (three-pass configurations only): smem -> butterfly R2 -> twiddle -> smem
+template <int L, class Acc>
+FFT_HD void fwd_mid(Acc sm, int t, const float2* __restrict__ tw) {
+  using C = Cfg<L>;
+  constexpr int R = C::R2, SP = L / C::R1, S = SP / R, NB = C::E / R;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int b = t + q * C::T, blk = b / S, j = b % S, base = blk * SP + j;
+    float2 v[R];
+#pragma unroll
+    for (int n = 0; n < R; ++n) v[n] = sm(base + n * S);
+    dft<R, false>(v);
+    sm(base) = v[0];
+#pragma unroll
+    for (int k = 1; k < R; ++k) sm(base + k * S) = cmul(v[k], tw[j * k * (L / SP)]);
+  }
+}
+
+// forward last pass: smem -> butterfly RLAST -> sink(spectrum index k, position, value)
+template <int L, class Acc, class Sink>
+FFT_HD void fwd_last(Acc sm, int t, Sink sink) {
+  using C = Cfg<L>;
+  constexpr int R = C::RLAST, NB = C::E / R;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int blk = t + q * C::T;
+    float2 v[R];
+#pragma unroll
+    for (int n = 0; n < R; ++n) v[n] = sm(blk * R + n);
+    dft<R, false>(v);
+#pragma unroll
+    for (int k = 0; k < R; ++k) sink(spectrum_index<L>(blk, k), blk * R + k, v[k]);
+  }
+}
+
+// inverse first pass: src(spectrum index k, position) -> inverse butterfly RLAST -> smem
+template <int L, class Src, class Acc>
+FFT_HD void inv_first(Src src, Acc sm, int t) {
+  using C = Cfg<L>;
+  constexpr int R = C::RLAST, NB = C::E / R;
+  float2 v[NB][R];
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int blk = t + q * C::T;
+#pragma unroll
+    for (int k = 0; k < R; ++k) v[q][k] = src(spectrum_index<L>(blk, k), blk * R + k);
+  }
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int blk = t + q * C::T;
+    dft<R, true>(v[q]);
+#pragma unroll
+    for (int n = 0; n < R; ++n) sm(blk * R + n) = v[q][n];
+  }
+}
+
+// fused: forward last pass -> multiply by a real spectrum g(k) -> inverse first pass, all in registers
+template <int L, class Acc, class G>
+FFT_HD void fwd_last_mul_inv_first(Acc sm, int t, G g) {
+  using C = Cfg<L>;
+  constexpr int R = C::RLAST, NB = C::E / R;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int blk = t + q * C::T;
+    float2 v[R];
+#pragma unroll
+    for (int n = 0; n < R; ++n) v[n] = sm(blk * R + n);
+    dft<R, false>(v);
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+      const float s = g(spectrum_index<L>(blk, k));
+      v[k].x *= s;
+      v[k].y *= s;
+    }
+    dft<R, true>(v);
+#pragma unroll
+    for (int n = 0; n < R; ++n) sm(blk * R + n) = v[n];
+  }
+}
+
+// inverse middle pass (three-pass configurations): smem -> conj twiddle -> inverse butterfly R2 -> smem
+template <int L, class Acc>
+FFT_HD void inv_mid(Acc sm, int t, const float2* __restrict__ tw) {
+  using C = Cfg<L>;
+  constexpr int R = C::R2, SP = L / C::R1, S = SP / R, NB = C::E / R;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int b = t + q * C::T, blk = b / S, j = b % S, base = blk * SP + j;
+    float2 v[R];
+    v[0] = sm(base);
+#pragma unroll
+    for (int k = 1; k < R; ++k) v[k] = cmul_conj(sm(base + k * S), tw[j * k * (L / SP)]);
+    dft<R, true>(v);
+#pragma unroll
+    for (int n = 0; n < R; ++n) sm(base + n * S) = v[n];
+  }
+}
+
+// inverse last pass: smem -> conj twiddle -> inverse butterfly R1 -> st(position e, value) for e < L/2 only
+template <int L, class Acc, class Store>
+FFT_HD void inv_last(Acc sm, int t, const float2* __restrict__ tw, Store st) {
+  using C = Cfg<L>;
+  constexpr int R = C::R1, S = L / R, NB = C::E / R;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int j = t + q * C::T;
+    float2 v[R];
+    v[0] = sm(j);
+#pragma unroll
+    for (int k = 1; k < R; ++k) v[k] = cmul_conj(sm(k * S + j), tw[j * k]);
+    dft<R, true>(v);
+#pragma unroll
+    for (int n = 0; n < R / 2; ++n) st(n * S + j, v[n]);
+  }
+}
+
+}  // namespace fft
+}  // namespace sopht

@@ -17,4 +17,14 @@ PoissonImpl* make_generic_poisson(int dtype, int dim, int nz, int ny, int nx, do
                                   const double* mz, const double* my, const double* mx,
                                   double origin, cudaStream_t st, int* rc);
 
+// Re(G_hat) * dx^dim / (doubled cell count) on (2nz, 2ny, nx+1), natural order (device, caller frees)
+template <typename T>
+int build_green_hat(T** g_out, int dim, int nz, int ny, int nx, double dx, const double* mz_h,
+                    const double* my_h, const double* mx_h, double origin_value, cudaStream_t st);
+
+// fp32, 3-D, power-of-two grids: pruned + fused shared-memory FFT pipeline (poisson_pow2.cu)
+bool pow2_poisson_eligible(int dtype, int dim, int nz, int ny, int nx);
+PoissonImpl* make_pow2_poisson(int nz, int ny, int nx, double dx, const double* mz, const double* my,
+                               const double* mx, double origin, cudaStream_t st, int* rc);
+
 }  // namespace sopht

@@ -45,10 +45,13 @@ int sopht_poisson_create(sopht_poisson_t* handle, int dtype, int dim, int nz, in
     const double pi = 3.14159265358979323846;
     origin_value = dim == 3 ? 1.0 / (4 * pi * dx) : -(2 * log(dx / sqrt(pi)) - 1) / (4 * pi);
   }
-  (void)flags;
   int rc = SOPHT_OK;
-  PoissonImpl* impl = make_generic_poisson(dtype, dim, nz, ny, nx, dx, mz, my, mx, origin_value,
-                                           as_stream(stream), &rc);
+  PoissonImpl* impl = nullptr;
+  if (flags != SOPHT_POISSON_FORCE_GENERIC && pow2_poisson_eligible(dtype, dim, nz, ny, nx))
+    impl = make_pow2_poisson(nz, ny, nx, dx, mz, my, mx, origin_value, as_stream(stream), &rc);
+  else
+    impl = make_generic_poisson(dtype, dim, nz, ny, nx, dx, mz, my, mx, origin_value,
+                                as_stream(stream), &rc);
   if (!impl) return rc;
   sopht_poisson* h = new sopht_poisson{dtype, dim, dim == 3 ? nz : 1, ny, nx, impl};
   *handle = h;

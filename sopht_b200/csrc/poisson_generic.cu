@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------------------------
 // G_hat (real part, scaled) on the doubled half-spectrum (n2z, n2y, nx+1), computed in double precision.
 template <typename T>
-static int build_green_hat(T** g_out, int dim, int nz, int ny, int nx, double dx, const double* mz_h,
+int build_green_hat(T** g_out, int dim, int nz, int ny, int nx, double dx, const double* mz_h,
                            const double* my_h, const double* mx_h, double origin_value,
                            cudaStream_t st) {
   const int n2z = dim == 3 ? 2 * nz : 1, n2y = 2 * ny, n2x = 2 * nx, nkx = nx + 1;
@@ -334,6 +334,11 @@ struct GenericPoisson : PoissonImpl {
 
   const void* green_hat() const override { return ghat; }
 };
+
+template int build_green_hat<float>(float**, int, int, int, int, double, const double*, const double*,
+                                     const double*, double, cudaStream_t);
+template int build_green_hat<double>(double**, int, int, int, int, double, const double*, const double*,
+                                      const double*, double, cudaStream_t);
 
 PoissonImpl* make_generic_poisson(int dtype, int dim, int nz, int ny, int nx, double dx,
                                   const double* mz, const double* my, const double* mx,

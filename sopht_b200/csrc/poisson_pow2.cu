@@ -1,0 +1,316 @@
+// Unbounded Poisson solve, fp32 power-of-two fast path: a pruned, zero-padding-free FFT pipeline of five
+// hand-written shared-memory FFT kernels (no cuFFT on the solve path). See poisson_pow2_phases.cuh for the
+// dataflow; this file holds the kernel launcher, the dispatch over transform lengths and the handle.
+//
+// HBM traffic per cell per component: x 4+8, y 8+16, z 16+16 (+ G_hat, folded by its even
+// symmetry and reused across the three components), y^-1 16+8, x^-1 8+4  = 104 B + G_hat.
+//
+// ref: sopht/numeric/eulerian_grid_ops/poisson_solver_3d/UnboundedPoissonSolverPYFFTW3D.py:111-172
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+#include "poisson.cuh"
+#include "poisson_pow2_phases.cuh"
+
+namespace sopht {
+
+namespace {
+
+template <class K, int P>
+struct DevPhases {
+  __device__ __forceinline__ static void run(const typename K::Params& p, int it, float2* smem) {
+    DevPhases<K, P - 1>::run(p, it, smem);
+    if (P > 0) __syncthreads();
+    K::template phase<P>(p, blockIdx.x, blockIdx.y, it, threadIdx.x, smem);
+  }
+};
+template <class K>
+struct DevPhases<K, -1> {
+  __device__ __forceinline__ static void run(const typename K::Params&, int, float2*) {}
+};
+
+template <class K>
+__global__ void __launch_bounds__(K::THREADS) p2_kernel(const typename K::Params p, int niter) {
+  extern __shared__ float2 p2_smem[];
+  for (int it = 0; it < niter; ++it) {
+    if (it) __syncthreads();
+    DevPhases<K, K::NPHASE - 1>::run(p, it, p2_smem);
+  }
+}
+
+template <class K>
+int launch(const typename K::Params& p, dim3 grid, int niter, cudaStream_t st) {
+  const size_t smem = sizeof(float2) * K::SMEM_ELEMS;
+  static bool configured = false;  // per kernel instantiation
+  if (!configured) {
+    if (smem > 48 * 1024)
+      SOPHT_CUDA(cudaFuncSetAttribute(p2_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  p2_kernel<K><<<grid, K::THREADS, smem, st>>>(p, niter);
+  SOPHT_CHECK_LAUNCH();
+  return SOPHT_OK;
+}
+
+constexpr int TX = 8;  // columns per CTA in the y / z passes (8 complex = 64 B segments)
+
+template <int L>
+constexpr int rows_per_cta() {  // x passes: aim for 128..256 threads per CTA
+  return fft::Cfg<L>::T >= 128 ? 1 : (128 / fft::Cfg<L>::T < 1 ? 1 : 128 / fft::Cfg<L>::T);
+}
+
+#define P2_SWITCH_L(Lval, MACRO)                                   \
+  switch (Lval) {                                                  \
+    case 16: MACRO(16); break;                                     \
+    case 32: MACRO(32); break;                                     \
+    case 64: MACRO(64); break;                                     \
+    case 128: MACRO(128); break;                                   \
+    case 256: MACRO(256); break;                                   \
+    case 512: MACRO(512); break;                                   \
+    case 1024: MACRO(1024); break;                                 \
+    case 2048: MACRO(2048); break;                                 \
+    default: SOPHT_FAIL(SOPHT_ERR_SHAPE, "poisson(pow2): unsupported transform length %d", (int)(Lval)); \
+  }
+
+int launch_xfwd(int L, const p2::XParams& p, int64_t rows, cudaStream_t st) {
+#define M(LL)                                                                         \
+  {                                                                                   \
+    constexpr int RX = rows_per_cta<LL>();                                            \
+    return launch<p2::XFwd<LL, RX>>(p, dim3((unsigned)(rows / RX), 1, 1), 1, st);     \
+  }
+  P2_SWITCH_L(L, M)
+#undef M
+  return SOPHT_OK;
+}
+int launch_xinv(int L, const p2::XParams& p, int64_t rows, cudaStream_t st) {
+#define M(LL)                                                                         \
+  {                                                                                   \
+    constexpr int RX = rows_per_cta<LL>();                                            \
+    return launch<p2::XInv<LL, RX>>(p, dim3((unsigned)(rows / RX), 1, 1), 1, st);     \
+  }
+  P2_SWITCH_L(L, M)
+#undef M
+  return SOPHT_OK;
+}
+int launch_yfwd(int L, const p2::ColParams& p, dim3 grid, cudaStream_t st) {
+#define M(LL) return launch<p2::YFwd<LL, TX>>(p, grid, 1, st);
+  P2_SWITCH_L(L, M)
+#undef M
+  return SOPHT_OK;
+}
+int launch_yinv(int L, const p2::ColParams& p, dim3 grid, cudaStream_t st) {
+#define M(LL) return launch<p2::YInv<LL, TX>>(p, grid, 1, st);
+  P2_SWITCH_L(L, M)
+#undef M
+  return SOPHT_OK;
+}
+int launch_zconv(int L, const p2::ZParams& p, dim3 grid, cudaStream_t st) {
+#define M(LL) return launch<p2::ZConv<LL, TX>>(p, grid, p.ncomp, st);
+  P2_SWITCH_L(L, M)
+#undef M
+  return SOPHT_OK;
+}
+
+// folded spectrum: gm[(fz*(ny+1) + fy)*nx + kx] (kx < nx), gn[fz*(ny+1) + fy] (kx = nx); x2 because the
+// half-length x transform's unnormalised round trip is nx * 2ny * 2nz, half the doubled cell count.
+__global__ void __launch_bounds__(256)
+    fold_green_kernel(float* gm, float* gn, const float* ghat, int nz, int ny, int nx) {
+  const int64_t total = (int64_t)(nz + 1) * (ny + 1) * (nx + 1);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
+       q += (int64_t)gridDim.x * blockDim.x) {
+    const int kx = (int)(q % (nx + 1));
+    const int64_t r = q / (nx + 1);
+    const int fy = (int)(r % (ny + 1)), fz = (int)(r / (ny + 1));
+    const float v = 2.0f * ghat[((int64_t)fz * 2 * ny + fy) * (nx + 1) + kx];
+    if (kx < nx)
+      gm[((int64_t)fz * (ny + 1) + fy) * nx + kx] = v;
+    else
+      gn[(int64_t)fz * (ny + 1) + fy] = v;
+  }
+}
+
+bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
+
+struct Pow2Poisson : PoissonImpl {
+  int nz, ny, nx;
+  double dx;
+  std::vector<double> mz, my, mx;
+  double origin;
+  float* ghat_natural = nullptr;  // (2nz, 2ny, nx+1), kept for sopht_poisson_green_hat
+  float *gm = nullptr, *gn = nullptr;
+  float2 *A = nullptr, *nyqA = nullptr, *B = nullptr, *nyqB = nullptr;
+  float2 *twx = nullptr, *twx2 = nullptr, *twy = nullptr, *twz = nullptr;
+  PoissonImpl* generic = nullptr;  // built lazily for views this path cannot take (x-stride != 1, ...)
+
+  ~Pow2Poisson() override {
+    cudaFree(ghat_natural);
+    cudaFree(gm);
+    cudaFree(gn);
+    cudaFree(A);
+    cudaFree(nyqA);
+    cudaFree(B);
+    cudaFree(nyqB);
+    cudaFree(twx);
+    cudaFree(twx2);
+    cudaFree(twy);
+    cudaFree(twz);
+    delete generic;
+  }
+
+  static int upload_twiddles(float2** dst, int L, int denom, cudaStream_t st) {
+    std::vector<float2> h(L);
+    for (int j = 0; j < L; ++j) {
+      const double a = -2.0 * 3.14159265358979323846 * j / denom;
+      h[j] = make_float2((float)cos(a), (float)sin(a));
+    }
+    SOPHT_CUDA(cudaMalloc(dst, sizeof(float2) * L));
+    SOPHT_CUDA(cudaMemcpyAsync(*dst, h.data(), sizeof(float2) * L, cudaMemcpyHostToDevice, st));
+    SOPHT_CUDA(cudaStreamSynchronize(st));
+    return SOPHT_OK;
+  }
+
+  int init(cudaStream_t st) {
+    int rc = build_green_hat<float>(&ghat_natural, 3, nz, ny, nx, dx, mz.data(), my.data(), mx.data(),
+                                    origin, st);
+    if (rc) return rc;
+    const size_t rows = (size_t)3 * nz * ny;
+    SOPHT_CUDA(cudaMalloc(&gm, sizeof(float) * (size_t)(nz + 1) * (ny + 1) * nx));
+    SOPHT_CUDA(cudaMalloc(&gn, sizeof(float) * (size_t)(nz + 1) * (ny + 1)));
+    fold_green_kernel<<<148 * 8, 256, 0, st>>>(gm, gn, ghat_natural, nz, ny, nx);
+    SOPHT_CHECK_LAUNCH();
+    SOPHT_CUDA(cudaMalloc(&A, sizeof(float2) * rows * nx));
+    SOPHT_CUDA(cudaMalloc(&nyqA, sizeof(float2) * rows));
+    SOPHT_CUDA(cudaMalloc(&B, sizeof(float2) * rows * 2 * nx));
+    SOPHT_CUDA(cudaMalloc(&nyqB, sizeof(float2) * rows * 2));
+    if ((rc = upload_twiddles(&twx, nx, nx, st))) return rc;
+    if ((rc = upload_twiddles(&twx2, nx, 2 * nx, st))) return rc;
+    if ((rc = upload_twiddles(&twy, 2 * ny, 2 * ny, st))) return rc;
+    if ((rc = upload_twiddles(&twz, 2 * nz, 2 * nz, st))) return rc;
+    SOPHT_CUDA(cudaStreamSynchronize(st));
+    return SOPHT_OK;
+  }
+
+  static bool view_ok(const sopht_field_t* f, int o) {
+    // rows contiguous and 8-byte aligned so a real row can be moved as float2
+    if (f->stride[o + 2] != 1) return false;
+    if ((reinterpret_cast<uintptr_t>(f->data) & 7) != 0) return false;
+    if ((f->stride[o] & 1) || (f->stride[o + 1] & 1)) return false;
+    if (o == 1 && (f->stride[0] & 1)) return false;
+    return true;
+  }
+
+  int solve(const sopht_field_t* sol, const sopht_field_t* rhs, cudaStream_t st) override {
+    const bool vec = sol->ndim == 4;
+    const int o = vec ? 1 : 0;
+    const int C = vec ? (int)sol->shape[0] : 1;
+    if (C > 3 || !view_ok(sol, o) || !view_ok(rhs, o)) {
+      if (!generic) {
+        int rc = SOPHT_OK;
+        generic = make_generic_poisson(SOPHT_F32, 3, nz, ny, nx, dx, mz.data(), my.data(), mx.data(),
+                                       origin, st, &rc);
+        if (!generic) return rc;
+      }
+      return generic->solve(sol, rhs, st);
+    }
+    const int LY = 2 * ny, LZ = 2 * nz;
+    const int64_t rows = (int64_t)C * nz * ny;
+    int rc;
+    p2::XParams xp{};
+    xp.real_in = reinterpret_cast<const float*>(rhs->data);
+    xp.sc = vec ? rhs->stride[0] : 0;
+    xp.sz = rhs->stride[o];
+    xp.sy = rhs->stride[o + 1];
+    xp.spec = A;
+    xp.nyq = nyqA;
+    xp.nz = nz;
+    xp.ny = ny;
+    xp.tw = twx;
+    xp.tw2 = twx2;
+    if ((rc = launch_xfwd(nx, xp, rows, st))) return rc;
+
+    p2::ColParams yp{};
+    yp.in = A;
+    yp.out = B;
+    yp.in_rs = nx, yp.in_cs = 1, yp.out_rs = nx, yp.out_cs = 1;
+    yp.in_bx = TX, yp.in_by = (int64_t)ny * nx, yp.out_bx = TX, yp.out_by = (int64_t)LY * nx;
+    yp.tw = twy;
+    if ((rc = launch_yfwd(LY, yp, dim3(nx / TX, C * nz, 1), st))) return rc;
+    p2::ColParams yn{};
+    yn.in = nyqA;
+    yn.out = nyqB;
+    yn.in_rs = 1, yn.in_cs = ny, yn.out_rs = 1, yn.out_cs = LY;
+    yn.in_bx = (int64_t)TX * ny, yn.in_by = 0, yn.out_bx = (int64_t)TX * LY, yn.out_by = 0;
+    yn.tw = twy;
+    if ((rc = launch_yfwd(LY, yn, dim3(C * nz / TX, 1, 1), st))) return rc;
+
+    p2::ZParams zp{};
+    zp.data = B;
+    zp.rs = (int64_t)LY * nx, zp.cs = 1, zp.d_bx = TX, zp.d_by = nx, zp.d_c = (int64_t)nz * LY * nx;
+    zp.ncomp = C;
+    zp.g = gm;
+    zp.g_zs = (int64_t)(ny + 1) * nx;
+    zp.g_ky_stride = nx;
+    zp.n2y = LY;
+    zp.nyq = 0;
+    zp.tw = twz;
+    if ((rc = launch_zconv(LZ, zp, dim3(nx / TX, LY, 1), st))) return rc;
+    p2::ZParams zn = zp;
+    zn.data = nyqB;
+    zn.rs = LY, zn.cs = 1, zn.d_bx = TX, zn.d_by = 0, zn.d_c = (int64_t)nz * LY;
+    zn.g = gn;
+    zn.g_zs = ny + 1;
+    zn.g_ky_stride = 1;
+    zn.nyq = 1;
+    if ((rc = launch_zconv(LZ, zn, dim3(LY / TX, 1, 1), st))) return rc;
+
+    p2::ColParams yi{};
+    yi.in = B;
+    yi.out = A;
+    yi.in_rs = nx, yi.in_cs = 1, yi.out_rs = nx, yi.out_cs = 1;
+    yi.in_bx = TX, yi.in_by = (int64_t)LY * nx, yi.out_bx = TX, yi.out_by = (int64_t)ny * nx;
+    yi.tw = twy;
+    if ((rc = launch_yinv(LY, yi, dim3(nx / TX, C * nz, 1), st))) return rc;
+    p2::ColParams yni{};
+    yni.in = nyqB;
+    yni.out = nyqA;
+    yni.in_rs = 1, yni.in_cs = LY, yni.out_rs = 1, yni.out_cs = ny;
+    yni.in_bx = (int64_t)TX * LY, yni.in_by = 0, yni.out_bx = (int64_t)TX * ny, yni.out_by = 0;
+    yni.tw = twy;
+    if ((rc = launch_yinv(LY, yni, dim3(C * nz / TX, 1, 1), st))) return rc;
+
+    xp.real_out = reinterpret_cast<float*>(sol->data);
+    xp.sc = vec ? sol->stride[0] : 0;
+    xp.sz = sol->stride[o];
+    xp.sy = sol->stride[o + 1];
+    return launch_xinv(nx, xp, rows, st);
+  }
+
+  const void* green_hat() const override { return ghat_natural; }
+  const char* path_name() const override { return "pow2"; }
+};
+
+}  // namespace
+
+bool pow2_poisson_eligible(int dtype, int dim, int nz, int ny, int nx) {
+  return dtype == SOPHT_F32 && dim == 3 && is_pow2(nx) && is_pow2(ny) && is_pow2(nz) && nx >= 16 &&
+         nx <= 2048 && ny >= 8 && ny <= 1024 && nz >= 8 && nz <= 1024;
+}
+
+PoissonImpl* make_pow2_poisson(int nz, int ny, int nx, double dx, const double* mz, const double* my,
+                               const double* mx, double origin, cudaStream_t st, int* rc) {
+  auto* p = new Pow2Poisson();
+  p->nz = nz, p->ny = ny, p->nx = nx, p->dx = dx, p->origin = origin;
+  p->mz.assign(mz, mz + 2 * nz);
+  p->my.assign(my, my + 2 * ny);
+  p->mx.assign(mx, mx + 2 * nx);
+  *rc = p->init(st);
+  if (*rc) {
+    delete p;
+    return nullptr;
+  }
+  return p;
+}
+
+}  // namespace sopht

@@ -1,0 +1,293 @@
+// Phase functions of the pruned, fused FFT pipeline for the unbounded Poisson solve (fp32, power-of-two
+// grids). Each kernel is a sequence of PHASES separated by __syncthreads(); a phase reads shared/global
+// memory, works in registers and writes shared/global memory, so the same code is emulated thread by thread
+// on the CPU (tests/host/fft_emul.cu) to pin the index arithmetic before it runs on the GPU.
+//
+// Pipeline for rhs (C, nz, ny, nx) real, doubled domain (2nz, 2ny, 2nx) never materialised:
+//   XFwd : rows (c,z,y): real row of nx (+ nx implicit zeros) -> half-length complex FFT (length nx, upper
+//          half of its input zero) + Hermitian post-processing -> A[c][z][y][kx<nx], nyqA[c][z][y] (kx = nx)
+//   YFwd : (c,z,kx-tile): ny rows (+ ny zeros) -> FFT length 2ny -> B[c][z][ky<2ny][kx]
+//   ZConv: (ky,kx-tile), loop c: nz rows (+ nz zeros) -> FFT 2nz -> x G_hat (real, even: folded storage) ->
+//          inverse FFT 2nz -> first nz rows back in place
+//   YInv : (c,z<nz,kx-tile): 2ny rows -> inverse FFT -> first ny rows -> A
+//   XInv : rows: Hermitian pre-processing -> inverse half-length FFT -> first nx reals -> solution
+// The kx = nx (Nyquist) plane travels as a separate small (C, nz, ny) array through the same Y/Z kernels
+// with different strides. ref: UnboundedPoissonSolverPYFFTW3D.py:111-149 (what is computed).
+#pragma once
+#include <stdint.h>
+
+#include "fft_tile.cuh"
+
+namespace sopht {
+namespace p2 {
+
+using fft::Cfg;
+
+// ---- shared-memory accessors ------------------------------------------------------------------------------
+// column mode: TX sequences side by side, column index fastest; a skew row every RLAST rows keeps the
+// stride-RLAST accesses of the last pass off the same banks.
+template <int L, int TX>
+struct ColAcc {
+  float2* s;
+  int col;
+  static constexpr int PADR = Cfg<L>::RLAST;
+  static constexpr int ROWS = L + L / PADR;
+  FFT_HD float2& operator()(int e) const { return s[(e + e / PADR) * TX + col]; }
+};
+// row mode: each sequence contiguous, one pad element every RLAST elements
+template <int L>
+struct RowAcc {
+  float2* s;
+  static constexpr int PADR = Cfg<L>::RLAST;
+  static constexpr int PITCH = L + L / PADR + 1;
+  FFT_HD float2& operator()(int e) const { return s[e + e / PADR]; }
+};
+
+// ---- Y forward / inverse (column mode) --------------------------------------------------------------------
+struct ColParams {
+  const float2* in;
+  float2* out;
+  int64_t in_rs, in_cs, out_rs, out_cs;          // row / column strides (complex elements)
+  int64_t in_bx, in_by, out_bx, out_by;          // tile origin = base + bx*_bx + by*_by
+  const float2* tw;                              // forward twiddles, length L
+};
+
+struct GlobalLoad {
+  const float2* p;
+  int64_t rs;
+  FFT_HD float2 operator()(int e) const { return p[e * rs]; }
+};
+struct GlobalStoreIdx {  // sink(k, pos, v) -> out[k]
+  float2* p;
+  int64_t rs;
+  FFT_HD void operator()(int k, int, float2 v) const { p[k * rs] = v; }
+};
+struct GlobalSrcIdx {  // src(k, pos) -> in[k]
+  const float2* p;
+  int64_t rs;
+  FFT_HD float2 operator()(int k, int) const { return p[k * rs]; }
+};
+struct GlobalStore {
+  float2* p;
+  int64_t rs;
+  FFT_HD void operator()(int e, float2 v) const { p[e * rs] = v; }
+};
+
+template <int L, int TX>
+struct YFwd {
+  using Params = ColParams;
+  static constexpr int THREADS = Cfg<L>::T * TX;
+  static constexpr int NPHASE = Cfg<L>::NP;
+  static constexpr int NITER = 1;
+  static constexpr int SMEM_ELEMS = ColAcc<L, TX>::ROWS * TX;
+  template <int P>
+  FFT_HD static void phase(const Params& p, int bx, int by, int, int tid, float2* smem) {
+    const int col = tid % TX, t = tid / TX;
+    ColAcc<L, TX> sm{smem, col};
+    if (P == 0) {
+      GlobalLoad ld{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, p.in_rs};
+      fft::fwd_first<L>(ld, sm, t, p.tw);
+    } else if (P == NPHASE - 1) {
+      GlobalStoreIdx st{p.out + bx * p.out_bx + by * p.out_by + col * p.out_cs, p.out_rs};
+      fft::fwd_last<L>(sm, t, st);
+    } else {
+      fft::fwd_mid<L>(sm, t, p.tw);
+    }
+  }
+};
+
+template <int L, int TX>
+struct YInv {
+  using Params = ColParams;
+  static constexpr int THREADS = Cfg<L>::T * TX;
+  static constexpr int NPHASE = Cfg<L>::NP;
+  static constexpr int NITER = 1;
+  static constexpr int SMEM_ELEMS = ColAcc<L, TX>::ROWS * TX;
+  template <int P>
+  FFT_HD static void phase(const Params& p, int bx, int by, int, int tid, float2* smem) {
+    const int col = tid % TX, t = tid / TX;
+    ColAcc<L, TX> sm{smem, col};
+    if (P == 0) {
+      GlobalSrcIdx src{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, p.in_rs};
+      fft::inv_first<L>(src, sm, t);
+    } else if (P == NPHASE - 1) {
+      GlobalStore st{p.out + bx * p.out_bx + by * p.out_by + col * p.out_cs, p.out_rs};
+      fft::inv_last<L>(sm, t, p.tw, st);
+    } else {
+      fft::inv_mid<L>(sm, t, p.tw);
+    }
+  }
+};
+
+// ---- Z: forward, Green's function multiply, inverse — in place ----------------------------------------------
+struct ZParams {
+  float2* data;            // tile origin = data + bx*d_bx + by*d_by + c*d_c
+  int64_t rs, cs, d_bx, d_by, d_c;
+  int ncomp;
+  const float* g;          // folded G_hat: g[fold(kz)*g_zs + goff]
+  int64_t g_zs;
+  int64_t g_ky_stride;     // main: nx (goff = fold(ky)*nx + kx); nyquist plane: 1 (goff = fold(ky))
+  int n2y;                 // 2*ny, for fold(ky)
+  int nyq;                 // 0: columns are kx (ky = by); 1: columns are ky (ky = bx*TX + col)
+  const float2* tw;
+};
+
+struct GreenFold {
+  const float* g;
+  int64_t zs;
+  int n2z;
+  FFT_HD float operator()(int kz) const {
+    const int f = kz <= n2z / 2 ? kz : n2z - kz;
+    return g[f * zs];
+  }
+};
+
+template <int L, int TX>
+struct ZConv {
+  using Params = ZParams;
+  static constexpr int THREADS = Cfg<L>::T * TX;
+  static constexpr int NP = Cfg<L>::NP;
+  static constexpr int NPHASE = 2 * NP - 1;  // fwd_first [fwd_mid] fused [inv_mid] inv_last
+  static constexpr int SMEM_ELEMS = ColAcc<L, TX>::ROWS * TX;
+  template <int P>
+  FFT_HD static void phase(const Params& p, int bx, int by, int c, int tid, float2* smem) {
+    const int col = tid % TX, t = tid / TX;
+    ColAcc<L, TX> sm{smem, col};
+    float2* base = p.data + bx * p.d_bx + by * p.d_by + c * p.d_c + col * p.cs;
+    if (P == 0) {
+      GlobalLoad ld{base, p.rs};
+      fft::fwd_first<L>(ld, sm, t, p.tw);
+    } else if (P == NP - 1) {
+      const int ky = p.nyq ? bx * TX + col : by;
+      const int fky = ky <= p.n2y / 2 ? ky : p.n2y - ky;
+      const int64_t goff = p.nyq ? (int64_t)fky : (int64_t)fky * p.g_ky_stride + bx * TX + col;
+      GreenFold g{p.g + goff, p.g_zs, L};
+      fft::fwd_last_mul_inv_first<L>(sm, t, g);
+    } else if (P == NPHASE - 1) {
+      GlobalStore st{base, p.rs};
+      fft::inv_last<L>(sm, t, p.tw, st);
+    } else if (P < NP - 1) {
+      fft::fwd_mid<L>(sm, t, p.tw);
+    } else {
+      fft::inv_mid<L>(sm, t, p.tw);
+    }
+  }
+};
+
+// ---- X forward: real rows -> half spectrum (row mode) -----------------------------------------------------
+struct XParams {
+  const float* real_in;    // XFwd: rhs;  element (c,z,y,x) at c*sc + z*sz + y*sy + x
+  float* real_out;         // XInv: solution
+  int64_t sc, sz, sy;      // strides of the real field (floats)
+  float2* spec;            // A: (rows, nx) complex
+  float2* nyq;             // (rows) complex
+  int nz, ny;              // row = (c*nz + z)*ny + y
+  const float2* tw;        // forward twiddles, length L = nx
+  const float2* tw2;       // exp(-2 pi i k / (2 nx)), k = 0..nx-1
+};
+
+template <int L>
+struct InPlaceSink {
+  RowAcc<L> sm;
+  FFT_HD void operator()(int, int pos, float2 v) const { sm(pos) = v; }
+};
+template <int L>
+struct InPlaceSrc {
+  RowAcc<L> sm;
+  FFT_HD float2 operator()(int, int pos) const { return sm(pos); }
+};
+struct RowLoad {
+  const float2* p;
+  FFT_HD float2 operator()(int e) const { return p[e]; }
+};
+struct RowStore {
+  float2* p;
+  FFT_HD void operator()(int e, float2 v) const { p[e] = v; }
+};
+
+template <int L, int RX>
+struct XFwd {
+  using Params = XParams;
+  static constexpr int T = Cfg<L>::T;
+  static constexpr int THREADS = T * RX;
+  static constexpr int NP = Cfg<L>::NP;
+  static constexpr int NPHASE = NP + 1;
+  static constexpr int NITER = 1;
+  static constexpr int SMEM_ELEMS = RowAcc<L>::PITCH * RX;
+  template <int P>
+  FFT_HD static void phase(const Params& p, int bx, int, int, int tid, float2* smem) {
+    const int t = tid % T, r = tid / T;
+    const int64_t row = (int64_t)bx * RX + r;
+    RowAcc<L> sm{smem + r * RowAcc<L>::PITCH};
+    if (P == 0) {
+      const int y = (int)(row % p.ny);
+      const int64_t cz = row / p.ny;
+      const int z = (int)(cz % p.nz);
+      const int64_t c = cz / p.nz;
+      RowLoad ld{reinterpret_cast<const float2*>(p.real_in + c * p.sc + z * p.sz + y * p.sy)};
+      fft::fwd_first<L>(ld, sm, t, p.tw);
+    } else if (P == NP - 1) {
+      fft::fwd_last<L>(sm, t, InPlaceSink<L>{sm});
+    } else if (P == NP) {
+      // X_k = E_k + w^k O_k, E = (Z_k + conj Z_{L-k})/2, O = (Z_k - conj Z_{L-k})/(2i); X_L = E_0 - O_0
+      float2* out = p.spec + row * L;
+#pragma unroll
+      for (int q = 0; q < Cfg<L>::E; ++q) {
+        const int k = t + q * T;
+        const float2 a = sm(fft::spectrum_position<L>(k));
+        const float2 b = sm(fft::spectrum_position<L>((L - k) & (L - 1)));
+        const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+        const float2 o = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
+        out[k] = fft::cadd(e, fft::cmul(o, p.tw2[k]));
+        if (k == 0) p.nyq[row] = make_float2(e.x - o.x, e.y - o.y);
+      }
+    } else {
+      fft::fwd_mid<L>(sm, t, p.tw);
+    }
+  }
+};
+
+template <int L, int RX>
+struct XInv {
+  using Params = XParams;
+  static constexpr int T = Cfg<L>::T;
+  static constexpr int THREADS = T * RX;
+  static constexpr int NP = Cfg<L>::NP;
+  static constexpr int NPHASE = NP + 1;
+  static constexpr int NITER = 1;
+  static constexpr int SMEM_ELEMS = RowAcc<L>::PITCH * RX;
+  template <int P>
+  FFT_HD static void phase(const Params& p, int bx, int, int, int tid, float2* smem) {
+    const int t = tid % T, r = tid / T;
+    const int64_t row = (int64_t)bx * RX + r;
+    RowAcc<L> sm{smem + r * RowAcc<L>::PITCH};
+    if (P == 0) {
+      // Z_k = E_k + i O_k, E = (X_k + conj X_{L-k})/2, O = conj(w^k) (X_k - conj X_{L-k})/2
+      const float2* in = p.spec + row * L;
+#pragma unroll
+      for (int q = 0; q < Cfg<L>::E; ++q) {
+        const int k = t + q * T;
+        const float2 a = in[k];
+        const float2 b = k == 0 ? p.nyq[row] : in[L - k];
+        const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+        const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
+        const float2 o = fft::cmul_conj(d, p.tw2[k]);
+        sm(fft::spectrum_position<L>(k)) = make_float2(e.x - o.y, e.y + o.x);
+      }
+    } else if (P == 1) {
+      fft::inv_first<L>(InPlaceSrc<L>{sm}, sm, t);
+    } else if (P == NPHASE - 1) {
+      const int y = (int)(row % p.ny);
+      const int64_t cz = row / p.ny;
+      const int z = (int)(cz % p.nz);
+      const int64_t c = cz / p.nz;
+      RowStore st{reinterpret_cast<float2*>(p.real_out + c * p.sc + z * p.sz + y * p.sy)};
+      fft::inv_last<L>(sm, t, p.tw, st);
+    } else {
+      fft::inv_mid<L>(sm, t, p.tw);
+    }
+  }
+};
+
+}  // namespace p2
+}  // namespace sopht

@@ -1,0 +1,237 @@
+// CPU emulation of the pruned FFT Poisson pipeline (csrc/poisson_pow2_phases.cuh): every kernel is run
+// block by block, phase by phase, thread by thread on the host and the result is compared with a
+// double-precision doubled-domain convolution. Pins the index arithmetic of the CUDA kernels without a GPU.
+//   nvcc -O2 -std=c++17 -Isopht_b200/csrc -Iinclude tests/host/fft_emul.cu -o build/fft_emul && build/fft_emul
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <complex>
+#include <vector>
+
+#include "poisson_pow2_phases.cuh"
+
+using namespace sopht;
+using cd = std::complex<double>;
+
+template <class K, int P>
+struct PhaseLoop {
+  static void run(const typename K::Params& p, int bx, int by, int it, float2* smem) {
+    PhaseLoop<K, P - 1>::run(p, bx, by, it, smem);
+    for (int tid = 0; tid < K::THREADS; ++tid) K::template phase<P>(p, bx, by, it, tid, smem);
+  }
+};
+template <class K>
+struct PhaseLoop<K, -1> {
+  static void run(const typename K::Params&, int, int, int, float2*) {}
+};
+
+template <class K>
+void emulate(const typename K::Params& p, int gx, int gy, int niter) {
+  std::vector<float2> smem(K::SMEM_ELEMS);
+  for (int by = 0; by < gy; ++by)
+    for (int bx = 0; bx < gx; ++bx)
+      for (int it = 0; it < niter; ++it) {
+        for (auto& v : smem) v = make_float2(NAN, NAN);  // poison: catches reads of unwritten slots
+        PhaseLoop<K, K::NPHASE - 1>::run(p, bx, by, it, smem.data());
+      }
+}
+
+static std::vector<float2> twiddles(int L, int denom) {
+  std::vector<float2> t(L);
+  for (int j = 0; j < L; ++j) {
+    const double a = -2.0 * M_PI * j / denom;
+    t[j] = make_float2((float)cos(a), (float)sin(a));
+  }
+  return t;
+}
+
+// reference radix-2 FFT (double), in place, sign = -1 forward / +1 inverse (unnormalised)
+static void fft_ref(std::vector<cd>& a, int sign) {
+  const int n = (int)a.size();
+  for (int i = 1, j = 0; i < n; ++i) {
+    int bit = n >> 1;
+    for (; j & bit; bit >>= 1) j ^= bit;
+    j ^= bit;
+    if (i < j) std::swap(a[i], a[j]);
+  }
+  for (int len = 2; len <= n; len <<= 1) {
+    const double ang = sign * 2 * M_PI / len;
+    for (int i = 0; i < n; i += len)
+      for (int k = 0; k < len / 2; ++k) {
+        const cd w(cos(ang * k), sin(ang * k));
+        const cd u = a[i + k], v = a[i + k + len / 2] * w;
+        a[i + k] = u + v;
+        a[i + k + len / 2] = u - v;
+      }
+  }
+}
+
+static void fft3_ref(std::vector<cd>& f, int n2z, int n2y, int n2x, int sign) {
+  std::vector<cd> line;
+  line.resize(n2x);
+  for (int k = 0; k < n2z; ++k)
+    for (int j = 0; j < n2y; ++j) {
+      for (int i = 0; i < n2x; ++i) line[i] = f[((size_t)k * n2y + j) * n2x + i];
+      fft_ref(line, sign);
+      for (int i = 0; i < n2x; ++i) f[((size_t)k * n2y + j) * n2x + i] = line[i];
+    }
+  line.resize(n2y);
+  for (int k = 0; k < n2z; ++k)
+    for (int i = 0; i < n2x; ++i) {
+      for (int j = 0; j < n2y; ++j) line[j] = f[((size_t)k * n2y + j) * n2x + i];
+      fft_ref(line, sign);
+      for (int j = 0; j < n2y; ++j) f[((size_t)k * n2y + j) * n2x + i] = line[j];
+    }
+  line.resize(n2z);
+  for (int j = 0; j < n2y; ++j)
+    for (int i = 0; i < n2x; ++i) {
+      for (int k = 0; k < n2z; ++k) line[k] = f[((size_t)k * n2y + j) * n2x + i];
+      fft_ref(line, sign);
+      for (int k = 0; k < n2z; ++k) f[((size_t)k * n2y + j) * n2x + i] = line[k];
+    }
+}
+
+template <int NZ, int NY, int NX>
+int run_case() {
+  constexpr int C = 3, TX = 8, RX = 4;
+  constexpr int LX = NX, LY = 2 * NY, LZ = 2 * NZ;
+  const size_t ncell = (size_t)NZ * NY * NX;
+  std::vector<float> rhs(C * ncell), sol(C * ncell, NAN);
+  srand(1234 + NX + 7 * NY + 13 * NZ);
+  for (auto& v : rhs) v = (float)rand() / RAND_MAX - 0.5f;
+  // folded real even spectrum, (NZ+1, NY+1, NX+1); main part [fz][fy][kx<NX], nyquist part [fz][fy]
+  std::vector<float> gmain((size_t)(NZ + 1) * (NY + 1) * NX), gnyq((size_t)(NZ + 1) * (NY + 1));
+  std::vector<double> gfull((size_t)(NZ + 1) * (NY + 1) * (NX + 1));
+  for (int a = 0; a <= NZ; ++a)
+    for (int b = 0; b <= NY; ++b)
+      for (int c = 0; c <= NX; ++c) {
+        const float v = 1.0f / (1.0f + a * 0.37f + b * 0.11f + c * 0.05f) + 0.01f * ((a * 7 + b * 3 + c) % 5);
+        gfull[((size_t)a * (NY + 1) + b) * (NX + 1) + c] = v;
+        if (c < NX)
+          gmain[((size_t)a * (NY + 1) + b) * NX + c] = v;
+        else
+          gnyq[(size_t)a * (NY + 1) + b] = v;
+      }
+  // buffers
+  const size_t rows = (size_t)C * NZ * NY;
+  std::vector<float2> A(rows * NX, make_float2(NAN, NAN)), nyqA(rows, make_float2(NAN, NAN));
+  std::vector<float2> B((size_t)C * NZ * LY * NX, make_float2(NAN, NAN)), nyqB((size_t)C * NZ * LY, make_float2(NAN, NAN));
+  auto twx = twiddles(LX, LX), twx2 = twiddles(LX, 2 * LX), twy = twiddles(LY, LY), twz = twiddles(LZ, LZ);
+
+  p2::XParams xp{};
+  xp.real_in = rhs.data();
+  xp.real_out = sol.data();
+  xp.sc = (int64_t)ncell;
+  xp.sz = (int64_t)NY * NX;
+  xp.sy = NX;
+  xp.spec = A.data();
+  xp.nyq = nyqA.data();
+  xp.nz = NZ;
+  xp.ny = NY;
+  xp.tw = twx.data();
+  xp.tw2 = twx2.data();
+  emulate<p2::XFwd<LX, RX>>(xp, (int)(rows / RX), 1, 1);
+
+  p2::ColParams yp{};
+  yp.in = A.data();
+  yp.out = B.data();
+  yp.in_rs = NX; yp.in_cs = 1; yp.out_rs = NX; yp.out_cs = 1;
+  yp.in_bx = TX; yp.in_by = (int64_t)NY * NX; yp.out_bx = TX; yp.out_by = (int64_t)LY * NX;
+  yp.tw = twy.data();
+  emulate<p2::YFwd<LY, TX>>(yp, NX / TX, C * NZ, 1);
+  p2::ColParams ynp{};
+  ynp.in = nyqA.data();
+  ynp.out = nyqB.data();
+  ynp.in_rs = 1; ynp.in_cs = NY; ynp.out_rs = 1; ynp.out_cs = LY;
+  ynp.in_bx = (int64_t)TX * NY; ynp.in_by = 0; ynp.out_bx = (int64_t)TX * LY; ynp.out_by = 0;
+  ynp.tw = twy.data();
+  emulate<p2::YFwd<LY, TX>>(ynp, C * NZ / TX, 1, 1);
+
+  p2::ZParams zp{};
+  zp.data = B.data();
+  zp.rs = (int64_t)LY * NX; zp.cs = 1; zp.d_bx = TX; zp.d_by = NX; zp.d_c = (int64_t)NZ * LY * NX;
+  zp.ncomp = C;
+  zp.g = gmain.data();
+  zp.g_zs = (int64_t)(NY + 1) * NX;
+  zp.g_ky_stride = NX;
+  zp.n2y = LY;
+  zp.nyq = 0;
+  zp.tw = twz.data();
+  emulate<p2::ZConv<LZ, TX>>(zp, NX / TX, LY, C);
+  p2::ZParams znp = zp;
+  znp.data = nyqB.data();
+  znp.rs = LY; znp.cs = 1; znp.d_bx = TX; znp.d_by = 0; znp.d_c = (int64_t)NZ * LY;
+  znp.g = gnyq.data();
+  znp.g_zs = NY + 1;
+  znp.g_ky_stride = 1;
+  znp.nyq = 1;
+  emulate<p2::ZConv<LZ, TX>>(znp, LY / TX, 1, C);
+
+  p2::ColParams yi{};
+  yi.in = B.data();
+  yi.out = A.data();
+  yi.in_rs = NX; yi.in_cs = 1; yi.out_rs = NX; yi.out_cs = 1;
+  yi.in_bx = TX; yi.in_by = (int64_t)LY * NX; yi.out_bx = TX; yi.out_by = (int64_t)NY * NX;
+  yi.tw = twy.data();
+  emulate<p2::YInv<LY, TX>>(yi, NX / TX, C * NZ, 1);
+  p2::ColParams yni{};
+  yni.in = nyqB.data();
+  yni.out = nyqA.data();
+  yni.in_rs = 1; yni.in_cs = LY; yni.out_rs = 1; yni.out_cs = NY;
+  yni.in_bx = (int64_t)TX * LY; yni.in_by = 0; yni.out_bx = (int64_t)TX * NY; yni.out_by = 0;
+  yni.tw = twy.data();
+  emulate<p2::YInv<LY, TX>>(yni, C * NZ / TX, 1, 1);
+
+  emulate<p2::XInv<LX, RX>>(xp, (int)(rows / RX), 1, 1);
+
+  // reference: doubled-domain convolution in double
+  double err2 = 0, ref2 = 0;
+  const int n2z = 2 * NZ, n2y = 2 * NY, n2x = 2 * NX;
+  const double scale = 1.0 / ((double)NX * n2y * n2z);  // pipeline's unnormalised round trip factor
+  for (int c = 0; c < C; ++c) {
+    std::vector<cd> f((size_t)n2z * n2y * n2x, cd(0, 0));
+    for (int k = 0; k < NZ; ++k)
+      for (int j = 0; j < NY; ++j)
+        for (int i = 0; i < NX; ++i)
+          f[((size_t)k * n2y + j) * n2x + i] = rhs[c * ncell + ((size_t)k * NY + j) * NX + i];
+    fft3_ref(f, n2z, n2y, n2x, -1);
+    for (int k = 0; k < n2z; ++k)
+      for (int j = 0; j < n2y; ++j)
+        for (int i = 0; i < n2x; ++i) {
+          const int fk = k <= NZ ? k : n2z - k, fj = j <= NY ? j : n2y - j, fi = i <= NX ? i : n2x - i;
+          f[((size_t)k * n2y + j) * n2x + i] *= gfull[((size_t)fk * (NY + 1) + fj) * (NX + 1) + fi];
+        }
+    fft3_ref(f, n2z, n2y, n2x, +1);
+    for (int k = 0; k < NZ; ++k)
+      for (int j = 0; j < NY; ++j)
+        for (int i = 0; i < NX; ++i) {
+          // reference inverse is unnormalised by 8N; the pipeline by NX*2NY*2NZ = 4N
+          const double r = f[((size_t)k * n2y + j) * n2x + i].real() / ((double)n2x * n2y * n2z);
+          const double s = sol[c * ncell + ((size_t)k * NY + j) * NX + i] * scale;
+          err2 += (r - s) * (r - s);
+          ref2 += r * r;
+        }
+  }
+  const double rel = sqrt(err2 / ref2);
+  printf("grid (%d,%d,%d): LX=%d LY=%d LZ=%d rel L2 err = %.3e %s\n", NZ, NY, NX, LX, LY, LZ, rel,
+         rel < 2e-6 ? "ok" : "FAIL");
+  return rel < 2e-6 ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
+  const bool full = argc > 1 && argv[1][0] == 'f';
+  int bad = 0;
+  bad += run_case<8, 8, 16>();     // L = 16 everywhere
+  bad += run_case<16, 32, 64>();   // 32, 64, 64
+  bad += run_case<8, 64, 128>();   // 16, 128, 128
+  bad += run_case<128, 8, 16>();   // 256 (z)
+  if (full) {                      // minutes on one core: every remaining decomposition, incl. three-pass 2048
+    bad += run_case<64, 128, 256>();
+    bad += run_case<256, 8, 512>();
+    bad += run_case<8, 512, 1024>();
+    bad += run_case<1024, 8, 2048>();
+  }
+  printf(bad ? "FAILED\n" : "ALL OK\n");
+  return bad;
+}

@@ -330,6 +330,36 @@ int sopht_ib_virtual_boundary_forcing(int dtype, int dim, const sopht_field_t *e
                                       double eul_grid_coord_shift, double weight_prefactor,
                                       double dx_pow_dim, double stiffness, double damping, void *stream);
 
+/* ------------------------------------------------------------------------ */
+/* Fused passes of the 3-D Navier-Stokes step (simulator-level path).         */
+/* Vector fields (3, nz, ny, nx) with unit x-stride; outputs must not alias   */
+/* inputs (neighbouring cells are read).                                      */
+/* ------------------------------------------------------------------------ */
+
+/* out = w + prefactor * curl_c(u x w) on the ring-1 interior, out = w on the ring: the cross product and the
+ * vorticity update of the rotational-form advection in one pass.
+ * ref: simulator/flow/navier_stokes_flow_simulators.py:454-465
+ *      (elementwise_ops_3d.py:390-449 + update_vorticity_from_velocity_forcing_3d.py:12-132) */
+int sopht_ns3d_advect_rotational(int dtype, const sopht_field_t *out_vorticity_field,
+                                 const sopht_field_t *vorticity_field,
+                                 const sopht_field_t *velocity_field, double prefactor, void *stream);
+
+/* out = f + nu_dt_by_dx2 * Lap_7pt(f) on the ring-1 interior, out = f on the ring, all three components;
+ * zero_field (may be NULL) is set to 0 in the same pass (the forcing-field reset of the forced step).
+ * ref: navier_stokes_flow_simulators.py:466-471, :498; stencil_ops_3d/diffusion_timestep_3d.py:12-80 */
+int sopht_ns3d_diffuse(int dtype, const sopht_field_t *out_field, const sopht_field_t *field,
+                       double nu_dt_by_dx2, const sopht_field_t *zero_field, void *stream);
+
+/* velocity = prefactor * curl_c(psi) (ring <- 0) + free_stream_velocity (HOST array of 3, may be NULL);
+ * if max_abs_sum_out (device pointer to one element of dtype) is not NULL it receives max_cells sum_c |u_c|,
+ * the reduction the stable-timestep estimate needs.
+ * ref: navier_stokes_flow_simulators.py:479-485 (curl_3d.py:13-132, elementwise_ops_3d.py:305-329),
+ *      passive_transport_flow_simulators.py:139-155 */
+int sopht_ns3d_velocity_from_stream_function(int dtype, const sopht_field_t *velocity_field,
+                                             const sopht_field_t *stream_func_field, double prefactor,
+                                             const double *free_stream_velocity, void *max_abs_sum_out,
+                                             void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -125,6 +125,10 @@ _HANDLE_SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "sopht_poisson_green_hat": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
     "sopht_poisson_path": (ctypes.c_char_p, [_P]),
     "sopht_poisson_destroy": (ctypes.c_int, [_P]),
+    # fused 3-D Navier-Stokes passes
+    "sopht_ns3d_advect_rotational": (ctypes.c_int, [_I, _F, _F, _F, _D, _P]),
+    "sopht_ns3d_diffuse": (ctypes.c_int, [_I, _F, _F, _D, _F, _P]),
+    "sopht_ns3d_velocity_from_stream_function": (ctypes.c_int, [_I, _F, _F, _D, _PD, _P, _P]),
     # immersed boundary (int dtype, int dim, ...)
     "sopht_ib_local_support": (ctypes.c_int, [_I, _I, _F, _F, _F, _I, _D, _D, _P]),
     "sopht_ib_interpolation_weights": (ctypes.c_int, [_I, _I, _I, _F, _F, _D, _D, _P]),

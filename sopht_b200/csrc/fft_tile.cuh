@@ -324,5 +324,45 @@ FFT_HD void inv_last(Acc sm, int t, const float2* __restrict__ tw, Store st) {
   }
 }
 
+
+// ---- which elements a thread consumes in its first pass (used to prefetch exactly those) -----------------
+template <int L, class F>
+FFT_HD void fwd_first_elems(int t, F f) {  // f(position e), e < L/2
+  using C = Cfg<L>;
+  constexpr int R = C::R1, S = L / R, NB = C::E / R;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int j = t + q * C::T;
+#pragma unroll
+    for (int n = 0; n < R / 2; ++n) f(n * S + j);
+  }
+}
+template <int L, class F>
+FFT_HD void inv_first_elems(int t, F f) {  // f(spectrum index k)
+  using C = Cfg<L>;
+  constexpr int R = C::RLAST, NB = C::E / R;
+#pragma unroll
+  for (int q = 0; q < NB; ++q) {
+    const int blk = t + q * C::T;
+#pragma unroll
+    for (int k = 0; k < R; ++k) f(spectrum_index<L>(blk, k));
+  }
+}
+
+// 8-byte asynchronous global -> shared copy (cp.async / LDGSTS); a plain copy in the host emulation
+FFT_HD void async_copy8(float2* smem_dst, const float2* gsrc) {
+#ifdef __CUDA_ARCH__
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+#else
+  *smem_dst = *gsrc;
+#endif
+}
+FFT_HD void async_commit_wait_all() {
+#ifdef __CUDA_ARCH__
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+#endif
+}
+
 }  // namespace fft
 }  // namespace sopht

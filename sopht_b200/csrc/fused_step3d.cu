@@ -1,0 +1,466 @@
+// Fused stencil passes of the 3-D Navier-Stokes step (the simulator-level path; the one-op-per-kernel
+// versions behind the public factories live in stencils3d.cu / elementwise.cu).
+//
+//   advect   : out = w + p * curl_c(u x w)            (cross product recomputed on the fly at the 6 neighbours,
+//              the reference's buffer_vector_field round trip disappears)   24 B read + 12 B written per cell
+//   diffuse  : out = f + q * Lap_7pt(f), optionally forcing_field <- 0 in the same pass   4+4 (+4) B per cell/comp
+//   velocity : u = p * curl_c(psi) (ring <- 0) + U_inf, max_cells sum_c |u_c| reduced on the device  12 + 12 B
+//
+// All three are z-marching kernels: a CTA owns a TX x TY patch of (x, y) columns and walks a chunk of z
+// planes. The raw fields of the incoming plane (patch + 1-cell halo) are staged in a double-buffered
+// shared-memory tile with coalesced loads; x/y neighbours come from that tile, z neighbours of a thread's own
+// column ride in registers. Ghost-ring rule of the reference's generated kernels: only cells with all
+// indices in [1, n-2] are updated, ring cells keep (advect, diffuse) or zero (velocity) their value.
+//
+// ref: sopht/simulator/flow/navier_stokes_flow_simulators.py:449-498 (step order),
+//      stencil_ops_3d/{elementwise_ops_3d.py:390-449, update_vorticity_from_velocity_forcing_3d.py:12-132,
+//      diffusion_timestep_3d.py:12-80, curl_3d.py:13-132}, passive_transport_flow_simulators.py:139-155
+#include "common.cuh"
+
+namespace sopht {
+
+namespace {
+
+// output patch per CTA (= threads), staged tile = patch + 1-cell halo; fp64 halves the x extent to stay
+// inside the 48 KB static shared-memory window
+template <typename T>
+struct Tile {
+  static constexpr int TX = sizeof(T) == 4 ? 64 : 32, TY = 8;
+  static constexpr int SX = TX + 2, SY = TY + 2, THREADS = TX * TY;
+};
+#define FTX (Tile<T>::TX)
+#define FTY (Tile<T>::TY)
+#define FSX (Tile<T>::SX)
+#define FSY (Tile<T>::SY)
+#define FTHREADS (Tile<T>::THREADS)
+
+template <typename T>
+struct Vec3View {
+  const T* p[3];
+  int64_t sz, sy;  // x stride is 1 (checked on the host)
+};
+template <typename T>
+struct Vec3Out {
+  T* p[3];
+  int64_t sz, sy;
+};
+
+// stage plane k of NF fields (patch + halo, zero outside the grid) into s[NF][FSY][FSX]
+template <typename T, int NF>
+__device__ __forceinline__ void load_plane(T (*s)[FSY][FSX], const T* const* f, int64_t sz, int64_t sy,
+                                           int k, int x0, int y0, int ny, int nx) {
+  const int tid = threadIdx.y * FTX + threadIdx.x;
+#pragma unroll 1
+  for (int q = tid; q < FSX * FSY; q += FTHREADS) {
+    const int ly = q / FSX, lx = q - ly * FSX;
+    const int gy = y0 - 1 + ly, gx = x0 - 1 + lx;
+    const bool in = gy >= 0 && gy < ny && gx >= 0 && gx < nx;
+    const int64_t o = (int64_t)k * sz + (int64_t)gy * sy + gx;
+#pragma unroll
+    for (int c = 0; c < NF; ++c) s[c][ly][lx] = in ? __ldg(f[c] + o) : T(0);
+  }
+}
+
+template <typename T>
+struct AtomicMaxNonNeg;  // max of non-negative floats through their (order-preserving) bit patterns
+template <>
+struct AtomicMaxNonNeg<float> {
+  __device__ static void apply(float* a, float v) { atomicMax(reinterpret_cast<int*>(a), __float_as_int(v)); }
+};
+template <>
+struct AtomicMaxNonNeg<double> {
+  __device__ static void apply(double* a, double v) {
+    atomicMax(reinterpret_cast<long long*>(a), __double_as_longlong(v));
+  }
+};
+
+// ---- advect: out = w + p * curl_c(u x w) --------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(FTHREADS, 2)
+    advect_rotational_kernel(Vec3Out<T> out, Vec3View<T> w, Vec3View<T> u, T p, int nz, int ny, int nx,
+                             int kchunk) {
+  __shared__ T s[2][6][FSY][FSX];  // fields: 0..2 = u, 3..5 = w
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int x0 = blockIdx.x * FTX, y0 = blockIdx.y * FTY;
+  const int i = x0 + tx, j = y0 + ty;
+  const int k0 = blockIdx.z * kchunk, k1 = min(k0 + kchunk, nz);
+  const T* f[6] = {u.p[0], u.p[1], u.p[2], w.p[0], w.p[1], w.p[2]};
+  const bool own = i < nx && j < ny;
+  const bool inner_xy = i >= 1 && i < nx - 1 && j >= 1 && j < ny - 1;
+  const int cy = ty + 1, cx = tx + 1;
+
+  T bprev_x = T(0), bprev_y = T(0);
+  if (k0 > 0 && own) {
+    const int64_t o = (int64_t)(k0 - 1) * w.sz + (int64_t)j * w.sy + i;
+    const T ux = __ldg(u.p[0] + o), uy = __ldg(u.p[1] + o), uz = __ldg(u.p[2] + o);
+    const T wx = __ldg(w.p[0] + o), wy = __ldg(w.p[1] + o), wz = __ldg(w.p[2] + o);
+    bprev_x = uy * wz - wy * uz;
+    bprev_y = uz * wx - wz * ux;
+  }
+  int cur = 0;
+  load_plane<T, 6>(s[cur], f, w.sz, w.sy, k0, x0, y0, ny, nx);
+  __syncthreads();
+  T bcur_x, bcur_y;
+  {
+    const T ux = s[cur][0][cy][cx], uy = s[cur][1][cy][cx], uz = s[cur][2][cy][cx];
+    const T wx = s[cur][3][cy][cx], wy = s[cur][4][cy][cx], wz = s[cur][5][cy][cx];
+    bcur_x = uy * wz - wy * uz;
+    bcur_y = uz * wx - wz * ux;
+  }
+  for (int k = k0; k < k1; ++k) {
+    const int nxt = cur ^ 1;
+    T bnext_x = T(0), bnext_y = T(0);
+    if (k + 1 < nz) {
+      load_plane<T, 6>(s[nxt], f, w.sz, w.sy, k + 1, x0, y0, ny, nx);
+      __syncthreads();
+      const T ux = s[nxt][0][cy][cx], uy = s[nxt][1][cy][cx], uz = s[nxt][2][cy][cx];
+      const T wx = s[nxt][3][cy][cx], wy = s[nxt][4][cy][cx], wz = s[nxt][5][cy][cx];
+      bnext_x = uy * wz - wy * uz;
+      bnext_y = uz * wx - wz * ux;
+    }
+    if (own) {
+      T ox = s[cur][3][cy][cx], oy = s[cur][4][cy][cx], oz = s[cur][5][cy][cx];
+      if (inner_xy && k >= 1 && k < nz - 1) {
+        // b = u x w at the four in-plane neighbours (only the components the curl needs)
+#define U_(c, yy, xx) s[cur][c][yy][xx]
+#define W_(c, yy, xx) s[cur][3 + c][yy][xx]
+#define BX_(yy, xx) (U_(1, yy, xx) * W_(2, yy, xx) - W_(1, yy, xx) * U_(2, yy, xx))
+#define BY_(yy, xx) (U_(2, yy, xx) * W_(0, yy, xx) - W_(2, yy, xx) * U_(0, yy, xx))
+#define BZ_(yy, xx) (U_(0, yy, xx) * W_(1, yy, xx) - W_(0, yy, xx) * U_(1, yy, xx))
+        const T bz_jp = BZ_(cy + 1, cx), bz_jm = BZ_(cy - 1, cx);
+        const T bz_ip = BZ_(cy, cx + 1), bz_im = BZ_(cy, cx - 1);
+        const T by_ip = BY_(cy, cx + 1), by_im = BY_(cy, cx - 1);
+        const T bx_jp = BX_(cy + 1, cx), bx_jm = BX_(cy - 1, cx);
+#undef U_
+#undef W_
+#undef BX_
+#undef BY_
+#undef BZ_
+        const T ccx = bz_jp - bz_jm - bnext_y + bprev_y;
+        const T ccy = bnext_x - bprev_x - bz_ip + bz_im;
+        const T ccz = by_ip - by_im - bx_jp + bx_jm;
+        ox = ox + p * ccx;
+        oy = oy + p * ccy;
+        oz = oz + p * ccz;
+      }
+      const int64_t o = (int64_t)k * out.sz + (int64_t)j * out.sy + i;
+      out.p[0][o] = ox;
+      out.p[1][o] = oy;
+      out.p[2][o] = oz;
+    }
+    bprev_x = bcur_x, bprev_y = bcur_y;
+    bcur_x = bnext_x, bcur_y = bnext_y;
+    cur = nxt;
+    __syncthreads();
+  }
+}
+
+// ---- diffuse: out = f + q * Lap(f); blockIdx.z = chunk * ncomp + comp ------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(FTHREADS, 2)
+    diffuse_kernel(Vec3Out<T> out, Vec3View<T> in, Vec3Out<T> zero, int has_zero, int ncomp, T q, int nz,
+                   int ny, int nx, int kchunk) {
+  __shared__ T s[2][1][FSY][FSX];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int x0 = blockIdx.x * FTX, y0 = blockIdx.y * FTY;
+  const int i = x0 + tx, j = y0 + ty;
+  const int comp = blockIdx.z % ncomp, chunk = blockIdx.z / ncomp;
+  const int k0 = chunk * kchunk, k1 = min(k0 + kchunk, nz);
+  const T* f[1] = {comp == 0 ? in.p[0] : (comp == 1 ? in.p[1] : in.p[2])};
+  T* o_p = comp == 0 ? out.p[0] : (comp == 1 ? out.p[1] : out.p[2]);
+  T* z_p = comp == 0 ? zero.p[0] : (comp == 1 ? zero.p[1] : zero.p[2]);
+  const bool own = i < nx && j < ny;
+  const bool inner_xy = i >= 1 && i < nx - 1 && j >= 1 && j < ny - 1;
+  const int cy = ty + 1, cx = tx + 1;
+  const int64_t col = (int64_t)j * in.sy + i;
+
+  T fprev = (k0 > 0 && own) ? __ldg(f[0] + (int64_t)(k0 - 1) * in.sz + col) : T(0);
+  int cur = 0;
+  load_plane<T, 1>(s[cur], f, in.sz, in.sy, k0, x0, y0, ny, nx);
+  __syncthreads();
+  T fcur = s[cur][0][cy][cx];
+  for (int k = k0; k < k1; ++k) {
+    const int nxt = cur ^ 1;
+    T fnext = T(0);
+    if (k + 1 < nz) {
+      load_plane<T, 1>(s[nxt], f, in.sz, in.sy, k + 1, x0, y0, ny, nx);
+      __syncthreads();
+      fnext = s[nxt][0][cy][cx];
+    }
+    if (own) {
+      T v = fcur;
+      if (inner_xy && k >= 1 && k < nz - 1) {
+        const T flux = q * (fnext + fprev + s[cur][0][cy + 1][cx] + s[cur][0][cy - 1][cx] +
+                            s[cur][0][cy][cx + 1] + s[cur][0][cy][cx - 1] - T(6) * fcur);
+        v = fcur + flux;
+      }
+      o_p[(int64_t)k * out.sz + (int64_t)j * out.sy + i] = v;
+      if (has_zero) z_p[(int64_t)k * zero.sz + (int64_t)j * zero.sy + i] = T(0);
+    }
+    fprev = fcur;
+    fcur = fnext;
+    cur = nxt;
+    __syncthreads();
+  }
+}
+
+// ---- velocity: u = p * curl_c(psi) on the interior, 0 on the ring, + U_inf; max sum_c |u_c| --------------
+template <typename T>
+__global__ void __launch_bounds__(FTHREADS, 2)
+    velocity_from_psi_kernel(Vec3Out<T> out, Vec3View<T> psi, T p, T fx, T fy, T fz, T* max_out, int nz,
+                             int ny, int nx, int kchunk) {
+  __shared__ T s[2][3][FSY][FSX];
+  __shared__ T wmax[FTHREADS / 32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int x0 = blockIdx.x * FTX, y0 = blockIdx.y * FTY;
+  const int i = x0 + tx, j = y0 + ty;
+  const int k0 = blockIdx.z * kchunk, k1 = min(k0 + kchunk, nz);
+  const T* f[3] = {psi.p[0], psi.p[1], psi.p[2]};
+  const bool own = i < nx && j < ny;
+  const bool inner_xy = i >= 1 && i < nx - 1 && j >= 1 && j < ny - 1;
+  const int cy = ty + 1, cx = tx + 1;
+  const int64_t col = (int64_t)j * psi.sy + i;
+
+  T pprev_x = T(0), pprev_y = T(0);
+  if (k0 > 0 && own) {
+    pprev_x = __ldg(f[0] + (int64_t)(k0 - 1) * psi.sz + col);
+    pprev_y = __ldg(f[1] + (int64_t)(k0 - 1) * psi.sz + col);
+  }
+  int cur = 0;
+  load_plane<T, 3>(s[cur], f, psi.sz, psi.sy, k0, x0, y0, ny, nx);
+  __syncthreads();
+  T pcur_x = s[cur][0][cy][cx], pcur_y = s[cur][1][cy][cx];
+  T m = T(0);
+  for (int k = k0; k < k1; ++k) {
+    const int nxt = cur ^ 1;
+    T pnext_x = T(0), pnext_y = T(0);
+    if (k + 1 < nz) {
+      load_plane<T, 3>(s[nxt], f, psi.sz, psi.sy, k + 1, x0, y0, ny, nx);
+      __syncthreads();
+      pnext_x = s[nxt][0][cy][cx];
+      pnext_y = s[nxt][1][cy][cx];
+    }
+    if (own) {
+      T ux = T(0), uy = T(0), uz = T(0);
+      if (inner_xy && k >= 1 && k < nz - 1) {
+        const T ccx = s[cur][2][cy + 1][cx] - s[cur][2][cy - 1][cx] - pnext_y + pprev_y;
+        const T ccy = pnext_x - pprev_x - s[cur][2][cy][cx + 1] + s[cur][2][cy][cx - 1];
+        const T ccz = s[cur][1][cy][cx + 1] - s[cur][1][cy][cx - 1] - s[cur][0][cy + 1][cx] + s[cur][0][cy - 1][cx];
+        ux = p * ccx;
+        uy = p * ccy;
+        uz = p * ccz;
+      }
+      ux = ux + fx;
+      uy = uy + fy;
+      uz = uz + fz;
+      const int64_t o = (int64_t)k * out.sz + (int64_t)j * out.sy + i;
+      out.p[0][o] = ux;
+      out.p[1][o] = uy;
+      out.p[2][o] = uz;
+      const T a = fabs(ux) + fabs(uy) + fabs(uz);
+      m = a > m ? a : m;
+    }
+    pprev_x = pcur_x, pprev_y = pcur_y;
+    pcur_x = pnext_x, pcur_y = pnext_y;
+    cur = nxt;
+    __syncthreads();
+  }
+  if (max_out) {
+    for (int off = 16; off > 0; off >>= 1) {
+      const T o = __shfl_xor_sync(0xffffffffu, m, off);
+      m = o > m ? o : m;
+    }
+    const int tid = ty * FTX + tx;
+    if ((tid & 31) == 0) wmax[tid >> 5] = m;
+    __syncthreads();
+    if (tid < 32) {
+      m = tid < FTHREADS / 32 ? wmax[tid] : T(0);
+      for (int off = 16; off > 0; off >>= 1) {
+        const T o = __shfl_xor_sync(0xffffffffu, m, off);
+        m = o > m ? o : m;
+      }
+      if (tid == 0) AtomicMaxNonNeg<T>::apply(max_out, m);
+    }
+  }
+}
+
+// ---- host side --------------------------------------------------------------------------------------
+int check_vec3(const char* fn, const sopht_field_t* f) {
+  if (!valid_field(f, 4, 4) || f->shape[0] != 3)
+    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: expected (3, nz, ny, nx) fields", fn);
+  if (f->stride[3] != 1 && f->shape[3] > 1)
+    SOPHT_FAIL(SOPHT_ERR_STRIDE, "%s: fused kernels need unit x-stride fields", fn);
+  for (int d = 1; d < 4; ++d)
+    if (f->shape[d] > 0x7fffffff) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", fn);
+  return SOPHT_OK;
+}
+
+template <typename T>
+Vec3View<T> in_view(const sopht_field_t* f) {
+  Vec3View<T> v;
+  for (int c = 0; c < 3; ++c) v.p[c] = reinterpret_cast<const T*>(f->data) + c * f->stride[0];
+  v.sz = f->stride[1];
+  v.sy = f->stride[2];
+  return v;
+}
+template <typename T>
+Vec3Out<T> out_view(const sopht_field_t* f) {
+  Vec3Out<T> v;
+  for (int c = 0; c < 3; ++c) v.p[c] = reinterpret_cast<T*>(f->data) + c * f->stride[0];
+  v.sz = f->stride[1];
+  v.sy = f->stride[2];
+  return v;
+}
+
+bool overlaps(const sopht_field_t* a, const sopht_field_t* b, size_t elem) {
+  auto span = [&](const sopht_field_t* f, const char** lo, const char** hi) {
+    int64_t last = 0;
+    for (int d = 0; d < f->ndim; ++d) last += (f->shape[d] - 1) * f->stride[d];
+    *lo = reinterpret_cast<const char*>(f->data);
+    *hi = *lo + (last + 1) * elem;
+  };
+  const char *alo, *ahi, *blo, *bhi;
+  span(a, &alo, &ahi);
+  span(b, &blo, &bhi);
+  return alo < bhi && blo < ahi;
+}
+
+// z chunking: enough CTAs for >= ~4 waves of 2 CTAs/SM, chunks of at least 8 planes
+int pick_kchunk(int nz, int ny, int nx, int ncomp_grids, int tx, int ty) {
+  const int64_t xy = (int64_t)((nx + tx - 1) / tx) * ((ny + ty - 1) / ty) * ncomp_grids;
+  int64_t chunks = (148 * 2 * 4 + xy - 1) / xy;
+  if (chunks < 1) chunks = 1;
+  int kchunk = (int)((nz + chunks - 1) / chunks);
+  if (kchunk < 8) kchunk = 8;
+  if (kchunk > nz) kchunk = nz;
+  return kchunk;
+}
+
+#undef FTX
+#undef FTY
+#undef FSX
+#undef FSY
+#undef FTHREADS
+
+}  // namespace
+}  // namespace sopht
+
+using namespace sopht;
+
+#define RETURN_IF(rc_expr) \
+  do {                     \
+    int rc__ = (rc_expr);  \
+    if (rc__) return rc__; \
+  } while (0)
+
+extern "C" {
+
+int sopht_ns3d_advect_rotational(int dtype, const sopht_field_t* out_vorticity_field,
+                                 const sopht_field_t* vorticity_field,
+                                 const sopht_field_t* velocity_field, double prefactor, void* stream) {
+  SOPHT_CHECK_DTYPE(dtype);
+  RETURN_IF(check_vec3(__func__, out_vorticity_field));
+  RETURN_IF(check_vec3(__func__, vorticity_field));
+  RETURN_IF(check_vec3(__func__, velocity_field));
+  if (!same_shape(out_vorticity_field, vorticity_field) || !same_shape(out_vorticity_field, velocity_field))
+    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: field shapes differ", __func__);
+  if (vorticity_field->stride[1] != velocity_field->stride[1] ||
+      vorticity_field->stride[2] != velocity_field->stride[2])
+    SOPHT_FAIL(SOPHT_ERR_STRIDE, "%s: vorticity and velocity must share their plane/row strides", __func__);
+  const size_t elem = dtype == SOPHT_F32 ? 4 : 8;
+  if (overlaps(out_vorticity_field, vorticity_field, elem) || overlaps(out_vorticity_field, velocity_field, elem))
+    SOPHT_FAIL(SOPHT_ERR_ARG, "%s: the output must not alias an input (neighbours are read)", __func__);
+  const int nz = (int)vorticity_field->shape[1], ny = (int)vorticity_field->shape[2],
+            nx = (int)vorticity_field->shape[3];
+  if ((int64_t)nz * ny * nx == 0) return SOPHT_OK;
+  const int tx = dtype == SOPHT_F32 ? Tile<float>::TX : Tile<double>::TX, ty = Tile<float>::TY;
+  const int kchunk = pick_kchunk(nz, ny, nx, 1, tx, ty);
+  dim3 grid((nx + tx - 1) / tx, (ny + ty - 1) / ty, (nz + kchunk - 1) / kchunk), block(tx, ty, 1);
+  if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == SOPHT_F32)
+    advect_rotational_kernel<float><<<grid, block, 0, st>>>(
+        out_view<float>(out_vorticity_field), in_view<float>(vorticity_field), in_view<float>(velocity_field),
+        (float)prefactor, nz, ny, nx, kchunk);
+  else
+    advect_rotational_kernel<double><<<grid, block, 0, st>>>(
+        out_view<double>(out_vorticity_field), in_view<double>(vorticity_field),
+        in_view<double>(velocity_field), prefactor, nz, ny, nx, kchunk);
+  SOPHT_CHECK_LAUNCH();
+  return SOPHT_OK;
+}
+
+int sopht_ns3d_diffuse(int dtype, const sopht_field_t* out_field, const sopht_field_t* field,
+                       double nu_dt_by_dx2, const sopht_field_t* zero_field, void* stream) {
+  SOPHT_CHECK_DTYPE(dtype);
+  RETURN_IF(check_vec3(__func__, out_field));
+  RETURN_IF(check_vec3(__func__, field));
+  if (!same_shape(out_field, field)) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: field shapes differ", __func__);
+  const size_t elem = dtype == SOPHT_F32 ? 4 : 8;
+  if (overlaps(out_field, field, elem))
+    SOPHT_FAIL(SOPHT_ERR_ARG, "%s: the output must not alias the input (neighbours are read)", __func__);
+  if (zero_field) {
+    RETURN_IF(check_vec3(__func__, zero_field));
+    if (!same_shape(zero_field, field)) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: field shapes differ", __func__);
+    if (overlaps(zero_field, field, elem) || overlaps(zero_field, out_field, elem))
+      SOPHT_FAIL(SOPHT_ERR_ARG, "%s: the field to zero must not alias input or output", __func__);
+  }
+  const int nz = (int)field->shape[1], ny = (int)field->shape[2], nx = (int)field->shape[3];
+  if ((int64_t)nz * ny * nx == 0) return SOPHT_OK;
+  const int tx = dtype == SOPHT_F32 ? Tile<float>::TX : Tile<double>::TX, ty = Tile<float>::TY;
+  const int kchunk = pick_kchunk(nz, ny, nx, 3, tx, ty);
+  const int nchunk = (nz + kchunk - 1) / kchunk;
+  dim3 grid((nx + tx - 1) / tx, (ny + ty - 1) / ty, nchunk * 3), block(tx, ty, 1);
+  if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
+  cudaStream_t st = as_stream(stream);
+  if (dtype == SOPHT_F32)
+    diffuse_kernel<float><<<grid, block, 0, st>>>(
+        out_view<float>(out_field), in_view<float>(field),
+        zero_field ? out_view<float>(zero_field) : out_view<float>(out_field), zero_field != nullptr, 3,
+        (float)nu_dt_by_dx2, nz, ny, nx, kchunk);
+  else
+    diffuse_kernel<double><<<grid, block, 0, st>>>(
+        out_view<double>(out_field), in_view<double>(field),
+        zero_field ? out_view<double>(zero_field) : out_view<double>(out_field), zero_field != nullptr, 3,
+        nu_dt_by_dx2, nz, ny, nx, kchunk);
+  SOPHT_CHECK_LAUNCH();
+  return SOPHT_OK;
+}
+
+int sopht_ns3d_velocity_from_stream_function(int dtype, const sopht_field_t* velocity_field,
+                                             const sopht_field_t* stream_func_field, double prefactor,
+                                             const double* free_stream_velocity, void* max_abs_sum_out,
+                                             void* stream) {
+  SOPHT_CHECK_DTYPE(dtype);
+  RETURN_IF(check_vec3(__func__, velocity_field));
+  RETURN_IF(check_vec3(__func__, stream_func_field));
+  if (!same_shape(velocity_field, stream_func_field))
+    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: field shapes differ", __func__);
+  const size_t elem = dtype == SOPHT_F32 ? 4 : 8;
+  if (overlaps(velocity_field, stream_func_field, elem))
+    SOPHT_FAIL(SOPHT_ERR_ARG, "%s: the output must not alias the input (neighbours are read)", __func__);
+  const int nz = (int)velocity_field->shape[1], ny = (int)velocity_field->shape[2],
+            nx = (int)velocity_field->shape[3];
+  if ((int64_t)nz * ny * nx == 0) return SOPHT_OK;
+  const double f0 = free_stream_velocity ? free_stream_velocity[0] : 0.0;
+  const double f1 = free_stream_velocity ? free_stream_velocity[1] : 0.0;
+  const double f2 = free_stream_velocity ? free_stream_velocity[2] : 0.0;
+  const int tx = dtype == SOPHT_F32 ? Tile<float>::TX : Tile<double>::TX, ty = Tile<float>::TY;
+  const int kchunk = pick_kchunk(nz, ny, nx, 1, tx, ty);
+  dim3 grid((nx + tx - 1) / tx, (ny + ty - 1) / ty, (nz + kchunk - 1) / kchunk), block(tx, ty, 1);
+  if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
+  cudaStream_t st = as_stream(stream);
+  if (max_abs_sum_out) SOPHT_CUDA(cudaMemsetAsync(max_abs_sum_out, 0, elem, st));
+  if (dtype == SOPHT_F32)
+    velocity_from_psi_kernel<float><<<grid, block, 0, st>>>(
+        out_view<float>(velocity_field), in_view<float>(stream_func_field), (float)prefactor, (float)f0,
+        (float)f1, (float)f2, reinterpret_cast<float*>(max_abs_sum_out), nz, ny, nx, kchunk);
+  else
+    velocity_from_psi_kernel<double><<<grid, block, 0, st>>>(
+        out_view<double>(velocity_field), in_view<double>(stream_func_field), prefactor, f0, f1, f2,
+        reinterpret_cast<double*>(max_abs_sum_out), nz, ny, nx, kchunk);
+  SOPHT_CHECK_LAUNCH();
+  return SOPHT_OK;
+}
+
+}  // extern "C"

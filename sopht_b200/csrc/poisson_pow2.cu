@@ -18,38 +18,83 @@ namespace sopht {
 
 namespace {
 
+// phases 1..P of kernel K, a barrier between consecutive phases (phase 0 is issued by the kernel loop)
 template <class K, int P>
 struct DevPhases {
-  __device__ __forceinline__ static void run(const typename K::Params& p, int it, float2* smem) {
-    DevPhases<K, P - 1>::run(p, it, smem);
-    if (P > 0) __syncthreads();
-    K::template phase<P>(p, blockIdx.x, blockIdx.y, it, threadIdx.x, smem);
+  __device__ __forceinline__ static void run(const typename K::Params& p, int bx, int by, int it,
+                                             float2* smem, const float2* stage) {
+    DevPhases<K, P - 1>::run(p, bx, by, it, smem, stage);
+    if (P > 1) __syncthreads();
+    K::template phase<P>(p, bx, by, it, threadIdx.x, smem, stage);
   }
 };
 template <class K>
-struct DevPhases<K, -1> {
-  __device__ __forceinline__ static void run(const typename K::Params&, int, float2*) {}
+struct DevPhases<K, 0> {
+  __device__ __forceinline__ static void run(const typename K::Params&, int, int, int, float2*, const float2*) {}
 };
 
+// cp.async staging pays when registers allow only one CTA per SM (32 elements per thread: radix-32 passes,
+// L >= 512 in the column kernels); kernels with several resident CTAs overlap load and compute through the
+// hardware scheduler instead (measured: staging costs them LSU/shared-memory wavefronts and time).
 template <class K>
-__global__ void __launch_bounds__(K::THREADS) p2_kernel(const typename K::Params p, int niter) {
+constexpr bool use_stage() {
+  return K::WANT_STAGE && sizeof(float2) * (size_t)(K::SMEM_ELEMS + K::STAGE_ELEMS) <= 200 * 1024;
+}
+
+// Persistent kernel: CTA b owns tiles b, b + gridDim.x, ... (neighbouring CTAs work on neighbouring tiles at
+// the same time, which keeps DRAM pages shared); all iterations (components) of a tile stay on one CTA.
+template <class K>
+__global__ void __launch_bounds__(K::THREADS) p2_kernel(const typename K::Params p, int gx, int gy) {
   extern __shared__ float2 p2_smem[];
-  for (int it = 0; it < niter; ++it) {
-    if (it) __syncthreads();
-    DevPhases<K, K::NPHASE - 1>::run(p, it, p2_smem);
+  constexpr bool STAGED = use_stage<K>();
+  float2* stage = STAGED ? p2_smem + K::SMEM_ELEMS : nullptr;
+  const int niter = K::niter(p);
+  const int64_t ntile = (int64_t)gx * gy;
+  int64_t s = blockIdx.x;
+  int it = 0;
+  if (s >= ntile) return;
+  if (STAGED) K::prefetch(p, (int)(s % gx), (int)(s / gx), 0, threadIdx.x, stage);
+  while (true) {
+    if (STAGED) {
+      fft::async_commit_wait_all();
+      if (K::STAGE_SHARED) __syncthreads();
+    }
+    const int bx = (int)(s % gx), by = (int)(s / gx);
+    int64_t ns = s;
+    int nit = it + 1;
+    if (nit == niter) {
+      nit = 0;
+      ns = s + gridDim.x;
+    }
+    const bool has_next = ns < ntile;
+    K::template phase<0>(p, bx, by, it, threadIdx.x, p2_smem, stage);
+    __syncthreads();
+    if (STAGED && has_next) K::prefetch(p, (int)(ns % gx), (int)(ns / gx), nit, threadIdx.x, stage);
+    DevPhases<K, K::NPHASE - 1>::run(p, bx, by, it, p2_smem, stage);
+    if (!has_next) break;
+    __syncthreads();
+    s = ns;
+    it = nit;
   }
 }
 
 template <class K>
-int launch(const typename K::Params& p, dim3 grid, int niter, cudaStream_t st) {
-  const size_t smem = sizeof(float2) * K::SMEM_ELEMS;
-  static bool configured = false;  // per kernel instantiation
-  if (!configured) {
+int launch(const typename K::Params& p, dim3 grid, int, cudaStream_t st) {
+  const size_t smem = sizeof(float2) * (K::SMEM_ELEMS + (use_stage<K>() ? K::STAGE_ELEMS : 0));
+  static int ctas_per_sm = 0, num_sm = 0;  // per kernel instantiation
+  if (!ctas_per_sm) {
     if (smem > 48 * 1024)
       SOPHT_CUDA(cudaFuncSetAttribute(p2_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    int dev = 0;
+    SOPHT_CUDA(cudaGetDevice(&dev));
+    SOPHT_CUDA(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
+    SOPHT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, p2_kernel<K>, K::THREADS, smem));
+    if (ctas_per_sm < 1) SOPHT_FAIL(SOPHT_ERR_CUDA, "poisson(pow2): kernel does not fit on an SM");
   }
-  p2_kernel<K><<<grid, K::THREADS, smem, st>>>(p, niter);
+  const int64_t ntile = (int64_t)grid.x * grid.y;
+  int64_t g = (int64_t)num_sm * ctas_per_sm;
+  if (g > ntile) g = ntile;
+  p2_kernel<K><<<(unsigned)g, K::THREADS, smem, st>>>(p, (int)grid.x, (int)grid.y);
   SOPHT_CHECK_LAUNCH();
   return SOPHT_OK;
 }

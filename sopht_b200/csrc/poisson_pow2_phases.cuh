@@ -13,6 +13,11 @@
 //   XInv : rows: Hermitian pre-processing -> inverse half-length FFT -> first nx reals -> solution
 // The kx = nx (Nyquist) plane travels as a separate small (C, nz, ny) array through the same Y/Z kernels
 // with different strides. ref: UnboundedPoissonSolverPYFFTW3D.py:111-149 (what is computed).
+//
+// Latency hiding: kernels are persistent (one CTA per SM slot loops over tiles). While a tile is in its
+// second..last phase, the FIRST-phase inputs of the CTA's next tile are already in flight as cp.async copies
+// into a staging buffer (`stage`), issued by the very threads that will consume them, so no registers are
+// held across the wait. prefetch() and phase<0>() must enumerate the same elements.
 #pragma once
 #include <stdint.h>
 
@@ -73,6 +78,25 @@ struct GlobalStore {
   FFT_HD void operator()(int e, float2 v) const { p[e * rs] = v; }
 };
 
+// staged variants: the element was copied to stage[index * TX + col] by this thread's own cp.async
+template <int TX>
+struct StageLoad {
+  const float2* s;
+  FFT_HD float2 operator()(int e) const { return s[e * TX]; }
+};
+template <int TX>
+struct StageSrcIdx {
+  const float2* s;
+  FFT_HD float2 operator()(int k, int) const { return s[k * TX]; }
+};
+template <int TX>
+struct StageCopy {
+  float2* s;
+  const float2* g;
+  int64_t rs;
+  FFT_HD void operator()(int e) const { fft::async_copy8(s + e * TX, g + e * rs); }
+};
+
 template <int L, int TX>
 struct YFwd {
   using Params = ColParams;
@@ -80,13 +104,26 @@ struct YFwd {
   static constexpr int NPHASE = Cfg<L>::NP;
   static constexpr int NITER = 1;
   static constexpr int SMEM_ELEMS = ColAcc<L, TX>::ROWS * TX;
+  static constexpr int STAGE_ELEMS = (L / 2) * TX;
+  static constexpr bool STAGE_SHARED = false;  // a thread reads back only what it copied itself
+  static constexpr bool WANT_STAGE = Cfg<L>::E >= 32;
+  FFT_HD static int niter(const Params&) { return 1; }
+  FFT_HD static void prefetch(const Params& p, int bx, int by, int, int tid, float2* stage) {
+    const int col = tid % TX, t = tid / TX;
+    StageCopy<TX> cp{stage + col, p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, p.in_rs};
+    fft::fwd_first_elems<L>(t, cp);
+  }
   template <int P>
-  FFT_HD static void phase(const Params& p, int bx, int by, int, int tid, float2* smem) {
+  FFT_HD static void phase(const Params& p, int bx, int by, int, int tid, float2* smem, const float2* stage) {
     const int col = tid % TX, t = tid / TX;
     ColAcc<L, TX> sm{smem, col};
     if (P == 0) {
-      GlobalLoad ld{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, p.in_rs};
-      fft::fwd_first<L>(ld, sm, t, p.tw);
+      if (stage) {
+        fft::fwd_first<L>(StageLoad<TX>{stage + col}, sm, t, p.tw);
+      } else {
+        GlobalLoad ld{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, p.in_rs};
+        fft::fwd_first<L>(ld, sm, t, p.tw);
+      }
     } else if (P == NPHASE - 1) {
       GlobalStoreIdx st{p.out + bx * p.out_bx + by * p.out_by + col * p.out_cs, p.out_rs};
       fft::fwd_last<L>(sm, t, st);
@@ -103,13 +140,26 @@ struct YInv {
   static constexpr int NPHASE = Cfg<L>::NP;
   static constexpr int NITER = 1;
   static constexpr int SMEM_ELEMS = ColAcc<L, TX>::ROWS * TX;
+  static constexpr int STAGE_ELEMS = L * TX;
+  static constexpr bool STAGE_SHARED = false;
+  static constexpr bool WANT_STAGE = Cfg<L>::E >= 32;
+  FFT_HD static int niter(const Params&) { return 1; }
+  FFT_HD static void prefetch(const Params& p, int bx, int by, int, int tid, float2* stage) {
+    const int col = tid % TX, t = tid / TX;
+    StageCopy<TX> cp{stage + col, p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, p.in_rs};
+    fft::inv_first_elems<L>(t, cp);
+  }
   template <int P>
-  FFT_HD static void phase(const Params& p, int bx, int by, int, int tid, float2* smem) {
+  FFT_HD static void phase(const Params& p, int bx, int by, int, int tid, float2* smem, const float2* stage) {
     const int col = tid % TX, t = tid / TX;
     ColAcc<L, TX> sm{smem, col};
     if (P == 0) {
-      GlobalSrcIdx src{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, p.in_rs};
-      fft::inv_first<L>(src, sm, t);
+      if (stage) {
+        fft::inv_first<L>(StageSrcIdx<TX>{stage + col}, sm, t);
+      } else {
+        GlobalSrcIdx src{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, p.in_rs};
+        fft::inv_first<L>(src, sm, t);
+      }
     } else if (P == NPHASE - 1) {
       GlobalStore st{p.out + bx * p.out_bx + by * p.out_by + col * p.out_cs, p.out_rs};
       fft::inv_last<L>(sm, t, p.tw, st);
@@ -148,15 +198,29 @@ struct ZConv {
   static constexpr int THREADS = Cfg<L>::T * TX;
   static constexpr int NP = Cfg<L>::NP;
   static constexpr int NPHASE = 2 * NP - 1;  // fwd_first [fwd_mid] fused [inv_mid] inv_last
+  static constexpr int NITER = 0;            // runtime: ncomp
   static constexpr int SMEM_ELEMS = ColAcc<L, TX>::ROWS * TX;
+  static constexpr int STAGE_ELEMS = (L / 2) * TX;
+  static constexpr bool STAGE_SHARED = false;
+  static constexpr bool WANT_STAGE = Cfg<L>::E >= 32;
+  FFT_HD static int niter(const Params& p) { return p.ncomp; }
+  FFT_HD static void prefetch(const Params& p, int bx, int by, int c, int tid, float2* stage) {
+    const int col = tid % TX, t = tid / TX;
+    StageCopy<TX> cp{stage + col, p.data + bx * p.d_bx + by * p.d_by + c * p.d_c + col * p.cs, p.rs};
+    fft::fwd_first_elems<L>(t, cp);
+  }
   template <int P>
-  FFT_HD static void phase(const Params& p, int bx, int by, int c, int tid, float2* smem) {
+  FFT_HD static void phase(const Params& p, int bx, int by, int c, int tid, float2* smem, const float2* stage) {
     const int col = tid % TX, t = tid / TX;
     ColAcc<L, TX> sm{smem, col};
     float2* base = p.data + bx * p.d_bx + by * p.d_by + c * p.d_c + col * p.cs;
     if (P == 0) {
-      GlobalLoad ld{base, p.rs};
-      fft::fwd_first<L>(ld, sm, t, p.tw);
+      if (stage) {
+        fft::fwd_first<L>(StageLoad<TX>{stage + col}, sm, t, p.tw);
+      } else {
+        GlobalLoad ld{base, p.rs};
+        fft::fwd_first<L>(ld, sm, t, p.tw);
+      }
     } else if (P == NP - 1) {
       const int ky = p.nyq ? bx * TX + col : by;
       const int fky = ky <= p.n2y / 2 ? ky : p.n2y - ky;
@@ -214,18 +278,34 @@ struct XFwd {
   static constexpr int NPHASE = NP + 1;
   static constexpr int NITER = 1;
   static constexpr int SMEM_ELEMS = RowAcc<L>::PITCH * RX;
+  static constexpr int STAGE_ELEMS = (L / 2) * RX;
+  static constexpr bool STAGE_SHARED = false;
+  static constexpr bool WANT_STAGE = false;
+  FFT_HD static int niter(const Params&) { return 1; }
+  FFT_HD static const float2* row_ptr(const Params& p, const float* base, int64_t row) {
+    const int y = (int)(row % p.ny);
+    const int64_t cz = row / p.ny;
+    const int z = (int)(cz % p.nz);
+    const int64_t c = cz / p.nz;
+    return reinterpret_cast<const float2*>(base + c * p.sc + z * p.sz + y * p.sy);
+  }
+  FFT_HD static void prefetch(const Params& p, int bx, int, int, int tid, float2* stage) {
+    const int t = tid % T, r = tid / T;
+    StageCopy<1> cp{stage + r * (L / 2), row_ptr(p, p.real_in, (int64_t)bx * RX + r), 1};
+    fft::fwd_first_elems<L>(t, cp);
+  }
   template <int P>
-  FFT_HD static void phase(const Params& p, int bx, int, int, int tid, float2* smem) {
+  FFT_HD static void phase(const Params& p, int bx, int, int, int tid, float2* smem, const float2* stage) {
     const int t = tid % T, r = tid / T;
     const int64_t row = (int64_t)bx * RX + r;
     RowAcc<L> sm{smem + r * RowAcc<L>::PITCH};
     if (P == 0) {
-      const int y = (int)(row % p.ny);
-      const int64_t cz = row / p.ny;
-      const int z = (int)(cz % p.nz);
-      const int64_t c = cz / p.nz;
-      RowLoad ld{reinterpret_cast<const float2*>(p.real_in + c * p.sc + z * p.sz + y * p.sy)};
-      fft::fwd_first<L>(ld, sm, t, p.tw);
+      if (stage) {
+        fft::fwd_first<L>(StageLoad<1>{stage + r * (L / 2)}, sm, t, p.tw);
+      } else {
+        RowLoad ld{row_ptr(p, p.real_in, row)};
+        fft::fwd_first<L>(ld, sm, t, p.tw);
+      }
     } else if (P == NP - 1) {
       fft::fwd_last<L>(sm, t, InPlaceSink<L>{sm});
     } else if (P == NP) {
@@ -256,19 +336,33 @@ struct XInv {
   static constexpr int NPHASE = NP + 1;
   static constexpr int NITER = 1;
   static constexpr int SMEM_ELEMS = RowAcc<L>::PITCH * RX;
+  static constexpr int STAGE_ELEMS = (L + 1) * RX;  // spectrum row + its Nyquist bin
+  static constexpr bool STAGE_SHARED = true;        // bin k is combined with bin L-k, staged by another thread
+  static constexpr bool WANT_STAGE = false;
+  FFT_HD static int niter(const Params&) { return 1; }
+  FFT_HD static void prefetch(const Params& p, int bx, int, int, int tid, float2* stage) {
+    const int t = tid % T, r = tid / T;
+    const int64_t row = (int64_t)bx * RX + r;
+    const float2* in = p.spec + row * L;
+    float2* s = stage + r * (L + 1);
+#pragma unroll
+    for (int q = 0; q < Cfg<L>::E; ++q) fft::async_copy8(s + t + q * T, in + t + q * T);
+    if (t == 0) fft::async_copy8(s + L, p.nyq + row);
+  }
   template <int P>
-  FFT_HD static void phase(const Params& p, int bx, int, int, int tid, float2* smem) {
+  FFT_HD static void phase(const Params& p, int bx, int, int, int tid, float2* smem, const float2* stage) {
     const int t = tid % T, r = tid / T;
     const int64_t row = (int64_t)bx * RX + r;
     RowAcc<L> sm{smem + r * RowAcc<L>::PITCH};
     if (P == 0) {
       // Z_k = E_k + i O_k, E = (X_k + conj X_{L-k})/2, O = conj(w^k) (X_k - conj X_{L-k})/2
-      const float2* in = p.spec + row * L;
+      const float2* in = stage ? stage + r * (L + 1) : p.spec + row * L;
+      const float2* nq = stage ? stage + r * (L + 1) + L : p.nyq + row;
 #pragma unroll
       for (int q = 0; q < Cfg<L>::E; ++q) {
         const int k = t + q * T;
         const float2 a = in[k];
-        const float2 b = k == 0 ? p.nyq[row] : in[L - k];
+        const float2 b = k == 0 ? *nq : in[L - k];
         const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
         const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
         const float2 o = fft::cmul_conj(d, p.tw2[k]);
@@ -277,11 +371,7 @@ struct XInv {
     } else if (P == 1) {
       fft::inv_first<L>(InPlaceSrc<L>{sm}, sm, t);
     } else if (P == NPHASE - 1) {
-      const int y = (int)(row % p.ny);
-      const int64_t cz = row / p.ny;
-      const int z = (int)(cz % p.nz);
-      const int64_t c = cz / p.nz;
-      RowStore st{reinterpret_cast<float2*>(p.real_out + c * p.sc + z * p.sz + y * p.sy)};
+      RowStore st{const_cast<float2*>(XFwd<L, RX>::row_ptr(p, p.real_out, row))};
       fft::inv_last<L>(sm, t, p.tw, st);
     } else {
       fft::inv_mid<L>(sm, t, p.tw);

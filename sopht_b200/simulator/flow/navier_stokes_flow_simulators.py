@@ -12,6 +12,7 @@ sub-step is a CUDA kernel behind the C ABI. Two step implementations are kept:
 
 from __future__ import annotations
 
+import ctypes
 import logging
 from typing import Any, Literal
 
@@ -170,9 +171,53 @@ class UnboundedNavierStokesFlowSimulator3D(FlowSimulator):
         self._update_velocity_with_free_stream = update_velocity_with_free_stream
 
     def _finalise_flow_time_step(self) -> None:
+        self._dt_code = _lib.dtype_code(self.real_t)
+        self._vel_absmax = self._zeros(1)  # max_cells sum_c |u_c|, refreshed by the fused velocity pass
+        self._vel_absmax_version = None
+        if self.step_mode == "auto":
+            self.step_mode = "fused"
+        if self.step_mode == "fused":
+            self._flow_time_step = self._navier_stokes_fused_time_step
+            return
         self._flow_time_step = self._navier_stokes_time_step
         if self.with_forcing:
             self._flow_time_step = self._navier_stokes_with_forcing_time_step
+
+    def _navier_stokes_fused_time_step(self, dt: float, free_stream_velocity=(0.0, 0.0, 0.0)) -> None:
+        """The step of navier_stokes_flow_simulators.py:449-498 with its stencil sub-steps fused:
+
+        [forcing] w += dt/(2 dx rho) curl(f)                      (in place, f read at neighbours)
+        advect    buf = w + dt/(2 dx) curl(u x w)                 (cross product never stored)
+        diffuse   w = buf + nu dt/dx^2 Lap(buf)  [and f <- 0]
+        [filter], penalise, Poisson (pruned FFT pipeline)
+        velocity  u = curl(psi)/(2 dx) + U_inf, and max sum|u| for the next stable-dt estimate
+        """
+        rt, dc = self.real_t, self._dt_code
+        if self.with_forcing:
+            self._update_vorticity_from_velocity_forcing(
+                vorticity_field=self.vorticity_field, velocity_forcing_field=self.eul_grid_forcing_field,
+                prefactor=rt(dt / (2 * self.dx * self.flow_density)))
+        lib = _lib.load()
+        fd = _lib.field_desc
+        st = _lib.current_stream()
+        fw, fu, fb = fd(self.vorticity_field, dc), fd(self.velocity_field, dc), fd(self.buffer_vector_field, dc)
+        _lib.check(lib.sopht_ns3d_advect_rotational(
+            dc, ctypes.byref(fb), ctypes.byref(fw), ctypes.byref(fu), float(rt(dt / (2 * self.dx))), st))
+        ff = fd(self.eul_grid_forcing_field, dc) if self.with_forcing else None
+        _lib.check(lib.sopht_ns3d_diffuse(
+            dc, ctypes.byref(fw), ctypes.byref(fb),
+            float(rt(self.kinematic_viscosity * dt / self.dx / self.dx)),
+            ctypes.byref(ff) if ff is not None else None, st))
+        self._filter_vector_field(vector_field=self.vorticity_field)
+        self._penalise_field_towards_boundary(vector_field=self.vorticity_field)
+        self._unbounded_poisson_solver.vector_field_solve(
+            solution_vector_field=self.stream_func_field, rhs_vector_field=self.vorticity_field)
+        fpsi = fd(self.stream_func_field, dc)
+        fsv = _lib.double_array(free_stream_velocity, 3) if self.with_free_stream_flow else None
+        _lib.check(lib.sopht_ns3d_velocity_from_stream_function(
+            dc, ctypes.byref(fu), ctypes.byref(fpsi), float(rt(0.5 / self.dx)), fsv,
+            ctypes.c_void_p(self._vel_absmax.data_ptr()), st))
+        self._vel_absmax_version = self.velocity_field._version
 
     def _navier_stokes_time_step(self, dt: float, free_stream_velocity=(0.0, 0.0, 0.0)) -> None:
         """navier_stokes_flow_simulators.py:449-485."""
@@ -203,6 +248,15 @@ class UnboundedNavierStokesFlowSimulator3D(FlowSimulator):
         self._set_field(vector_field=self.eul_grid_forcing_field, fixed_vals=[0.0] * self.grid_dim)
 
     def compute_stable_timestep(self, dt_prefac: float = 1.0) -> float:
+        """Stable dt (navier_stokes_flow_simulators.py:501-512). After a fused step the velocity maximum is
+        already on the device (reduced inside the velocity pass), so only one scalar is read back; the
+        reference's side effect of leaving sum|u| in buffer_scalar_field is kept on the uncached path only."""
+        if (self._vel_absmax_version is not None
+                and self._vel_absmax_version == self.velocity_field._version):
+            dt = stable_timestep_from_max(
+                self.real_t(self._vel_absmax.item()), self.grid_dim, self.dx, self.cfl,
+                self.kinematic_viscosity, self.real_t)
+            return dt * dt_prefac
         dt = compute_advection_diffusion_stable_timestep(
             velocity_field=self.velocity_field, velocity_magnitude_field=self.buffer_scalar_field,
             grid_dim=self.grid_dim, dx=self.dx, cfl=self.cfl,

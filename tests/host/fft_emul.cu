@@ -16,24 +16,28 @@ using cd = std::complex<double>;
 
 template <class K, int P>
 struct PhaseLoop {
-  static void run(const typename K::Params& p, int bx, int by, int it, float2* smem) {
-    PhaseLoop<K, P - 1>::run(p, bx, by, it, smem);
-    for (int tid = 0; tid < K::THREADS; ++tid) K::template phase<P>(p, bx, by, it, tid, smem);
+  static void run(const typename K::Params& p, int bx, int by, int it, float2* smem, const float2* stage) {
+    PhaseLoop<K, P - 1>::run(p, bx, by, it, smem, stage);
+    for (int tid = 0; tid < K::THREADS; ++tid) K::template phase<P>(p, bx, by, it, tid, smem, stage);
   }
 };
 template <class K>
 struct PhaseLoop<K, -1> {
-  static void run(const typename K::Params&, int, int, int, float2*) {}
+  static void run(const typename K::Params&, int, int, int, float2*, const float2*) {}
 };
 
+// staged = true emulates the persistent kernel's cp.async prefetch into the staging buffer
 template <class K>
-void emulate(const typename K::Params& p, int gx, int gy, int niter) {
-  std::vector<float2> smem(K::SMEM_ELEMS);
+void emulate(const typename K::Params& p, int gx, int gy, int niter, bool staged = true) {
+  std::vector<float2> smem(K::SMEM_ELEMS), stage(K::STAGE_ELEMS);
   for (int by = 0; by < gy; ++by)
     for (int bx = 0; bx < gx; ++bx)
       for (int it = 0; it < niter; ++it) {
         for (auto& v : smem) v = make_float2(NAN, NAN);  // poison: catches reads of unwritten slots
-        PhaseLoop<K, K::NPHASE - 1>::run(p, bx, by, it, smem.data());
+        for (auto& v : stage) v = make_float2(NAN, NAN);
+        if (staged)
+          for (int tid = 0; tid < K::THREADS; ++tid) K::prefetch(p, bx, by, it, tid, stage.data());
+        PhaseLoop<K, K::NPHASE - 1>::run(p, bx, by, it, smem.data(), staged ? stage.data() : nullptr);
       }
 }
 

@@ -60,6 +60,12 @@ int sopht_version(void);
 /* number of kernel launches issued through this library since load (for bench accounting) */
 int64_t sopht_launch_count(void);
 
+/* Per-kernel CUDA-event timers around the instrumented launch sites (off by default; used by bench.py
+ * for the roofline of the dominant kernel). sopht_profile_report() synchronises the recorded events,
+ * clears them, and returns a JSON object {"label": {"launches": n, "ms": total}, ...} owned by the library. */
+int sopht_profile_enable(int on);
+const char *sopht_profile_report(void);
+
 /* ------------------------------------------------------------------------ */
 /* Elementwise operations on strided views (1..4-D, 2D and 3D grids alike)   */
 /* ------------------------------------------------------------------------ */

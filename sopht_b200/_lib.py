@@ -98,6 +98,10 @@ def load() -> ctypes.CDLL:
     lib.sopht_last_error.argtypes = []
     lib.sopht_version.restype = ctypes.c_int
     lib.sopht_launch_count.restype = ctypes.c_int64
+    lib.sopht_profile_enable.restype = ctypes.c_int
+    lib.sopht_profile_enable.argtypes = [ctypes.c_int]
+    lib.sopht_profile_report.restype = ctypes.c_char_p
+    lib.sopht_profile_report.argtypes = []
     for name, kinds in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
@@ -147,6 +151,8 @@ def exported_symbols() -> list[str]:
         "sopht_last_error",
         "sopht_version",
         "sopht_launch_count",
+        "sopht_profile_enable",
+        "sopht_profile_report",
         *_SIGNATURES.keys(),
         *_HANDLE_SIGNATURES.keys(),
     ]
@@ -154,6 +160,18 @@ def exported_symbols() -> list[str]:
 
 def launch_count() -> int:
     return int(load().sopht_launch_count())
+
+
+def profile_enable(on: bool) -> None:
+    """Switch the library's per-kernel CUDA-event timers on or off (include/sopht_b200.h)."""
+    load().sopht_profile_enable(1 if on else 0)
+
+
+def profile_report() -> dict:
+    """{label: {"launches": n, "ms": total}} of the launches recorded since the last report."""
+    import json
+
+    return json.loads(load().sopht_profile_report().decode())
 
 
 # -------------------------------------------------------------------------------------------------

@@ -41,6 +41,16 @@ extern int64_t g_launch_count;
                  cudaGetErrorString(e__));                                            \
   } while (0)
 
+// ---- optional per-kernel event timers (profile.cu) ---------------------------------------------
+extern bool g_prof_on;
+struct ProfScope {
+  ProfScope(const char* label, cudaStream_t st);
+  ~ProfScope();
+  cudaStream_t st_;
+  int idx_;
+};
+#define SOPHT_PROF(label, st) ::sopht::ProfScope prof_scope__(label, st)
+
 // ---- device-side views ----------------------------------------------------------------------
 // 3-D scalar view (z, y, x); strides in elements.
 template <typename T>

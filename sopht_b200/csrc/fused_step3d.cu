@@ -16,6 +16,7 @@
 //      stencil_ops_3d/{elementwise_ops_3d.py:390-449, update_vorticity_from_velocity_forcing_3d.py:12-132,
 //      diffusion_timestep_3d.py:12-80, curl_3d.py:13-132}, passive_transport_flow_simulators.py:139-155
 #include "common.cuh"
+#include "stream_vec.cuh"
 
 namespace sopht {
 
@@ -284,6 +285,292 @@ __global__ void __launch_bounds__(FTHREADS, 2)
   }
 }
 
+// ======================================================================================================
+// Register-marching versions (stream_vec.cuh): 16-byte vectors along x, no shared memory, no barriers.
+// Taken whenever nx, the row/plane strides and the base addresses are multiples of the vector width;
+// the shared-memory kernels above remain for every other view.
+// ======================================================================================================
+using sv::Vec;
+
+constexpr int VBY = 8;  // rows of a CTA: block = (32 lanes, VBY)
+
+template <typename T>
+__device__ __forceinline__ Vec<T> cross_x(const Vec<T>* u, const Vec<T>* w) {
+  Vec<T> r;
+#pragma unroll
+  for (int m = 0; m < Vec<T>::W; ++m) r.v[m] = u[1].v[m] * w[2].v[m] - w[1].v[m] * u[2].v[m];
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ Vec<T> cross_y(const Vec<T>* u, const Vec<T>* w) {
+  Vec<T> r;
+#pragma unroll
+  for (int m = 0; m < Vec<T>::W; ++m) r.v[m] = u[2].v[m] * w[0].v[m] - w[2].v[m] * u[0].v[m];
+  return r;
+}
+template <typename T>
+__device__ __forceinline__ Vec<T> cross_z(const Vec<T>* u, const Vec<T>* w) {
+  Vec<T> r;
+#pragma unroll
+  for (int m = 0; m < Vec<T>::W; ++m) r.v[m] = u[0].v[m] * w[1].v[m] - w[0].v[m] * u[1].v[m];
+  return r;
+}
+
+// out = w + p * curl_c(u x w). 24 B read + 12 B written per cell (fp32).
+template <typename T>
+__global__ void __launch_bounds__(32 * VBY, 2)
+    advect_vec_kernel(Vec3Out<T> out, Vec3View<T> w, Vec3View<T> u, T p, int nz, int ny, int nx, int kchunk) {
+  constexpr int W = Vec<T>::W;
+  const int lane = threadIdx.x;
+  const int i0 = (blockIdx.x * 32 + lane) * W;
+  const int j = blockIdx.y * VBY + threadIdx.y;
+  if (j >= ny) return;  // warp-uniform
+  const int k0 = blockIdx.z * kchunk, k1 = min(k0 + kchunk, nz);
+  const bool act = i0 < nx;
+  const bool jin = j >= 1 && j < ny - 1;
+  const bool has_l = lane == 0 && act && i0 > 0;
+  const bool has_r = lane == 31 && act && i0 + W < nx;
+  const int64_t col = (int64_t)j * w.sy + i0;  // u shares sz / sy with w (checked on the host)
+  const int64_t ocol = (int64_t)j * out.sy + i0;
+
+  Vec<T> uc[3], wc[3];
+  Vec<T> bprev_x = sv::vzero<T>(), bprev_y = sv::vzero<T>();
+  if (k0 > 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      uc[c] = sv::vload_if(act, u.p[c] + (int64_t)(k0 - 1) * w.sz + col);
+      wc[c] = sv::vload_if(act, w.p[c] + (int64_t)(k0 - 1) * w.sz + col);
+    }
+    bprev_x = cross_x(uc, wc);
+    bprev_y = cross_y(uc, wc);
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    uc[c] = sv::vload_if(act, u.p[c] + (int64_t)k0 * w.sz + col);
+    wc[c] = sv::vload_if(act, w.p[c] + (int64_t)k0 * w.sz + col);
+  }
+  Vec<T> bcur_x = cross_x(uc, wc), bcur_y = cross_y(uc, wc), bcur_z = cross_z(uc, wc);
+
+#pragma unroll 1
+  for (int k = k0; k < k1; ++k) {
+    const int64_t pl = (int64_t)k * w.sz + col;
+    // issue every load of this iteration first: next plane (centre), rows j+1 / j-1 and the two x edges
+    Vec<T> un[3], wn[3], uu[3], wu[3], ud[3], wd[3];
+    T ul[3], wl[3], ur[3], wr[3];
+    const bool kn = act && k + 1 < nz, up = act && j + 1 < ny, dn = act && j >= 1;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      un[c] = sv::vload_if(kn, u.p[c] + pl + w.sz);
+      wn[c] = sv::vload_if(kn, w.p[c] + pl + w.sz);
+      uu[c] = sv::vload_if(up, u.p[c] + pl + w.sy);
+      wu[c] = sv::vload_if(up, w.p[c] + pl + w.sy);
+      ud[c] = sv::vload_if(dn, u.p[c] + pl - w.sy);
+      wd[c] = sv::vload_if(dn, w.p[c] + pl - w.sy);
+      ul[c] = sv::sload_if(has_l, u.p[c] + pl - 1);
+      wl[c] = sv::sload_if(has_l, w.p[c] + pl - 1);
+      ur[c] = sv::sload_if(has_r, u.p[c] + pl + W);
+      wr[c] = sv::sload_if(has_r, w.p[c] + pl + W);
+    }
+    const Vec<T> bnext_x = cross_x(un, wn), bnext_y = cross_y(un, wn), bnext_z = cross_z(un, wn);
+    const Vec<T> bz_jp = cross_z(uu, wu), bx_jp = cross_x(uu, wu);
+    const Vec<T> bz_jm = cross_z(ud, wd), bx_jm = cross_x(ud, wd);
+    const T ebz_l = ul[0] * wl[1] - wl[0] * ul[1], eby_l = ul[2] * wl[0] - wl[2] * ul[0];
+    const T ebz_r = ur[0] * wr[1] - wr[0] * ur[1], eby_r = ur[2] * wr[0] - wr[2] * ur[0];
+    Vec<T> bz_im, bz_ip, by_im, by_ip;
+    sv::x_neighbours(bcur_z, ebz_l, ebz_r, lane, bz_im, bz_ip);
+    sv::x_neighbours(bcur_y, eby_l, eby_r, lane, by_im, by_ip);
+    if (act) {
+      Vec<T> ox = wc[0], oy = wc[1], oz = wc[2];
+      if (jin && k >= 1 && k < nz - 1) {
+#pragma unroll
+        for (int m = 0; m < W; ++m) {
+          const int i = i0 + m;
+          if (i >= 1 && i < nx - 1) {
+            const T ccx = bz_jp.v[m] - bz_jm.v[m] - bnext_y.v[m] + bprev_y.v[m];
+            const T ccy = bnext_x.v[m] - bprev_x.v[m] - bz_ip.v[m] + bz_im.v[m];
+            const T ccz = by_ip.v[m] - by_im.v[m] - bx_jp.v[m] + bx_jm.v[m];
+            ox.v[m] = ox.v[m] + p * ccx;
+            oy.v[m] = oy.v[m] + p * ccy;
+            oz.v[m] = oz.v[m] + p * ccz;
+          }
+        }
+      }
+      const int64_t o = (int64_t)k * out.sz + ocol;
+      sv::vstore(out.p[0] + o, ox);
+      sv::vstore(out.p[1] + o, oy);
+      sv::vstore(out.p[2] + o, oz);
+    }
+    bprev_x = bcur_x, bprev_y = bcur_y;
+    bcur_x = bnext_x, bcur_y = bnext_y, bcur_z = bnext_z;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) wc[c] = wn[c];
+  }
+}
+
+// out = f + q * Lap_7pt(f) [, zero <- 0]; blockIdx.z = chunk * ncomp + comp. 4 + 4 (+4) B per cell (fp32).
+template <typename T>
+__global__ void __launch_bounds__(32 * VBY)
+    diffuse_vec_kernel(Vec3Out<T> out, Vec3View<T> in, Vec3Out<T> zero, int has_zero, int ncomp, T q, int nz,
+                       int ny, int nx, int kchunk) {
+  constexpr int W = Vec<T>::W;
+  const int lane = threadIdx.x;
+  const int i0 = (blockIdx.x * 32 + lane) * W;
+  const int j = blockIdx.y * VBY + threadIdx.y;
+  if (j >= ny) return;
+  const int comp = blockIdx.z % ncomp, chunk = blockIdx.z / ncomp;
+  const int k0 = chunk * kchunk, k1 = min(k0 + kchunk, nz);
+  const T* f = comp == 0 ? in.p[0] : (comp == 1 ? in.p[1] : in.p[2]);
+  T* o_p = comp == 0 ? out.p[0] : (comp == 1 ? out.p[1] : out.p[2]);
+  T* z_p = comp == 0 ? zero.p[0] : (comp == 1 ? zero.p[1] : zero.p[2]);
+  const bool act = i0 < nx;
+  const bool jin = j >= 1 && j < ny - 1;
+  const bool has_l = lane == 0 && act && i0 > 0;
+  const bool has_r = lane == 31 && act && i0 + W < nx;
+  const bool up = act && j + 1 < ny, dn = act && j >= 1;
+  f += (int64_t)j * in.sy + i0;
+  o_p += (int64_t)j * out.sy + i0;
+  z_p += (int64_t)j * zero.sy + i0;
+
+  Vec<T> fprev = sv::vload_if(act && k0 > 0, f + (int64_t)(k0 - 1) * in.sz);
+  Vec<T> fcur = sv::vload_if(act, f + (int64_t)k0 * in.sz);
+#pragma unroll 2
+  for (int k = k0; k < k1; ++k) {
+    const T* pk = f + (int64_t)k * in.sz;
+    const Vec<T> fnext = sv::vload_if(act && k + 1 < nz, pk + in.sz);
+    const Vec<T> fup = sv::vload_if(up, pk + in.sy);
+    const Vec<T> fdn = sv::vload_if(dn, pk - in.sy);
+    const T el = sv::sload_if(has_l, pk - 1), er = sv::sload_if(has_r, pk + W);
+    Vec<T> xl, xr;
+    sv::x_neighbours(fcur, el, er, lane, xl, xr);
+    if (act) {
+      Vec<T> v = fcur;
+      if (jin && k >= 1 && k < nz - 1) {
+#pragma unroll
+        for (int m = 0; m < W; ++m) {
+          const int i = i0 + m;
+          if (i >= 1 && i < nx - 1) {
+            const T flux =
+                q * (fnext.v[m] + fprev.v[m] + fup.v[m] + fdn.v[m] + xr.v[m] + xl.v[m] - T(6) * fcur.v[m]);
+            v.v[m] = fcur.v[m] + flux;
+          }
+        }
+      }
+      sv::vstore(o_p + (int64_t)k * out.sz, v);
+      if (has_zero) sv::vstore(z_p + (int64_t)k * zero.sz, sv::vzero<T>());
+    }
+    fprev = fcur;
+    fcur = fnext;
+  }
+}
+
+// u = p * curl_c(psi) (ring <- 0) + U_inf; max_cells sum_c |u_c|. 12 B read + 12 B written per cell (fp32).
+template <typename T>
+__global__ void __launch_bounds__(32 * VBY)
+    velocity_vec_kernel(Vec3Out<T> out, Vec3View<T> psi, T p, T fx, T fy, T fz, T* max_out, int nz, int ny,
+                        int nx, int kchunk) {
+  constexpr int W = Vec<T>::W;
+  __shared__ T wmax[VBY];
+  const int lane = threadIdx.x;
+  const int i0 = (blockIdx.x * 32 + lane) * W;
+  const int j = blockIdx.y * VBY + threadIdx.y;
+  const int k0 = blockIdx.z * kchunk, k1 = min(k0 + kchunk, nz);
+  const bool row = j < ny;
+  const bool act = row && i0 < nx;
+  const bool jin = j >= 1 && j < ny - 1;
+  const bool has_l = lane == 0 && act && i0 > 0;
+  const bool has_r = lane == 31 && act && i0 + W < nx;
+  const bool up = act && j + 1 < ny, dn = act && j >= 1;
+  const int64_t col = (int64_t)j * psi.sy + i0;
+  const int64_t ocol = (int64_t)j * out.sy + i0;
+  T m_acc = T(0);
+
+  // psi_x, psi_y are needed at k +- 1; psi_z only in-plane
+  Vec<T> pxm = sv::vload_if(act && k0 > 0, psi.p[0] + (int64_t)(k0 - 1) * psi.sz + col);
+  Vec<T> pym = sv::vload_if(act && k0 > 0, psi.p[1] + (int64_t)(k0 - 1) * psi.sz + col);
+  Vec<T> pxc = sv::vload_if(act, psi.p[0] + (int64_t)k0 * psi.sz + col);
+  Vec<T> pyc = sv::vload_if(act, psi.p[1] + (int64_t)k0 * psi.sz + col);
+#pragma unroll 2
+  for (int k = k0; k < k1; ++k) {
+    const int64_t pl = (int64_t)k * psi.sz + col;
+    const bool kn = act && k + 1 < nz;
+    const Vec<T> pxn = sv::vload_if(kn, psi.p[0] + pl + psi.sz);
+    const Vec<T> pyn = sv::vload_if(kn, psi.p[1] + pl + psi.sz);
+    const Vec<T> pzc = sv::vload_if(act, psi.p[2] + pl);
+    const Vec<T> pz_jp = sv::vload_if(up, psi.p[2] + pl + psi.sy);
+    const Vec<T> pz_jm = sv::vload_if(dn, psi.p[2] + pl - psi.sy);
+    const Vec<T> px_jp = sv::vload_if(up, psi.p[0] + pl + psi.sy);
+    const Vec<T> px_jm = sv::vload_if(dn, psi.p[0] + pl - psi.sy);
+    const T ezl = sv::sload_if(has_l, psi.p[2] + pl - 1), ezr = sv::sload_if(has_r, psi.p[2] + pl + W);
+    const T eyl = sv::sload_if(has_l, psi.p[1] + pl - 1), eyr = sv::sload_if(has_r, psi.p[1] + pl + W);
+    Vec<T> pz_im, pz_ip, py_im, py_ip;
+    sv::x_neighbours(pzc, ezl, ezr, lane, pz_im, pz_ip);
+    sv::x_neighbours(pyc, eyl, eyr, lane, py_im, py_ip);
+    if (act) {
+      Vec<T> ux, uy, uz;
+      const bool kin = jin && k >= 1 && k < nz - 1;
+#pragma unroll
+      for (int m = 0; m < W; ++m) {
+        const int i = i0 + m;
+        T vx = T(0), vy = T(0), vz = T(0);
+        if (kin && i >= 1 && i < nx - 1) {
+          const T ccx = pz_jp.v[m] - pz_jm.v[m] - pyn.v[m] + pym.v[m];
+          const T ccy = pxn.v[m] - pxm.v[m] - pz_ip.v[m] + pz_im.v[m];
+          const T ccz = py_ip.v[m] - py_im.v[m] - px_jp.v[m] + px_jm.v[m];
+          vx = p * ccx;
+          vy = p * ccy;
+          vz = p * ccz;
+        }
+        vx = vx + fx;
+        vy = vy + fy;
+        vz = vz + fz;
+        ux.v[m] = vx, uy.v[m] = vy, uz.v[m] = vz;
+        const T a = fabs(vx) + fabs(vy) + fabs(vz);
+        m_acc = a > m_acc ? a : m_acc;
+      }
+      const int64_t o = (int64_t)k * out.sz + ocol;
+      sv::vstore(out.p[0] + o, ux);
+      sv::vstore(out.p[1] + o, uy);
+      sv::vstore(out.p[2] + o, uz);
+    }
+    pxm = pxc, pym = pyc;
+    pxc = pxn, pyc = pyn;
+  }
+  if (max_out) {
+    for (int off = 16; off > 0; off >>= 1) {
+      const T o = __shfl_xor_sync(0xffffffffu, m_acc, off);
+      m_acc = o > m_acc ? o : m_acc;
+    }
+    if (lane == 0) wmax[threadIdx.y] = m_acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && lane == 0) {
+      T m = wmax[0];
+#pragma unroll
+      for (int r = 1; r < VBY; ++r) m = wmax[r] > m ? wmax[r] : m;
+      AtomicMaxNonNeg<T>::apply(max_out, m);
+    }
+  }
+}
+
+// eligibility of the register-marching kernels for a (3, nz, ny, nx) view
+bool vec_ok(const sopht_field_t* f, int dtype) {
+  const int64_t w = dtype == SOPHT_F32 ? 4 : 2;
+  const size_t elem = dtype == SOPHT_F32 ? 4 : 8;
+  if (f->stride[3] != 1 || f->shape[3] % w) return false;
+  if (f->stride[0] % w || f->stride[1] % w || f->stride[2] % w) return false;
+  return (reinterpret_cast<uintptr_t>(f->data) % (w * elem)) == 0;
+}
+
+// z chunking of the marching kernels: >= ~6 CTAs per SM over the whole grid, chunks of at least 16 planes
+int pick_vec_kchunk(int nz, int ny, int nx, int ncomp_grids, int w) {
+  const int64_t xy = (int64_t)((nx + 32 * w - 1) / (32 * w)) * ((ny + VBY - 1) / VBY) * ncomp_grids;
+  int64_t chunks = (148 * 6 + xy - 1) / xy;
+  if (chunks < 1) chunks = 1;
+  int kchunk = (int)((nz + chunks - 1) / chunks);
+  if (kchunk < 16) kchunk = 16;
+  if (kchunk > nz) kchunk = nz;
+  return kchunk;
+}
+
 // ---- host side --------------------------------------------------------------------------------------
 int check_vec3(const char* fn, const sopht_field_t* f) {
   if (!valid_field(f, 4, 4) || f->shape[0] != 3)
@@ -373,11 +660,28 @@ int sopht_ns3d_advect_rotational(int dtype, const sopht_field_t* out_vorticity_f
   const int nz = (int)vorticity_field->shape[1], ny = (int)vorticity_field->shape[2],
             nx = (int)vorticity_field->shape[3];
   if ((int64_t)nz * ny * nx == 0) return SOPHT_OK;
+  cudaStream_t st = as_stream(stream);
+  SOPHT_PROF("ns3d.advect", st);
+  if (vec_ok(out_vorticity_field, dtype) && vec_ok(vorticity_field, dtype) && vec_ok(velocity_field, dtype)) {
+    const int w = dtype == SOPHT_F32 ? 4 : 2;
+    const int kchunk = pick_vec_kchunk(nz, ny, nx, 1, w);
+    dim3 grid((nx + 32 * w - 1) / (32 * w), (ny + VBY - 1) / VBY, (nz + kchunk - 1) / kchunk), block(32, VBY, 1);
+    if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
+    if (dtype == SOPHT_F32)
+      advect_vec_kernel<float><<<grid, block, 0, st>>>(
+          out_view<float>(out_vorticity_field), in_view<float>(vorticity_field),
+          in_view<float>(velocity_field), (float)prefactor, nz, ny, nx, kchunk);
+    else
+      advect_vec_kernel<double><<<grid, block, 0, st>>>(
+          out_view<double>(out_vorticity_field), in_view<double>(vorticity_field),
+          in_view<double>(velocity_field), prefactor, nz, ny, nx, kchunk);
+    SOPHT_CHECK_LAUNCH();
+    return SOPHT_OK;
+  }
   const int tx = dtype == SOPHT_F32 ? Tile<float>::TX : Tile<double>::TX, ty = Tile<float>::TY;
   const int kchunk = pick_kchunk(nz, ny, nx, 1, tx, ty);
   dim3 grid((nx + tx - 1) / tx, (ny + ty - 1) / ty, (nz + kchunk - 1) / kchunk), block(tx, ty, 1);
   if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
-  cudaStream_t st = as_stream(stream);
   if (dtype == SOPHT_F32)
     advect_rotational_kernel<float><<<grid, block, 0, st>>>(
         out_view<float>(out_vorticity_field), in_view<float>(vorticity_field), in_view<float>(velocity_field),
@@ -407,12 +711,32 @@ int sopht_ns3d_diffuse(int dtype, const sopht_field_t* out_field, const sopht_fi
   }
   const int nz = (int)field->shape[1], ny = (int)field->shape[2], nx = (int)field->shape[3];
   if ((int64_t)nz * ny * nx == 0) return SOPHT_OK;
+  cudaStream_t st = as_stream(stream);
+  SOPHT_PROF("ns3d.diffuse", st);
+  if (vec_ok(out_field, dtype) && vec_ok(field, dtype) && (!zero_field || vec_ok(zero_field, dtype))) {
+    const int w = dtype == SOPHT_F32 ? 4 : 2;
+    const int kchunk = pick_vec_kchunk(nz, ny, nx, 3, w);
+    const int nchunk = (nz + kchunk - 1) / kchunk;
+    dim3 grid((nx + 32 * w - 1) / (32 * w), (ny + VBY - 1) / VBY, nchunk * 3), block(32, VBY, 1);
+    if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
+    if (dtype == SOPHT_F32)
+      diffuse_vec_kernel<float><<<grid, block, 0, st>>>(
+          out_view<float>(out_field), in_view<float>(field),
+          zero_field ? out_view<float>(zero_field) : out_view<float>(out_field), zero_field != nullptr, 3,
+          (float)nu_dt_by_dx2, nz, ny, nx, kchunk);
+    else
+      diffuse_vec_kernel<double><<<grid, block, 0, st>>>(
+          out_view<double>(out_field), in_view<double>(field),
+          zero_field ? out_view<double>(zero_field) : out_view<double>(out_field), zero_field != nullptr, 3,
+          nu_dt_by_dx2, nz, ny, nx, kchunk);
+    SOPHT_CHECK_LAUNCH();
+    return SOPHT_OK;
+  }
   const int tx = dtype == SOPHT_F32 ? Tile<float>::TX : Tile<double>::TX, ty = Tile<float>::TY;
   const int kchunk = pick_kchunk(nz, ny, nx, 3, tx, ty);
   const int nchunk = (nz + kchunk - 1) / kchunk;
   dim3 grid((nx + tx - 1) / tx, (ny + ty - 1) / ty, nchunk * 3), block(tx, ty, 1);
   if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
-  cudaStream_t st = as_stream(stream);
   if (dtype == SOPHT_F32)
     diffuse_kernel<float><<<grid, block, 0, st>>>(
         out_view<float>(out_field), in_view<float>(field),
@@ -445,12 +769,29 @@ int sopht_ns3d_velocity_from_stream_function(int dtype, const sopht_field_t* vel
   const double f0 = free_stream_velocity ? free_stream_velocity[0] : 0.0;
   const double f1 = free_stream_velocity ? free_stream_velocity[1] : 0.0;
   const double f2 = free_stream_velocity ? free_stream_velocity[2] : 0.0;
+  cudaStream_t st = as_stream(stream);
+  SOPHT_PROF("ns3d.velocity", st);
+  if (max_abs_sum_out) SOPHT_CUDA(cudaMemsetAsync(max_abs_sum_out, 0, elem, st));
+  if (vec_ok(velocity_field, dtype) && vec_ok(stream_func_field, dtype)) {
+    const int w = dtype == SOPHT_F32 ? 4 : 2;
+    const int kchunk = pick_vec_kchunk(nz, ny, nx, 1, w);
+    dim3 grid((nx + 32 * w - 1) / (32 * w), (ny + VBY - 1) / VBY, (nz + kchunk - 1) / kchunk), block(32, VBY, 1);
+    if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
+    if (dtype == SOPHT_F32)
+      velocity_vec_kernel<float><<<grid, block, 0, st>>>(
+          out_view<float>(velocity_field), in_view<float>(stream_func_field), (float)prefactor, (float)f0,
+          (float)f1, (float)f2, reinterpret_cast<float*>(max_abs_sum_out), nz, ny, nx, kchunk);
+    else
+      velocity_vec_kernel<double><<<grid, block, 0, st>>>(
+          out_view<double>(velocity_field), in_view<double>(stream_func_field), prefactor, f0, f1, f2,
+          reinterpret_cast<double*>(max_abs_sum_out), nz, ny, nx, kchunk);
+    SOPHT_CHECK_LAUNCH();
+    return SOPHT_OK;
+  }
   const int tx = dtype == SOPHT_F32 ? Tile<float>::TX : Tile<double>::TX, ty = Tile<float>::TY;
   const int kchunk = pick_kchunk(nz, ny, nx, 1, tx, ty);
   dim3 grid((nx + tx - 1) / tx, (ny + ty - 1) / ty, (nz + kchunk - 1) / kchunk), block(tx, ty, 1);
   if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
-  cudaStream_t st = as_stream(stream);
-  if (max_abs_sum_out) SOPHT_CUDA(cudaMemsetAsync(max_abs_sum_out, 0, elem, st));
   if (dtype == SOPHT_F32)
     velocity_from_psi_kernel<float><<<grid, block, 0, st>>>(
         out_view<float>(velocity_field), in_view<float>(stream_func_field), (float)prefactor, (float)f0,

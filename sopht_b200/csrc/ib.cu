@@ -562,6 +562,7 @@ int sopht_ib_virtual_boundary_forcing(int dtype, int dim, const sopht_field_t* e
   a.stiffness = stiffness;
   a.damping = damping;
   cudaStream_t st = as_stream(stream);
+  SOPHT_PROF("ib.virtual_boundary_fused", st);
 #define CALL(T, D)                                                               \
   if (pos_dtype == SOPHT_F64)                                                    \
     vbf_fused_kernel<T, double, D><<<warp_grid(n), 256, 0, st>>>(a, vv, fv);     \

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(K::THREADS) p2_kernel(const typename K::Params
 }
 
 template <class K>
-int launch(const typename K::Params& p, dim3 grid, int, cudaStream_t st) {
+int launch(const typename K::Params& p, dim3 grid, const char* label, cudaStream_t st) {
   const size_t smem = sizeof(float2) * (K::SMEM_ELEMS + (use_stage<K>() ? K::STAGE_ELEMS : 0));
   static int ctas_per_sm = 0, num_sm = 0;  // per kernel instantiation
   if (!ctas_per_sm) {
@@ -94,6 +94,7 @@ int launch(const typename K::Params& p, dim3 grid, int, cudaStream_t st) {
   const int64_t ntile = (int64_t)grid.x * grid.y;
   int64_t g = (int64_t)num_sm * ctas_per_sm;
   if (g > ntile) g = ntile;
+  SOPHT_PROF(label, st);
   p2_kernel<K><<<(unsigned)g, K::THREADS, smem, st>>>(p, (int)grid.x, (int)grid.y);
   SOPHT_CHECK_LAUNCH();
   return SOPHT_OK;
@@ -123,7 +124,7 @@ int launch_xfwd(int L, const p2::XParams& p, int64_t rows, cudaStream_t st) {
 #define M(LL)                                                                         \
   {                                                                                   \
     constexpr int RX = rows_per_cta<LL>();                                            \
-    return launch<p2::XFwd<LL, RX>>(p, dim3((unsigned)(rows / RX), 1, 1), 1, st);     \
+    return launch<p2::XFwd<LL, RX>>(p, dim3((unsigned)(rows / RX), 1, 1), "poisson.x_fwd", st);     \
   }
   P2_SWITCH_L(L, M)
 #undef M
@@ -133,26 +134,26 @@ int launch_xinv(int L, const p2::XParams& p, int64_t rows, cudaStream_t st) {
 #define M(LL)                                                                         \
   {                                                                                   \
     constexpr int RX = rows_per_cta<LL>();                                            \
-    return launch<p2::XInv<LL, RX>>(p, dim3((unsigned)(rows / RX), 1, 1), 1, st);     \
+    return launch<p2::XInv<LL, RX>>(p, dim3((unsigned)(rows / RX), 1, 1), "poisson.x_inv", st);     \
   }
   P2_SWITCH_L(L, M)
 #undef M
   return SOPHT_OK;
 }
 int launch_yfwd(int L, const p2::ColParams& p, dim3 grid, cudaStream_t st) {
-#define M(LL) return launch<p2::YFwd<LL, TX>>(p, grid, 1, st);
+#define M(LL) return launch<p2::YFwd<LL, TX>>(p, grid, grid.y > 1 ? "poisson.y_fwd" : "poisson.y_fwd.nyquist", st);
   P2_SWITCH_L(L, M)
 #undef M
   return SOPHT_OK;
 }
 int launch_yinv(int L, const p2::ColParams& p, dim3 grid, cudaStream_t st) {
-#define M(LL) return launch<p2::YInv<LL, TX>>(p, grid, 1, st);
+#define M(LL) return launch<p2::YInv<LL, TX>>(p, grid, grid.y > 1 ? "poisson.y_inv" : "poisson.y_inv.nyquist", st);
   P2_SWITCH_L(L, M)
 #undef M
   return SOPHT_OK;
 }
 int launch_zconv(int L, const p2::ZParams& p, dim3 grid, cudaStream_t st) {
-#define M(LL) return launch<p2::ZConv<LL, TX>>(p, grid, p.ncomp, st);
+#define M(LL) return launch<p2::ZConv<LL, TX>>(p, grid, p.nyq ? "poisson.z_conv.nyquist" : "poisson.z_conv", st);
   P2_SWITCH_L(L, M)
 #undef M
   return SOPHT_OK;

@@ -285,6 +285,7 @@ static int penalise3d_impl(const View3<T>& f, int nz, int ny, int nx, int w, con
     tab.v[2][q] = rz[q];
   }
   const int lz = nz - 2 * w + 2, ly = ny - 2 * w + 2, lx = nx - 2 * w + 2;
+  SOPHT_PROF("penalise_field_boundary", st);
   dim3 block(128, 1, 1);
   {
     dim3 grid((lx + 127) / 128, ly, 2);
@@ -356,6 +357,7 @@ template <typename T, int MODE>
 static int curl_impl(const sopht_field_t* out, const sopht_field_t* field, double p, int reset,
                      cudaStream_t st) {
   GRID_DIMS(field)
+  SOPHT_PROF(MODE == 1 ? "update_vorticity_from_velocity_forcing" : "curl", st);
   curl_kernel<T, MODE><<<g.grid, g.block, 0, st>>>(
       comp3<T>(out, 0), comp3<T>(out, 1), comp3<T>(out, 2), cview(comp3<T>(field, 0)),
       cview(comp3<T>(field, 1)), cview(comp3<T>(field, 2)), (T)p, nz, ny, nx, reset);

@@ -23,7 +23,10 @@ def _seed_state(sim, ref, rng, real_t, names):
 @pytest.mark.parametrize("with_free_stream", [False, True])
 @pytest.mark.parametrize("filter_vorticity", [False, True])
 @pytest.mark.parametrize("step_mode", ["unfused", "auto"])
-@pytest.mark.parametrize("grid", [(16, 16, 16), (8, 12, 20), (32, 16, 64)])
+# (10, 11, 15): x extent not a multiple of the vector width -> shared-memory fused kernels; (40, 12, 132) and
+# (6, 20, 260): several z chunks / several (partially filled) x tiles of the register-marching kernels
+@pytest.mark.parametrize("grid", [(16, 16, 16), (8, 12, 20), (32, 16, 64), (10, 11, 15), (40, 12, 132),
+                                  (6, 20, 260)])
 def test_navier_stokes_3d_step(rng, precision, with_forcing, with_free_stream, filter_vorticity, step_mode, grid):
     from oracle import flow as oflow
     from sopht_b200.simulator import UnboundedNavierStokesFlowSimulator3D

@@ -18,7 +18,9 @@ MAX_DIMS = 5
 SOPHT_F32 = 0
 SOPHT_F64 = 1
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libsopht_b200.so")
+# SOPHT_B200_LIB: an experiment build of the same library (Makefile: EXTRA= / LIBNAME=)
+_LIB_PATH = os.environ.get("SOPHT_B200_LIB") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "lib", "libsopht_b200.so")
 
 
 class SophtField(ctypes.Structure):

@@ -162,7 +162,11 @@ SOPHT_FFT_CFG(64, 8, 8, 1, 8)
 SOPHT_FFT_CFG(128, 16, 8, 1, 16)
 SOPHT_FFT_CFG(256, 16, 16, 1, 16)
 SOPHT_FFT_CFG(512, 32, 16, 1, 32)
+#ifdef SOPHT_FFT_1024_E16
+SOPHT_FFT_CFG(1024, 4, 16, 16, 16)
+#else
 SOPHT_FFT_CFG(1024, 32, 32, 1, 32)
+#endif
 SOPHT_FFT_CFG(2048, 16, 16, 8, 16)
 #undef SOPHT_FFT_CFG
 
@@ -202,9 +206,9 @@ FFT_HD void fwd_first(Load ld, Acc sm, int t, const float2* __restrict__ tw) {
   for (int q = 0; q < NB; ++q) {
     const int j = t + q * C::T;
     dft<R, false>(v[q]);
-    sm(j) = v[q][0];
+    sm.at(0, j) = v[q][0];
 #pragma unroll
-    for (int k = 1; k < R; ++k) sm(k * S + j) = cmul(v[q][k], tw[j * k]);
+    for (int k = 1; k < R; ++k) sm.at(k * S, j) = cmul(v[q][k], tw[j * k]);
   }
 }
 
@@ -218,11 +222,11 @@ FFT_HD void fwd_mid(Acc sm, int t, const float2* __restrict__ tw) {
     const int b = t + q * C::T, blk = b / S, j = b % S, base = blk * SP + j;
     float2 v[R];
 #pragma unroll
-    for (int n = 0; n < R; ++n) v[n] = sm(base + n * S);
+    for (int n = 0; n < R; ++n) v[n] = sm.at(n * S, base);
     dft<R, false>(v);
-    sm(base) = v[0];
+    sm.at(0, base) = v[0];
 #pragma unroll
-    for (int k = 1; k < R; ++k) sm(base + k * S) = cmul(v[k], tw[j * k * (L / SP)]);
+    for (int k = 1; k < R; ++k) sm.at(k * S, base) = cmul(v[k], tw[j * k * (L / SP)]);
   }
 }
 
@@ -236,7 +240,7 @@ FFT_HD void fwd_last(Acc sm, int t, Sink sink) {
     const int blk = t + q * C::T;
     float2 v[R];
 #pragma unroll
-    for (int n = 0; n < R; ++n) v[n] = sm(blk * R + n);
+    for (int n = 0; n < R; ++n) v[n] = sm.at(n, blk * R);
     dft<R, false>(v);
 #pragma unroll
     for (int k = 0; k < R; ++k) sink(spectrum_index<L>(blk, k), blk * R + k, v[k]);
@@ -260,7 +264,7 @@ FFT_HD void inv_first(Src src, Acc sm, int t) {
     const int blk = t + q * C::T;
     dft<R, true>(v[q]);
 #pragma unroll
-    for (int n = 0; n < R; ++n) sm(blk * R + n) = v[q][n];
+    for (int n = 0; n < R; ++n) sm.at(n, blk * R) = v[q][n];
   }
 }
 
@@ -274,17 +278,17 @@ FFT_HD void fwd_last_mul_inv_first(Acc sm, int t, G g) {
     const int blk = t + q * C::T;
     float2 v[R];
 #pragma unroll
-    for (int n = 0; n < R; ++n) v[n] = sm(blk * R + n);
+    for (int n = 0; n < R; ++n) v[n] = sm.at(n, blk * R);
     dft<R, false>(v);
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      const float s = g(spectrum_index<L>(blk, k));
+      const float s = g(blk, k);
       v[k].x *= s;
       v[k].y *= s;
     }
     dft<R, true>(v);
 #pragma unroll
-    for (int n = 0; n < R; ++n) sm(blk * R + n) = v[n];
+    for (int n = 0; n < R; ++n) sm.at(n, blk * R) = v[n];
   }
 }
 
@@ -297,12 +301,12 @@ FFT_HD void inv_mid(Acc sm, int t, const float2* __restrict__ tw) {
   for (int q = 0; q < NB; ++q) {
     const int b = t + q * C::T, blk = b / S, j = b % S, base = blk * SP + j;
     float2 v[R];
-    v[0] = sm(base);
+    v[0] = sm.at(0, base);
 #pragma unroll
-    for (int k = 1; k < R; ++k) v[k] = cmul_conj(sm(base + k * S), tw[j * k * (L / SP)]);
+    for (int k = 1; k < R; ++k) v[k] = cmul_conj(sm.at(k * S, base), tw[j * k * (L / SP)]);
     dft<R, true>(v);
 #pragma unroll
-    for (int n = 0; n < R; ++n) sm(base + n * S) = v[n];
+    for (int n = 0; n < R; ++n) sm.at(n * S, base) = v[n];
   }
 }
 
@@ -315,9 +319,9 @@ FFT_HD void inv_last(Acc sm, int t, const float2* __restrict__ tw, Store st) {
   for (int q = 0; q < NB; ++q) {
     const int j = t + q * C::T;
     float2 v[R];
-    v[0] = sm(j);
+    v[0] = sm.at(0, j);
 #pragma unroll
-    for (int k = 1; k < R; ++k) v[k] = cmul_conj(sm(k * S + j), tw[j * k]);
+    for (int k = 1; k < R; ++k) v[k] = cmul_conj(sm.at(k * S, j), tw[j * k]);
     dft<R, true>(v);
 #pragma unroll
     for (int n = 0; n < R / 2; ++n) st(n * S + j, v[n]);
@@ -354,6 +358,14 @@ FFT_HD void async_copy8(float2* smem_dst, const float2* gsrc) {
 #ifdef __CUDA_ARCH__
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+#else
+  *smem_dst = *gsrc;
+#endif
+}
+FFT_HD void async_copy4(float* smem_dst, const float* gsrc) {
+#ifdef __CUDA_ARCH__
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
 #else
   *smem_dst = *gsrc;
 #endif

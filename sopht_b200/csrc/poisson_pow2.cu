@@ -7,6 +7,7 @@
 //
 // ref: sopht/numeric/eulerian_grid_ops/poisson_solver_3d/UnboundedPoissonSolverPYFFTW3D.py:111-172
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -33,26 +34,32 @@ struct DevPhases<K, 0> {
   __device__ __forceinline__ static void run(const typename K::Params&, int, int, int, float2*, const float2*) {}
 };
 
-// cp.async staging pays when registers allow only one CTA per SM (32 elements per thread: radix-32 passes,
-// L >= 512 in the column kernels); kernels with several resident CTAs overlap load and compute through the
-// hardware scheduler instead (measured: staging costs them LSU/shared-memory wavefronts and time).
+// Two tuning knobs per kernel family, chosen from measurements on B200 (profiles/): MINB = CTAs per SM the
+// register allocation is bounded for, STAGED = cp.async prefetch of the next tile's first-phase inputs into a
+// staging buffer. Staging pays when only one CTA fits an SM; with two resident CTAs the hardware scheduler
+// overlaps one CTA's loads with the other's butterflies.
 template <class K>
-constexpr bool use_stage() {
-  return K::WANT_STAGE && sizeof(float2) * (size_t)(K::SMEM_ELEMS + K::STAGE_ELEMS) <= 200 * 1024;
+constexpr bool stage_fits(int ctas) {
+  return sizeof(float2) * (size_t)(K::SMEM_ELEMS + K::EXTRA_ELEMS + K::STAGE_ELEMS) * ctas <= 226 * 1024;
+}
+template <class K>
+constexpr int auto_min_ctas() {
+  return 512 / K::THREADS > 1 ? 512 / K::THREADS : 1;
 }
 
 // Persistent kernel: CTA b owns tiles b, b + gridDim.x, ... (neighbouring CTAs work on neighbouring tiles at
 // the same time, which keeps DRAM pages shared); all iterations (components) of a tile stay on one CTA.
-template <class K>
-__global__ void __launch_bounds__(K::THREADS) p2_kernel(const typename K::Params p, int gx, int gy) {
+template <class K, int MINB, bool STAGED>
+__global__ void __launch_bounds__(K::THREADS, MINB) p2_kernel(const typename K::Params p, int gx, int gy) {
   extern __shared__ float2 p2_smem[];
-  constexpr bool STAGED = use_stage<K>();
-  float2* stage = STAGED ? p2_smem + K::SMEM_ELEMS : nullptr;
+  float2* stage = STAGED ? p2_smem + K::SMEM_ELEMS + K::EXTRA_ELEMS : nullptr;
   const int niter = K::niter(p);
   const int64_t ntile = (int64_t)gx * gy;
   int64_t s = blockIdx.x;
   int it = 0;
   if (s >= ntile) return;
+  K::init(p, threadIdx.x, p2_smem);  // shared-memory tables (twiddles are read from phase 0 on)
+  if (K::EXTRA_ELEMS) __syncthreads();
   if (STAGED) K::prefetch(p, (int)(s % gx), (int)(s / gx), 0, threadIdx.x, stage);
   while (true) {
     if (STAGED) {
@@ -78,26 +85,54 @@ __global__ void __launch_bounds__(K::THREADS) p2_kernel(const typename K::Params
   }
 }
 
-template <class K>
-int launch(const typename K::Params& p, dim3 grid, const char* label, cudaStream_t st) {
-  const size_t smem = sizeof(float2) * (K::SMEM_ELEMS + (use_stage<K>() ? K::STAGE_ELEMS : 0));
+template <class K, int MINB, bool STAGED>
+int launch_variant(const typename K::Params& p, dim3 grid, const char* label, cudaStream_t st) {
+  const size_t smem = sizeof(float2) * (K::SMEM_ELEMS + K::EXTRA_ELEMS + (STAGED ? K::STAGE_ELEMS : 0));
   static int ctas_per_sm = 0, num_sm = 0;  // per kernel instantiation
   if (!ctas_per_sm) {
     if (smem > 48 * 1024)
-      SOPHT_CUDA(cudaFuncSetAttribute(p2_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      SOPHT_CUDA(cudaFuncSetAttribute(p2_kernel<K, MINB, STAGED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
     int dev = 0;
     SOPHT_CUDA(cudaGetDevice(&dev));
     SOPHT_CUDA(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
-    SOPHT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, p2_kernel<K>, K::THREADS, smem));
+    SOPHT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, p2_kernel<K, MINB, STAGED>,
+                                                             K::THREADS, smem));
     if (ctas_per_sm < 1) SOPHT_FAIL(SOPHT_ERR_CUDA, "poisson(pow2): kernel does not fit on an SM");
   }
   const int64_t ntile = (int64_t)grid.x * grid.y;
   int64_t g = (int64_t)num_sm * ctas_per_sm;
   if (g > ntile) g = ntile;
   SOPHT_PROF(label, st);
-  p2_kernel<K><<<(unsigned)g, K::THREADS, smem, st>>>(p, (int)grid.x, (int)grid.y);
+  p2_kernel<K, MINB, STAGED><<<(unsigned)g, K::THREADS, smem, st>>>(p, (int)grid.x, (int)grid.y);
   SOPHT_CHECK_LAUNCH();
   return SOPHT_OK;
+}
+
+// experiment switches (SOPHT_P2_MINB = 1 | 2, SOPHT_P2_STAGE = 0 | 1); unset = the tuned default
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v && *v ? atoi(v) : dflt;
+}
+
+template <class K>
+int launch(const typename K::Params& p, dim3 grid, const char* label, cudaStream_t st) {
+  constexpr int AUTO = auto_min_ctas<K>();
+  static const int minb = env_int("SOPHT_P2_MINB", 0);
+  static const int stg = env_int("SOPHT_P2_STAGE", -1);
+  if constexpr (!K::WANT_STAGE) {
+    return launch_variant<K, AUTO, false>(p, grid, label, st);
+  } else {
+  // big radix-32 column kernels: 256 threads per CTA
+  const bool two = minb ? minb >= 2 : false;
+  bool staged = stg >= 0 ? stg != 0 : true;
+  if (two) {
+    if (staged && stage_fits<K>(AUTO)) return launch_variant<K, AUTO, true>(p, grid, label, st);
+    return launch_variant<K, AUTO, false>(p, grid, label, st);
+  }
+  if (staged && stage_fits<K>(1)) return launch_variant<K, 1, true>(p, grid, label, st);
+  return launch_variant<K, 1, false>(p, grid, label, st);
+  }
 }
 
 constexpr int TX = 8;  // columns per CTA in the y / z passes (8 complex = 64 B segments)

@@ -38,6 +38,9 @@ struct ColAcc {
   static constexpr int PADR = Cfg<L>::RLAST;
   static constexpr int ROWS = L + L / PADR;
   FFT_HD float2& operator()(int e) const { return s[(e + e / PADR) * TX + col]; }
+  // position c + v where c is a compile-time constant after unrolling and (c % PADR) + (v % PADR) < PADR,
+  // so the padding term splits and the constant part folds into the instruction's immediate offset
+  FFT_HD float2& at(int c, int v) const { return s[(v + v / PADR) * TX + col + (c + c / PADR) * TX]; }
 };
 // row mode: each sequence contiguous, one pad element every RLAST elements
 template <int L>
@@ -46,7 +49,25 @@ struct RowAcc {
   static constexpr int PADR = Cfg<L>::RLAST;
   static constexpr int PITCH = L + L / PADR + 1;
   FFT_HD float2& operator()(int e) const { return s[e + e / PADR]; }
+  FFT_HD float2& at(int c, int v) const { return s[(v + v / PADR) + (c + c / PADR)]; }
 };
+
+// ---- shared-memory tables --------------------------------------------------------------------------------
+// The twiddle table (and, in the z pass, the tile's slice of the folded Green's function) live in shared memory
+// right behind the data tile: smem = [data SMEM_ELEMS][tables EXTRA_ELEMS][staging]. Read from global memory
+// they cost one LDG with a 64-bit address register pair per use, and those registers stay scoreboarded until the
+// load has read them - measured as the top stall of the 255-register radix-32 kernels. init() fills the
+// twiddle part once per (persistent) CTA.
+#ifndef SOPHT_P2_NO_SMEM_TABLES
+#define SOPHT_P2_SMEM_TABLES 1
+#else
+#define SOPHT_P2_SMEM_TABLES 0
+#endif
+
+template <int THREADS>
+FFT_HD void copy_table(float2* dst, const float2* src, int n, int tid) {
+  for (int i = tid; i < n; i += THREADS) dst[i] = src[i];
+}
 
 // ---- Y forward / inverse (column mode) --------------------------------------------------------------------
 struct ColParams {
@@ -57,25 +78,28 @@ struct ColParams {
   const float2* tw;                              // forward twiddles, length L
 };
 
+// Row strides travel as 32-bit unsigned: for every eligible grid (nz, ny <= 1024, nx <= 2048) the largest
+// element offset inside a tile column, (L - 1) * rs, stays below 2^32, and an unsigned 32-bit product plus one
+// IMAD.WIDE replaces a 64-bit multiply per access.
 struct GlobalLoad {
   const float2* p;
-  int64_t rs;
-  FFT_HD float2 operator()(int e) const { return p[e * rs]; }
+  unsigned rs;
+  FFT_HD float2 operator()(int e) const { return p[(unsigned)e * rs]; }
 };
 struct GlobalStoreIdx {  // sink(k, pos, v) -> out[k]
   float2* p;
-  int64_t rs;
-  FFT_HD void operator()(int k, int, float2 v) const { p[k * rs] = v; }
+  unsigned rs;
+  FFT_HD void operator()(int k, int, float2 v) const { p[(unsigned)k * rs] = v; }
 };
 struct GlobalSrcIdx {  // src(k, pos) -> in[k]
   const float2* p;
-  int64_t rs;
-  FFT_HD float2 operator()(int k, int) const { return p[k * rs]; }
+  unsigned rs;
+  FFT_HD float2 operator()(int k, int) const { return p[(unsigned)k * rs]; }
 };
 struct GlobalStore {
   float2* p;
-  int64_t rs;
-  FFT_HD void operator()(int e, float2 v) const { p[e * rs] = v; }
+  unsigned rs;
+  FFT_HD void operator()(int e, float2 v) const { p[(unsigned)e * rs] = v; }
 };
 
 // staged variants: the element was copied to stage[index * TX + col] by this thread's own cp.async
@@ -93,8 +117,8 @@ template <int TX>
 struct StageCopy {
   float2* s;
   const float2* g;
-  int64_t rs;
-  FFT_HD void operator()(int e) const { fft::async_copy8(s + e * TX, g + e * rs); }
+  unsigned rs;
+  FFT_HD void operator()(int e) const { fft::async_copy8(s + e * TX, g + (unsigned)e * rs); }
 };
 
 template <int L, int TX>
@@ -104,31 +128,36 @@ struct YFwd {
   static constexpr int NPHASE = Cfg<L>::NP;
   static constexpr int NITER = 1;
   static constexpr int SMEM_ELEMS = ColAcc<L, TX>::ROWS * TX;
+  static constexpr int EXTRA_ELEMS = SOPHT_P2_SMEM_TABLES ? L : 0;
   static constexpr int STAGE_ELEMS = (L / 2) * TX;
   static constexpr bool STAGE_SHARED = false;  // a thread reads back only what it copied itself
   static constexpr bool WANT_STAGE = Cfg<L>::E >= 32;
   FFT_HD static int niter(const Params&) { return 1; }
+  FFT_HD static void init(const Params& p, int tid, float2* smem) {
+    if (EXTRA_ELEMS) copy_table<THREADS>(smem + SMEM_ELEMS, p.tw, L, tid);
+  }
   FFT_HD static void prefetch(const Params& p, int bx, int by, int, int tid, float2* stage) {
     const int col = tid % TX, t = tid / TX;
-    StageCopy<TX> cp{stage + col, p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, p.in_rs};
+    StageCopy<TX> cp{stage + col, p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, (unsigned)p.in_rs};
     fft::fwd_first_elems<L>(t, cp);
   }
   template <int P>
   FFT_HD static void phase(const Params& p, int bx, int by, int, int tid, float2* smem, const float2* stage) {
     const int col = tid % TX, t = tid / TX;
     ColAcc<L, TX> sm{smem, col};
+    const float2* tw = EXTRA_ELEMS ? smem + SMEM_ELEMS : p.tw;
     if (P == 0) {
       if (stage) {
-        fft::fwd_first<L>(StageLoad<TX>{stage + col}, sm, t, p.tw);
+        fft::fwd_first<L>(StageLoad<TX>{stage + col}, sm, t, tw);
       } else {
-        GlobalLoad ld{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, p.in_rs};
-        fft::fwd_first<L>(ld, sm, t, p.tw);
+        GlobalLoad ld{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, (unsigned)p.in_rs};
+        fft::fwd_first<L>(ld, sm, t, tw);
       }
     } else if (P == NPHASE - 1) {
-      GlobalStoreIdx st{p.out + bx * p.out_bx + by * p.out_by + col * p.out_cs, p.out_rs};
+      GlobalStoreIdx st{p.out + bx * p.out_bx + by * p.out_by + col * p.out_cs, (unsigned)p.out_rs};
       fft::fwd_last<L>(sm, t, st);
     } else {
-      fft::fwd_mid<L>(sm, t, p.tw);
+      fft::fwd_mid<L>(sm, t, tw);
     }
   }
 };
@@ -140,31 +169,36 @@ struct YInv {
   static constexpr int NPHASE = Cfg<L>::NP;
   static constexpr int NITER = 1;
   static constexpr int SMEM_ELEMS = ColAcc<L, TX>::ROWS * TX;
+  static constexpr int EXTRA_ELEMS = SOPHT_P2_SMEM_TABLES ? L : 0;
   static constexpr int STAGE_ELEMS = L * TX;
   static constexpr bool STAGE_SHARED = false;
   static constexpr bool WANT_STAGE = Cfg<L>::E >= 32;
   FFT_HD static int niter(const Params&) { return 1; }
+  FFT_HD static void init(const Params& p, int tid, float2* smem) {
+    if (EXTRA_ELEMS) copy_table<THREADS>(smem + SMEM_ELEMS, p.tw, L, tid);
+  }
   FFT_HD static void prefetch(const Params& p, int bx, int by, int, int tid, float2* stage) {
     const int col = tid % TX, t = tid / TX;
-    StageCopy<TX> cp{stage + col, p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, p.in_rs};
+    StageCopy<TX> cp{stage + col, p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, (unsigned)p.in_rs};
     fft::inv_first_elems<L>(t, cp);
   }
   template <int P>
   FFT_HD static void phase(const Params& p, int bx, int by, int, int tid, float2* smem, const float2* stage) {
     const int col = tid % TX, t = tid / TX;
     ColAcc<L, TX> sm{smem, col};
+    const float2* tw = EXTRA_ELEMS ? smem + SMEM_ELEMS : p.tw;
     if (P == 0) {
       if (stage) {
         fft::inv_first<L>(StageSrcIdx<TX>{stage + col}, sm, t);
       } else {
-        GlobalSrcIdx src{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, p.in_rs};
+        GlobalSrcIdx src{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, (unsigned)p.in_rs};
         fft::inv_first<L>(src, sm, t);
       }
     } else if (P == NPHASE - 1) {
-      GlobalStore st{p.out + bx * p.out_bx + by * p.out_by + col * p.out_cs, p.out_rs};
-      fft::inv_last<L>(sm, t, p.tw, st);
+      GlobalStore st{p.out + bx * p.out_bx + by * p.out_by + col * p.out_cs, (unsigned)p.out_rs};
+      fft::inv_last<L>(sm, t, tw, st);
     } else {
-      fft::inv_mid<L>(sm, t, p.tw);
+      fft::inv_mid<L>(sm, t, tw);
     }
   }
 };
@@ -182,13 +216,26 @@ struct ZParams {
   const float2* tw;
 };
 
-struct GreenFold {
+// G_hat(kz) for one column, kz given as (blk, klast) of the position the forward last pass leaves it at.
+// Whether kz folds (kz > L/2 -> L - kz) depends on klast alone: the spectrum index is
+// rev(blk) + (L/RLAST) * klast with rev(blk) < L/RLAST, and L/2 is a multiple of L/RLAST.
+template <int L>
+struct GreenFold {  // straight from global memory (g already offset to this thread's column)
   const float* g;
   int64_t zs;
-  int n2z;
-  FFT_HD float operator()(int kz) const {
-    const int f = kz <= n2z / 2 ? kz : n2z - kz;
+  FFT_HD float operator()(int blk, int klast) const {
+    const int kz = fft::spectrum_index<L>(blk, klast);
+    const int f = klast < Cfg<L>::RLAST / 2 ? kz : L - kz;
     return g[f * zs];
+  }
+};
+template <int L, int TX>
+struct GreenTile {  // from the tile's shared-memory slice gs[f * TX + col], f = 0 .. L/2
+  const float* gs;
+  FFT_HD float operator()(int blk, int klast) const {
+    const int kz = fft::spectrum_index<L>(blk, klast);
+    const int f = klast < Cfg<L>::RLAST / 2 ? kz : L - kz;
+    return gs[f * TX];
   }
 };
 
@@ -200,40 +247,57 @@ struct ZConv {
   static constexpr int NPHASE = 2 * NP - 1;  // fwd_first [fwd_mid] fused [inv_mid] inv_last
   static constexpr int NITER = 0;            // runtime: ncomp
   static constexpr int SMEM_ELEMS = ColAcc<L, TX>::ROWS * TX;
+  static constexpr int G_FLOATS = (L / 2 + 1) * TX;  // the tile's folded G_hat slice, shared by its components
+  static constexpr int EXTRA_ELEMS = SOPHT_P2_SMEM_TABLES ? L + (G_FLOATS + 1) / 2 : 0;
   static constexpr int STAGE_ELEMS = (L / 2) * TX;
   static constexpr bool STAGE_SHARED = false;
   static constexpr bool WANT_STAGE = Cfg<L>::E >= 32;
   FFT_HD static int niter(const Params& p) { return p.ncomp; }
+  FFT_HD static void init(const Params& p, int tid, float2* smem) {
+    if (EXTRA_ELEMS) copy_table<THREADS>(smem + SMEM_ELEMS, p.tw, L, tid);
+  }
   FFT_HD static void prefetch(const Params& p, int bx, int by, int c, int tid, float2* stage) {
     const int col = tid % TX, t = tid / TX;
-    StageCopy<TX> cp{stage + col, p.data + bx * p.d_bx + by * p.d_by + c * p.d_c + col * p.cs, p.rs};
+    StageCopy<TX> cp{stage + col, p.data + bx * p.d_bx + by * p.d_by + c * p.d_c + col * p.cs, (unsigned)p.rs};
     fft::fwd_first_elems<L>(t, cp);
+  }
+  FFT_HD static int64_t green_offset(const Params& p, int bx, int by, int col) {
+    const int ky = p.nyq ? bx * TX + col : by;
+    const int fky = ky <= p.n2y / 2 ? ky : p.n2y - ky;
+    return p.nyq ? (int64_t)fky : (int64_t)fky * p.g_ky_stride + bx * TX + col;
   }
   template <int P>
   FFT_HD static void phase(const Params& p, int bx, int by, int c, int tid, float2* smem, const float2* stage) {
     const int col = tid % TX, t = tid / TX;
     ColAcc<L, TX> sm{smem, col};
     float2* base = p.data + bx * p.d_bx + by * p.d_by + c * p.d_c + col * p.cs;
+    const float2* tw = EXTRA_ELEMS ? smem + SMEM_ELEMS : p.tw;
+    float* gs = reinterpret_cast<float*>(smem + SMEM_ELEMS + L);
     if (P == 0) {
-      if (stage) {
-        fft::fwd_first<L>(StageLoad<TX>{stage + col}, sm, t, p.tw);
-      } else {
-        GlobalLoad ld{base, p.rs};
-        fft::fwd_first<L>(ld, sm, t, p.tw);
+      if (EXTRA_ELEMS && c == 0) {  // this tile's G_hat slice, asynchronously, behind the first butterflies
+        const float* g = p.g + green_offset(p, bx, by, col);
+        for (int f = t; f <= L / 2; f += Cfg<L>::T) fft::async_copy4(gs + f * TX + col, g + f * p.g_zs);
       }
+      if (stage) {
+        fft::fwd_first<L>(StageLoad<TX>{stage + col}, sm, t, tw);
+      } else {
+        GlobalLoad ld{base, (unsigned)p.rs};
+        fft::fwd_first<L>(ld, sm, t, tw);
+      }
+      if (EXTRA_ELEMS && c == 0) fft::async_commit_wait_all();  // published by the barrier after this phase
     } else if (P == NP - 1) {
-      const int ky = p.nyq ? bx * TX + col : by;
-      const int fky = ky <= p.n2y / 2 ? ky : p.n2y - ky;
-      const int64_t goff = p.nyq ? (int64_t)fky : (int64_t)fky * p.g_ky_stride + bx * TX + col;
-      GreenFold g{p.g + goff, p.g_zs, L};
-      fft::fwd_last_mul_inv_first<L>(sm, t, g);
+      if (EXTRA_ELEMS) {
+        fft::fwd_last_mul_inv_first<L>(sm, t, GreenTile<L, TX>{gs + col});
+      } else {
+        fft::fwd_last_mul_inv_first<L>(sm, t, GreenFold<L>{p.g + green_offset(p, bx, by, col), p.g_zs});
+      }
     } else if (P == NPHASE - 1) {
-      GlobalStore st{base, p.rs};
-      fft::inv_last<L>(sm, t, p.tw, st);
+      GlobalStore st{base, (unsigned)p.rs};
+      fft::inv_last<L>(sm, t, tw, st);
     } else if (P < NP - 1) {
-      fft::fwd_mid<L>(sm, t, p.tw);
+      fft::fwd_mid<L>(sm, t, tw);
     } else {
-      fft::inv_mid<L>(sm, t, p.tw);
+      fft::inv_mid<L>(sm, t, tw);
     }
   }
 };
@@ -278,10 +342,17 @@ struct XFwd {
   static constexpr int NPHASE = NP + 1;
   static constexpr int NITER = 1;
   static constexpr int SMEM_ELEMS = RowAcc<L>::PITCH * RX;
+  static constexpr int EXTRA_ELEMS = SOPHT_P2_SMEM_TABLES ? 2 * L : 0;  // tw, tw2
   static constexpr int STAGE_ELEMS = (L / 2) * RX;
   static constexpr bool STAGE_SHARED = false;
   static constexpr bool WANT_STAGE = false;
   FFT_HD static int niter(const Params&) { return 1; }
+  FFT_HD static void init(const Params& p, int tid, float2* smem) {
+    if (EXTRA_ELEMS) {
+      copy_table<THREADS>(smem + SMEM_ELEMS, p.tw, L, tid);
+      copy_table<THREADS>(smem + SMEM_ELEMS + L, p.tw2, L, tid);
+    }
+  }
   FFT_HD static const float2* row_ptr(const Params& p, const float* base, int64_t row) {
     const int y = (int)(row % p.ny);
     const int64_t cz = row / p.ny;
@@ -291,7 +362,7 @@ struct XFwd {
   }
   FFT_HD static void prefetch(const Params& p, int bx, int, int, int tid, float2* stage) {
     const int t = tid % T, r = tid / T;
-    StageCopy<1> cp{stage + r * (L / 2), row_ptr(p, p.real_in, (int64_t)bx * RX + r), 1};
+    StageCopy<1> cp{stage + r * (L / 2), row_ptr(p, p.real_in, (int64_t)bx * RX + r), 1u};
     fft::fwd_first_elems<L>(t, cp);
   }
   template <int P>
@@ -299,12 +370,14 @@ struct XFwd {
     const int t = tid % T, r = tid / T;
     const int64_t row = (int64_t)bx * RX + r;
     RowAcc<L> sm{smem + r * RowAcc<L>::PITCH};
+    const float2* tw = EXTRA_ELEMS ? smem + SMEM_ELEMS : p.tw;
+    const float2* tw2 = EXTRA_ELEMS ? smem + SMEM_ELEMS + L : p.tw2;
     if (P == 0) {
       if (stage) {
-        fft::fwd_first<L>(StageLoad<1>{stage + r * (L / 2)}, sm, t, p.tw);
+        fft::fwd_first<L>(StageLoad<1>{stage + r * (L / 2)}, sm, t, tw);
       } else {
         RowLoad ld{row_ptr(p, p.real_in, row)};
-        fft::fwd_first<L>(ld, sm, t, p.tw);
+        fft::fwd_first<L>(ld, sm, t, tw);
       }
     } else if (P == NP - 1) {
       fft::fwd_last<L>(sm, t, InPlaceSink<L>{sm});
@@ -318,11 +391,11 @@ struct XFwd {
         const float2 b = sm(fft::spectrum_position<L>((L - k) & (L - 1)));
         const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
         const float2 o = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
-        out[k] = fft::cadd(e, fft::cmul(o, p.tw2[k]));
+        out[k] = fft::cadd(e, fft::cmul(o, tw2[k]));
         if (k == 0) p.nyq[row] = make_float2(e.x - o.x, e.y - o.y);
       }
     } else {
-      fft::fwd_mid<L>(sm, t, p.tw);
+      fft::fwd_mid<L>(sm, t, tw);
     }
   }
 };
@@ -336,10 +409,12 @@ struct XInv {
   static constexpr int NPHASE = NP + 1;
   static constexpr int NITER = 1;
   static constexpr int SMEM_ELEMS = RowAcc<L>::PITCH * RX;
+  static constexpr int EXTRA_ELEMS = SOPHT_P2_SMEM_TABLES ? 2 * L : 0;  // tw, tw2
   static constexpr int STAGE_ELEMS = (L + 1) * RX;  // spectrum row + its Nyquist bin
   static constexpr bool STAGE_SHARED = true;        // bin k is combined with bin L-k, staged by another thread
   static constexpr bool WANT_STAGE = false;
   FFT_HD static int niter(const Params&) { return 1; }
+  FFT_HD static void init(const Params& p, int tid, float2* smem) { XFwd<L, RX>::init(p, tid, smem); }
   FFT_HD static void prefetch(const Params& p, int bx, int, int, int tid, float2* stage) {
     const int t = tid % T, r = tid / T;
     const int64_t row = (int64_t)bx * RX + r;
@@ -354,6 +429,8 @@ struct XInv {
     const int t = tid % T, r = tid / T;
     const int64_t row = (int64_t)bx * RX + r;
     RowAcc<L> sm{smem + r * RowAcc<L>::PITCH};
+    const float2* tw = EXTRA_ELEMS ? smem + SMEM_ELEMS : p.tw;
+    const float2* tw2 = EXTRA_ELEMS ? smem + SMEM_ELEMS + L : p.tw2;
     if (P == 0) {
       // Z_k = E_k + i O_k, E = (X_k + conj X_{L-k})/2, O = conj(w^k) (X_k - conj X_{L-k})/2
       const float2* in = stage ? stage + r * (L + 1) : p.spec + row * L;
@@ -365,16 +442,16 @@ struct XInv {
         const float2 b = k == 0 ? *nq : in[L - k];
         const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
         const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
-        const float2 o = fft::cmul_conj(d, p.tw2[k]);
+        const float2 o = fft::cmul_conj(d, tw2[k]);
         sm(fft::spectrum_position<L>(k)) = make_float2(e.x - o.y, e.y + o.x);
       }
     } else if (P == 1) {
       fft::inv_first<L>(InPlaceSrc<L>{sm}, sm, t);
     } else if (P == NPHASE - 1) {
       RowStore st{const_cast<float2*>(XFwd<L, RX>::row_ptr(p, p.real_out, row))};
-      fft::inv_last<L>(sm, t, p.tw, st);
+      fft::inv_last<L>(sm, t, tw, st);
     } else {
-      fft::inv_mid<L>(sm, t, p.tw);
+      fft::inv_mid<L>(sm, t, tw);
     }
   }
 };

@@ -18,4 +18,11 @@ for _ in range(reps):
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 n = nz * ny * nx
+from sopht_b200 import _lib
+_lib.profile_enable(True)
+for _ in range(reps):
+    s.vector_field_solve(sol, rhs)
+torch.cuda.synchronize()
+rep = _lib.profile_report()
+print("  " + "  ".join(f"{k.replace('poisson.', '')}={v['ms'] / reps:.3f}" for k, v in rep.items() if "nyq" not in k))
 print(f"poisson {s.path} ({nz},{ny},{nx}): {ms:.3f} ms per vector solve, {324 * n / ms / 1e6:.0f} GB/s algorithmic (324 B/cell)")

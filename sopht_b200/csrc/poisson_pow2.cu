@@ -124,8 +124,10 @@ int launch(const typename K::Params& p, dim3 grid, const char* label, cudaStream
     return launch_variant<K, AUTO, false>(p, grid, label, st);
   } else {
   // big radix-32 column kernels: 256 threads per CTA
-  const bool two = minb ? minb >= 2 : false;
-  bool staged = stg >= 0 ? stg != 0 : true;
+  // measured defaults (512^3, L = 1024; profiles/): the y passes run best as two 128-register CTAs per SM
+  // without staging, the fused z pass as one 255-register CTA with the next tile's inputs staged
+  const bool two = minb ? minb >= 2 : K::DEFAULT_TWO_CTAS;
+  bool staged = stg >= 0 ? stg != 0 : K::DEFAULT_STAGED;
   if (two) {
     if (staged && stage_fits<K>(AUTO)) return launch_variant<K, AUTO, true>(p, grid, label, st);
     return launch_variant<K, AUTO, false>(p, grid, label, st);

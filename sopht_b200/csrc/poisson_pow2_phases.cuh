@@ -132,6 +132,7 @@ struct YFwd {
   static constexpr int STAGE_ELEMS = (L / 2) * TX;
   static constexpr bool STAGE_SHARED = false;  // a thread reads back only what it copied itself
   static constexpr bool WANT_STAGE = Cfg<L>::E >= 32;
+  static constexpr bool DEFAULT_TWO_CTAS = true, DEFAULT_STAGED = false;
   FFT_HD static int niter(const Params&) { return 1; }
   FFT_HD static void init(const Params& p, int tid, float2* smem) {
     if (EXTRA_ELEMS) copy_table<THREADS>(smem + SMEM_ELEMS, p.tw, L, tid);
@@ -173,6 +174,7 @@ struct YInv {
   static constexpr int STAGE_ELEMS = L * TX;
   static constexpr bool STAGE_SHARED = false;
   static constexpr bool WANT_STAGE = Cfg<L>::E >= 32;
+  static constexpr bool DEFAULT_TWO_CTAS = true, DEFAULT_STAGED = false;
   FFT_HD static int niter(const Params&) { return 1; }
   FFT_HD static void init(const Params& p, int tid, float2* smem) {
     if (EXTRA_ELEMS) copy_table<THREADS>(smem + SMEM_ELEMS, p.tw, L, tid);
@@ -252,6 +254,8 @@ struct ZConv {
   static constexpr int STAGE_ELEMS = (L / 2) * TX;
   static constexpr bool STAGE_SHARED = false;
   static constexpr bool WANT_STAGE = Cfg<L>::E >= 32;
+  // L = 1024 (256 threads): one staged 255-register CTA; L = 512 (128 threads): four unstaged CTAs
+  static constexpr bool DEFAULT_TWO_CTAS = THREADS < 256, DEFAULT_STAGED = THREADS >= 256;
   FFT_HD static int niter(const Params& p) { return p.ncomp; }
   FFT_HD static void init(const Params& p, int tid, float2* smem) {
     if (EXTRA_ELEMS) copy_table<THREADS>(smem + SMEM_ELEMS, p.tw, L, tid);
@@ -346,6 +350,7 @@ struct XFwd {
   static constexpr int STAGE_ELEMS = (L / 2) * RX;
   static constexpr bool STAGE_SHARED = false;
   static constexpr bool WANT_STAGE = false;
+  static constexpr bool DEFAULT_TWO_CTAS = false, DEFAULT_STAGED = false;
   FFT_HD static int niter(const Params&) { return 1; }
   FFT_HD static void init(const Params& p, int tid, float2* smem) {
     if (EXTRA_ELEMS) {
@@ -413,6 +418,7 @@ struct XInv {
   static constexpr int STAGE_ELEMS = (L + 1) * RX;  // spectrum row + its Nyquist bin
   static constexpr bool STAGE_SHARED = true;        // bin k is combined with bin L-k, staged by another thread
   static constexpr bool WANT_STAGE = false;
+  static constexpr bool DEFAULT_TWO_CTAS = false, DEFAULT_STAGED = false;
   FFT_HD static int niter(const Params&) { return 1; }
   FFT_HD static void init(const Params& p, int tid, float2* smem) { XFwd<L, RX>::init(p, tid, smem); }
   FFT_HD static void prefetch(const Params& p, int bx, int, int, int tid, float2* stage) {

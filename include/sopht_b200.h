@@ -212,6 +212,14 @@ int sopht_penalise_field_boundary_3d(int dtype, const sopht_field_t *field, int 
                                      const double *ramp_x, const double *ramp_y,
                                      const double *ramp_z, void *stream);
 
+/* The same on a z-slab of a z-decomposed grid: `field` is the slab (nz_local planes), z_faces bit 0 / bit 1
+ * say whether the slab's low / high z face is the global boundary (3 = whole grid). A face that is not
+ * global is treated as interior. ref: penalise_field_boundary_3d.py:182-208 (the z part applies on the
+ * boundary ranks only; the x and y parts on every rank) */
+int sopht_penalise_field_boundary_3d_slab(int dtype, const sopht_field_t *field, int width,
+                                          const double *ramp_x, const double *ramp_y,
+                                          const double *ramp_z, int z_faces, void *stream);
+
 /* ------------------------------------------------------------------------ */
 /* 2D stencils                                                               */
 /* ------------------------------------------------------------------------ */
@@ -284,6 +292,37 @@ int sopht_poisson_green_hat(sopht_poisson_t handle, const void **device_ptr);
 const char *sopht_poisson_path(sopht_poisson_t handle);
 
 int sopht_poisson_destroy(sopht_poisson_t handle);
+
+/* ------------------------------------------------------------------------ */
+/* The same solve on a z-slab decomposed grid (fp32, power-of-two grids):     */
+/* the three LOCAL phases between the two all-to-all transposes, which the    */
+/* host layer issues on its own process group (NCCL). Rank r owns planes      */
+/* [r nz/P, (r+1) nz/P) of the fields and, for the y/z passes, the kx bins     */
+/* [r nx/P, (r+1) nx/P) of the half spectrum. Buffers are caller-owned device */
+/* memory of complex64 elements:                                              */
+/*   send / recv  (C, P, nz/P, ny, nx/P)  ==  (C, nz, ny, nx/P) after exchange */
+/*   work         (C, nz, 2 ny, nx/P)                                          */
+/*   nyquist_local (C, nz/P, ny), nyquist_all (C, nz, ny), nyquist_work (C, nz, 2 ny) */
+/* Sequence per solve (sopht_b200/parallel/slab_poisson.py):                  */
+/*   forward_x -> per component all-to-all(send -> recv), all-gather(nyquist)  */
+/*   -> yz -> per component all-to-all(recv -> send), slice nyquist -> inverse_x */
+/* ref: UnboundedPoissonSolverPYFFTW3D.py:111-172 (what is computed); the      */
+/* reference has no distributed path                            */
+/* ------------------------------------------------------------------------ */
+typedef struct sopht_poisson_slab *sopht_poisson_slab_t;
+
+int sopht_poisson_slab_create(sopht_poisson_slab_t *handle, int ncomp, int nz, int ny, int nx, int nranks,
+                              int rank, double dx, const double *mz, const double *my, const double *mx,
+                              double origin_value, void *stream);
+/* rhs_field: this rank's (C, nz/P, ny, nx) slab (strided view allowed) */
+int sopht_poisson_slab_forward_x(sopht_poisson_slab_t handle, const sopht_field_t *rhs_field,
+                                 void *send_buffer, void *nyquist_local, void *stream);
+/* y forward, z forward x G_hat x z inverse, y inverse on the kx-slab, in place in recv_buffer / nyquist_all */
+int sopht_poisson_slab_yz(sopht_poisson_slab_t handle, void *recv_buffer, void *nyquist_all,
+                          void *work_buffer, void *nyquist_work, void *stream);
+int sopht_poisson_slab_inverse_x(sopht_poisson_slab_t handle, const sopht_field_t *solution_field,
+                                 void *recv_buffer, void *nyquist_local, void *stream);
+int sopht_poisson_slab_destroy(sopht_poisson_slab_t handle);
 
 /* ------------------------------------------------------------------------ */
 /* Immersed boundary: Eulerian <-> Lagrangian transfer, 4-point delta kernels */

@@ -65,6 +65,7 @@ _SIGNATURES: dict[str, list[Any]] = {
     "sopht_advection_flux_eno3_3d": [_F, _F, _F, _D],
     "sopht_laplacian_filter_flux_3d": [_F, _F, _I],
     "sopht_penalise_field_boundary_3d": [_F, _I, _PD, _PD, _PD],
+    "sopht_penalise_field_boundary_3d_slab": [_F, _I, _PD, _PD, _PD, _I],
     "sopht_diffusion_flux_2d": [_F, _F, _D, _I],
     "sopht_advection_flux_eno3_2d": [_F, _F, _F, _D],
     "sopht_outplane_field_curl_2d": [_F, _F, _D, _I],
@@ -131,6 +132,15 @@ _HANDLE_SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "sopht_poisson_green_hat": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
     "sopht_poisson_path": (ctypes.c_char_p, [_P]),
     "sopht_poisson_destroy": (ctypes.c_int, [_P]),
+    # z-slab decomposed Poisson solve (local phases)
+    "sopht_poisson_slab_create": (
+        ctypes.c_int,
+        [ctypes.POINTER(_P), _I, _I, _I, _I, _I, _I, _D, _PD, _PD, _PD, _D, _P],
+    ),
+    "sopht_poisson_slab_forward_x": (ctypes.c_int, [_P, _F, _P, _P, _P]),
+    "sopht_poisson_slab_yz": (ctypes.c_int, [_P, _P, _P, _P, _P, _P]),
+    "sopht_poisson_slab_inverse_x": (ctypes.c_int, [_P, _F, _P, _P, _P]),
+    "sopht_poisson_slab_destroy": (ctypes.c_int, [_P]),
     # fused 3-D Navier-Stokes passes
     "sopht_ns3d_advect_rotational": (ctypes.c_int, [_I, _F, _F, _F, _D, _P]),
     "sopht_ns3d_diffuse": (ctypes.c_int, [_I, _F, _F, _D, _F, _P]),

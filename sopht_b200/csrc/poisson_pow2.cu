@@ -198,8 +198,9 @@ int launch_zconv(int L, const p2::ZParams& p, dim3 grid, cudaStream_t st) {
 
 // folded spectrum: gm[(fz*(ny+1) + fy)*nx + kx] (kx < nx), gn[fz*(ny+1) + fy] (kx = nx); x2 because the
 // half-length x transform's unnormalised round trip is nx * 2ny * 2nz, half the doubled cell count.
+// gm keeps the kx range [kx0, kx0 + g_row) only (the whole spectrum on one GPU, a rank's slice otherwise)
 __global__ void __launch_bounds__(256)
-    fold_green_kernel(float* gm, float* gn, const float* ghat, int nz, int ny, int nx) {
+    fold_green_kernel(float* gm, float* gn, const float* ghat, int nz, int ny, int nx, int kx0, int g_row) {
   const int64_t total = (int64_t)(nz + 1) * (ny + 1) * (nx + 1);
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total;
        q += (int64_t)gridDim.x * blockDim.x) {
@@ -207,10 +208,10 @@ __global__ void __launch_bounds__(256)
     const int64_t r = q / (nx + 1);
     const int fy = (int)(r % (ny + 1)), fz = (int)(r / (ny + 1));
     const float v = 2.0f * ghat[((int64_t)fz * 2 * ny + fy) * (nx + 1) + kx];
-    if (kx < nx)
-      gm[((int64_t)fz * (ny + 1) + fy) * nx + kx] = v;
-    else
+    if (kx == nx)
       gn[(int64_t)fz * (ny + 1) + fy] = v;
+    else if (kx >= kx0 && kx < kx0 + g_row)
+      gm[((int64_t)fz * (ny + 1) + fy) * g_row + (kx - kx0)] = v;
   }
 }
 
@@ -261,7 +262,7 @@ struct Pow2Poisson : PoissonImpl {
     const size_t rows = (size_t)3 * nz * ny;
     SOPHT_CUDA(cudaMalloc(&gm, sizeof(float) * (size_t)(nz + 1) * (ny + 1) * nx));
     SOPHT_CUDA(cudaMalloc(&gn, sizeof(float) * (size_t)(nz + 1) * (ny + 1)));
-    fold_green_kernel<<<148 * 8, 256, 0, st>>>(gm, gn, ghat_natural, nz, ny, nx);
+    fold_green_kernel<<<148 * 8, 256, 0, st>>>(gm, gn, ghat_natural, nz, ny, nx, 0, nx);
     SOPHT_CHECK_LAUNCH();
     SOPHT_CUDA(cudaMalloc(&A, sizeof(float2) * rows * nx));
     SOPHT_CUDA(cudaMalloc(&nyqA, sizeof(float2) * rows));
@@ -299,79 +300,128 @@ struct Pow2Poisson : PoissonImpl {
     }
     const int LY = 2 * ny, LZ = 2 * nz;
     const int64_t rows = (int64_t)C * nz * ny;
+    const p2::SlabDims d{C, nz, ny, nx, 1, 0};
     int rc;
-    p2::XParams xp{};
-    xp.real_in = reinterpret_cast<const float*>(rhs->data);
-    xp.sc = vec ? rhs->stride[0] : 0;
-    xp.sz = rhs->stride[o];
-    xp.sy = rhs->stride[o + 1];
-    xp.spec = A;
-    xp.nyq = nyqA;
-    xp.nz = nz;
-    xp.ny = ny;
-    xp.tw = twx;
-    xp.tw2 = twx2;
+    p2::XParams xp = p2::slab_x_params(d, reinterpret_cast<const float*>(rhs->data), nullptr,
+                                       vec ? rhs->stride[0] : 0, rhs->stride[o], rhs->stride[o + 1], A, nyqA,
+                                       twx, twx2);
     if ((rc = launch_xfwd(nx, xp, rows, st))) return rc;
-
-    p2::ColParams yp{};
-    yp.in = A;
-    yp.out = B;
-    yp.in_rs = nx, yp.in_cs = 1, yp.out_rs = nx, yp.out_cs = 1;
-    yp.in_bx = TX, yp.in_by = (int64_t)ny * nx, yp.out_bx = TX, yp.out_by = (int64_t)LY * nx;
-    yp.tw = twy;
-    if ((rc = launch_yfwd(LY, yp, dim3(nx / TX, C * nz, 1), st))) return rc;
-    p2::ColParams yn{};
-    yn.in = nyqA;
-    yn.out = nyqB;
-    yn.in_rs = 1, yn.in_cs = ny, yn.out_rs = 1, yn.out_cs = LY;
-    yn.in_bx = (int64_t)TX * ny, yn.in_by = 0, yn.out_bx = (int64_t)TX * LY, yn.out_by = 0;
-    yn.tw = twy;
-    if ((rc = launch_yfwd(LY, yn, dim3(C * nz / TX, 1, 1), st))) return rc;
-
-    p2::ZParams zp{};
-    zp.data = B;
-    zp.rs = (int64_t)LY * nx, zp.cs = 1, zp.d_bx = TX, zp.d_by = nx, zp.d_c = (int64_t)nz * LY * nx;
-    zp.ncomp = C;
-    zp.g = gm;
-    zp.g_zs = (int64_t)(ny + 1) * nx;
-    zp.g_ky_stride = nx;
-    zp.n2y = LY;
-    zp.nyq = 0;
-    zp.tw = twz;
-    if ((rc = launch_zconv(LZ, zp, dim3(nx / TX, LY, 1), st))) return rc;
-    p2::ZParams zn = zp;
-    zn.data = nyqB;
-    zn.rs = LY, zn.cs = 1, zn.d_bx = TX, zn.d_by = 0, zn.d_c = (int64_t)nz * LY;
-    zn.g = gn;
-    zn.g_zs = ny + 1;
-    zn.g_ky_stride = 1;
-    zn.nyq = 1;
-    if ((rc = launch_zconv(LZ, zn, dim3(LY / TX, 1, 1), st))) return rc;
-
-    p2::ColParams yi{};
-    yi.in = B;
-    yi.out = A;
-    yi.in_rs = nx, yi.in_cs = 1, yi.out_rs = nx, yi.out_cs = 1;
-    yi.in_bx = TX, yi.in_by = (int64_t)LY * nx, yi.out_bx = TX, yi.out_by = (int64_t)ny * nx;
-    yi.tw = twy;
-    if ((rc = launch_yinv(LY, yi, dim3(nx / TX, C * nz, 1), st))) return rc;
-    p2::ColParams yni{};
-    yni.in = nyqB;
-    yni.out = nyqA;
-    yni.in_rs = 1, yni.in_cs = LY, yni.out_rs = 1, yni.out_cs = ny;
-    yni.in_bx = (int64_t)TX * LY, yni.in_by = 0, yni.out_bx = (int64_t)TX * ny, yni.out_by = 0;
-    yni.tw = twy;
-    if ((rc = launch_yinv(LY, yni, dim3(C * nz / TX, 1, 1), st))) return rc;
-
-    xp.real_out = reinterpret_cast<float*>(sol->data);
-    xp.sc = vec ? sol->stride[0] : 0;
-    xp.sz = sol->stride[o];
-    xp.sy = sol->stride[o + 1];
+    if ((rc = launch_yfwd(LY, p2::slab_y_params(d, TX, A, B, true, twy), dim3(nx / TX, C * nz, 1), st)))
+      return rc;
+    if ((rc = launch_yfwd(LY, p2::nyquist_y_params(d, TX, nyqA, nyqB, true, twy), dim3(C * nz / TX, 1, 1), st)))
+      return rc;
+    if ((rc = launch_zconv(LZ, p2::slab_z_params(d, TX, B, gm, nx, 0, twz), dim3(nx / TX, LY, 1), st)))
+      return rc;
+    if ((rc = launch_zconv(LZ, p2::nyquist_z_params(d, TX, nyqB, gn, twz), dim3(LY / TX, 1, 1), st))) return rc;
+    if ((rc = launch_yinv(LY, p2::slab_y_params(d, TX, B, A, false, twy), dim3(nx / TX, C * nz, 1), st)))
+      return rc;
+    if ((rc = launch_yinv(LY, p2::nyquist_y_params(d, TX, nyqB, nyqA, false, twy), dim3(C * nz / TX, 1, 1), st)))
+      return rc;
+    xp = p2::slab_x_params(d, nullptr, reinterpret_cast<float*>(sol->data), vec ? sol->stride[0] : 0,
+                           sol->stride[o], sol->stride[o + 1], A, nyqA, twx, twx2);
     return launch_xinv(nx, xp, rows, st);
   }
 
   const void* green_hat() const override { return ghat_natural; }
   const char* path_name() const override { return "pow2"; }
+};
+
+
+// ---- z-slab decomposed solve: the three local phases between the all-to-all transposes ----------------------
+// (the exchanges themselves are issued by the host layer on its process group; see SlabDims in
+// poisson_pow2_phases.cuh and sopht_b200/parallel/slab_poisson.py)
+struct SlabPow2Poisson {
+  p2::SlabDims d{};
+  float *gm = nullptr, *gn = nullptr;  // this rank's kx slice of the folded G_hat, and the Nyquist plane's
+  float2 *twx = nullptr, *twx2 = nullptr, *twy = nullptr, *twz = nullptr;
+
+  ~SlabPow2Poisson() {
+    cudaFree(gm);
+    cudaFree(gn);
+    cudaFree(twx);
+    cudaFree(twx2);
+    cudaFree(twy);
+    cudaFree(twz);
+  }
+
+  int init(double dx, const double* mz, const double* my, const double* mx, double origin, cudaStream_t st) {
+    const int nz = d.nz, ny = d.ny, nx = d.nx, nxl = d.nxl();
+    float* ghat = nullptr;
+    int rc = build_green_hat<float>(&ghat, 3, nz, ny, nx, dx, mz, my, mx, origin, st);
+    if (rc) return rc;
+    auto fail = [&](int code) {
+      cudaFree(ghat);
+      return code;
+    };
+    if (cudaMalloc(&gm, sizeof(float) * (size_t)(nz + 1) * (ny + 1) * nxl) != cudaSuccess ||
+        cudaMalloc(&gn, sizeof(float) * (size_t)(nz + 1) * (ny + 1)) != cudaSuccess) {
+      set_error("poisson(slab): out of device memory for the Green's function slice");
+      return fail(SOPHT_ERR_ALLOC);
+    }
+    fold_green_kernel<<<148 * 8, 256, 0, st>>>(gm, gn, ghat, nz, ny, nx, d.rank * nxl, nxl);
+    g_launch_count++;
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+      set_error("poisson(slab): folding the Green's function failed");
+      return fail(SOPHT_ERR_CUDA);
+    }
+    cudaFree(ghat);
+    if ((rc = Pow2Poisson::upload_twiddles(&twx, nx, nx, st))) return rc;
+    if ((rc = Pow2Poisson::upload_twiddles(&twx2, nx, 2 * nx, st))) return rc;
+    if ((rc = Pow2Poisson::upload_twiddles(&twy, 2 * ny, 2 * ny, st))) return rc;
+    if ((rc = Pow2Poisson::upload_twiddles(&twz, 2 * nz, 2 * nz, st))) return rc;
+    return SOPHT_OK;
+  }
+
+  static bool real_view_ok(const sopht_field_t* f) {
+    if (f->ndim != 4 || f->stride[3] != 1) return false;
+    if ((reinterpret_cast<uintptr_t>(f->data) & 7) != 0) return false;
+    return !((f->stride[0] | f->stride[1] | f->stride[2]) & 1);
+  }
+
+  int check_local(const char* fn, const sopht_field_t* f) const {
+    if (!valid_field(f, 4, 4) || f->shape[0] != d.C || f->shape[1] != d.nzl() || f->shape[2] != d.ny ||
+        f->shape[3] != d.nx)
+      SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: expected this rank's (%d, %d, %d, %d) z-slab", fn, d.C, d.nzl(), d.ny,
+                 d.nx);
+    if (!real_view_ok(f))
+      SOPHT_FAIL(SOPHT_ERR_STRIDE, "%s: rows must be contiguous, 8-byte aligned, even plane/row strides", fn);
+    return SOPHT_OK;
+  }
+
+  int forward_x(const sopht_field_t* rhs, float2* send, float2* nyq_local, cudaStream_t st) const {
+    int rc = check_local(__func__, rhs);
+    if (rc) return rc;
+    const p2::XParams xp =
+        p2::slab_x_params(d, reinterpret_cast<const float*>(rhs->data), nullptr, rhs->stride[0], rhs->stride[1],
+                          rhs->stride[2], send, nyq_local, twx, twx2);
+    return launch_xfwd(d.nx, xp, (int64_t)d.C * d.nzl() * d.ny, st);
+  }
+
+  int yz(float2* recv, float2* nyq_all, float2* work, float2* nyq_work, cudaStream_t st) const {
+    const int LY = 2 * d.ny, LZ = 2 * d.nz, nxl = d.nxl();
+    int rc;
+    if ((rc = launch_yfwd(LY, p2::slab_y_params(d, TX, recv, work, true, twy), dim3(nxl / TX, d.C * d.nz, 1), st)))
+      return rc;
+    if ((rc = launch_yfwd(LY, p2::nyquist_y_params(d, TX, nyq_all, nyq_work, true, twy),
+                          dim3(d.C * d.nz / TX, 1, 1), st)))
+      return rc;
+    if ((rc = launch_zconv(LZ, p2::slab_z_params(d, TX, work, gm, nxl, 0, twz), dim3(nxl / TX, LY, 1), st)))
+      return rc;
+    if ((rc = launch_zconv(LZ, p2::nyquist_z_params(d, TX, nyq_work, gn, twz), dim3(LY / TX, 1, 1), st)))
+      return rc;
+    if ((rc = launch_yinv(LY, p2::slab_y_params(d, TX, work, recv, false, twy), dim3(nxl / TX, d.C * d.nz, 1), st)))
+      return rc;
+    return launch_yinv(LY, p2::nyquist_y_params(d, TX, nyq_work, nyq_all, false, twy),
+                       dim3(d.C * d.nz / TX, 1, 1), st);
+  }
+
+  int inverse_x(const sopht_field_t* sol, float2* recv2, float2* nyq_local, cudaStream_t st) const {
+    int rc = check_local(__func__, sol);
+    if (rc) return rc;
+    const p2::XParams xp = p2::slab_x_params(d, nullptr, reinterpret_cast<float*>(sol->data), sol->stride[0],
+                                             sol->stride[1], sol->stride[2], recv2, nyq_local, twx, twx2);
+    return launch_xinv(d.nx, xp, (int64_t)d.C * d.nzl() * d.ny, st);
+  }
 };
 
 }  // namespace
@@ -397,3 +447,66 @@ PoissonImpl* make_pow2_poisson(int nz, int ny, int nx, double dx, const double* 
 }
 
 }  // namespace sopht
+
+using namespace sopht;
+
+struct sopht_poisson_slab {
+  SlabPow2Poisson impl;
+};
+
+extern "C" {
+
+int sopht_poisson_slab_create(sopht_poisson_slab_t* handle, int ncomp, int nz, int ny, int nx, int nranks,
+                              int rank, double dx, const double* mz, const double* my, const double* mx,
+                              double origin_value, void* stream) {
+  if (!handle) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: null handle pointer", __func__);
+  if (!pow2_poisson_eligible(SOPHT_F32, 3, nz, ny, nx))
+    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: the slab solver needs a power-of-two fp32 3-D grid", __func__);
+  if (ncomp < 1 || ncomp > 3) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: 1..3 components", __func__);
+  if (nranks < 1 || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks)
+    SOPHT_FAIL(SOPHT_ERR_ARG, "%s: nranks must be a power of two and 0 <= rank < nranks", __func__);
+  if (nz % nranks || nx % nranks || (nx / nranks) % TX || ((int64_t)ncomp * (nz / nranks) * ny) % 32 ||
+      (ncomp * nz) % TX)
+    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: nz/nranks planes and nx/nranks >= %d kx bins per rank are required",
+               __func__, TX);
+  if (!mz || !my || !mx) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: null Green's function coordinate arrays", __func__);
+  auto* h = new sopht_poisson_slab();
+  h->impl.d = p2::SlabDims{ncomp, nz, ny, nx, nranks, rank};
+  const int rc = h->impl.init(dx, mz, my, mx, origin_value, as_stream(stream));
+  if (rc) {
+    delete h;
+    return rc;
+  }
+  *handle = h;
+  return SOPHT_OK;
+}
+
+int sopht_poisson_slab_forward_x(sopht_poisson_slab_t h, const sopht_field_t* rhs_field, void* send_buffer,
+                                 void* nyquist_local, void* stream) {
+  if (!h || !send_buffer || !nyquist_local) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
+  return h->impl.forward_x(rhs_field, reinterpret_cast<float2*>(send_buffer),
+                           reinterpret_cast<float2*>(nyquist_local), as_stream(stream));
+}
+
+int sopht_poisson_slab_yz(sopht_poisson_slab_t h, void* recv_buffer, void* nyquist_all, void* work_buffer,
+                          void* nyquist_work, void* stream) {
+  if (!h || !recv_buffer || !nyquist_all || !work_buffer || !nyquist_work)
+    SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
+  return h->impl.yz(reinterpret_cast<float2*>(recv_buffer), reinterpret_cast<float2*>(nyquist_all),
+                    reinterpret_cast<float2*>(work_buffer), reinterpret_cast<float2*>(nyquist_work),
+                    as_stream(stream));
+}
+
+int sopht_poisson_slab_inverse_x(sopht_poisson_slab_t h, const sopht_field_t* solution_field, void* recv_buffer,
+                                 void* nyquist_local, void* stream) {
+  if (!h || !recv_buffer || !nyquist_local) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
+  return h->impl.inverse_x(solution_field, reinterpret_cast<float2*>(recv_buffer),
+                           reinterpret_cast<float2*>(nyquist_local), as_stream(stream));
+}
+
+int sopht_poisson_slab_destroy(sopht_poisson_slab_t h) {
+  delete h;
+  return SOPHT_OK;
+}
+
+}  // extern "C"

@@ -316,6 +316,20 @@ struct XParams {
   int nz, ny;              // row = (c*nz + z)*ny + y
   const float2* tw;        // forward twiddles, length L = nx
   const float2* tw2;       // exp(-2 pi i k / (2 nx)), k = 0..nx-1
+  // Address of bin k of spectrum row `row` in `spec` (complex elements):
+  //   (row >> rpc_shift) * comp_stride + (row & rpc_mask) * chunk_len + (k >> chunk_shift) * chunk_stride
+  //   + (k & (chunk_len - 1)),   chunk_len = 1 << chunk_shift.
+  // One GPU: chunk_len = L, comp_stride = rows_per_component * L (plain (rows, L) rows). Slab-decomposed
+  // solve: spec is the all-to-all buffer (C, P, nz_local, ny, nx/P) - the kx range of rank r is chunk r -
+  // so the transposes need no pack / unpack pass.
+  int rpc_shift, chunk_shift;
+  int64_t comp_stride, chunk_stride;
+  FFT_HD int64_t row_base(int64_t row) const {
+    return (row >> rpc_shift) * comp_stride + ((row & (((int64_t)1 << rpc_shift) - 1)) << chunk_shift);
+  }
+  FFT_HD int64_t bin(int k) const {
+    return (int64_t)(k >> chunk_shift) * chunk_stride + (k & ((1 << chunk_shift) - 1));
+  }
 };
 
 template <int L>
@@ -388,7 +402,7 @@ struct XFwd {
       fft::fwd_last<L>(sm, t, InPlaceSink<L>{sm});
     } else if (P == NP) {
       // X_k = E_k + w^k O_k, E = (Z_k + conj Z_{L-k})/2, O = (Z_k - conj Z_{L-k})/(2i); X_L = E_0 - O_0
-      float2* out = p.spec + row * L;
+      float2* out = p.spec + p.row_base(row);
 #pragma unroll
       for (int q = 0; q < Cfg<L>::E; ++q) {
         const int k = t + q * T;
@@ -396,7 +410,7 @@ struct XFwd {
         const float2 b = sm(fft::spectrum_position<L>((L - k) & (L - 1)));
         const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
         const float2 o = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
-        out[k] = fft::cadd(e, fft::cmul(o, tw2[k]));
+        out[p.bin(k)] = fft::cadd(e, fft::cmul(o, tw2[k]));
         if (k == 0) p.nyq[row] = make_float2(e.x - o.x, e.y - o.y);
       }
     } else {
@@ -424,10 +438,10 @@ struct XInv {
   FFT_HD static void prefetch(const Params& p, int bx, int, int, int tid, float2* stage) {
     const int t = tid % T, r = tid / T;
     const int64_t row = (int64_t)bx * RX + r;
-    const float2* in = p.spec + row * L;
+    const float2* in = p.spec + p.row_base(row);
     float2* s = stage + r * (L + 1);
 #pragma unroll
-    for (int q = 0; q < Cfg<L>::E; ++q) fft::async_copy8(s + t + q * T, in + t + q * T);
+    for (int q = 0; q < Cfg<L>::E; ++q) fft::async_copy8(s + t + q * T, in + p.bin(t + q * T));
     if (t == 0) fft::async_copy8(s + L, p.nyq + row);
   }
   template <int P>
@@ -439,13 +453,13 @@ struct XInv {
     const float2* tw2 = EXTRA_ELEMS ? smem + SMEM_ELEMS + L : p.tw2;
     if (P == 0) {
       // Z_k = E_k + i O_k, E = (X_k + conj X_{L-k})/2, O = conj(w^k) (X_k - conj X_{L-k})/2
-      const float2* in = stage ? stage + r * (L + 1) : p.spec + row * L;
+      const float2* in = stage ? stage + r * (L + 1) : p.spec + p.row_base(row);
       const float2* nq = stage ? stage + r * (L + 1) + L : p.nyq + row;
 #pragma unroll
       for (int q = 0; q < Cfg<L>::E; ++q) {
         const int k = t + q * T;
-        const float2 a = in[k];
-        const float2 b = k == 0 ? *nq : in[L - k];
+        const float2 a = stage ? in[k] : in[p.bin(k)];
+        const float2 b = k == 0 ? *nq : (stage ? in[L - k] : in[p.bin(L - k)]);
         const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
         const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
         const float2 o = fft::cmul_conj(d, tw2[k]);
@@ -461,6 +475,103 @@ struct XInv {
     }
   }
 };
+
+// ---- parameter blocks of the pipeline, shared by the library (poisson_pow2.cu) and the host emulation ---------
+// Whole grid on one GPU: P = 1. z-slab decomposition over P ranks (nz_local = nz / P planes per rank for the
+// x passes, kx range of nx / P bins per rank for the y and z passes):
+//   x forward (z-slab)  -> all-to-all per component ->  y forward, z convolution, y inverse (kx-slab)
+//                       -> all-to-all back           ->  x inverse (z-slab)
+// The kx = nx (Nyquist) plane is all-gathered and processed redundantly by every rank.
+struct SlabDims {
+  int C, nz, ny, nx, P, rank;
+  FFT_HD int nzl() const { return nz / P; }
+  FFT_HD int nxl() const { return nx / P; }
+};
+FFT_HD int ilog2(int64_t v) {
+  int s = 0;
+  while (((int64_t)1 << s) < v) ++s;
+  return s;
+}
+// x passes on this rank's z-slab; `spec` is (C, P, nzl, ny, nxl) complex, `nyq` (C, nzl, ny)
+inline XParams slab_x_params(const SlabDims& d, const float* real_in, float* real_out, int64_t sc, int64_t sz,
+                             int64_t sy, float2* spec, float2* nyq, const float2* tw, const float2* tw2) {
+  XParams xp{};
+  xp.real_in = real_in;
+  xp.real_out = real_out;
+  xp.sc = sc, xp.sz = sz, xp.sy = sy;
+  xp.spec = spec;
+  xp.nyq = nyq;
+  xp.nz = d.nzl();
+  xp.ny = d.ny;
+  xp.tw = tw;
+  xp.tw2 = tw2;
+  xp.rpc_shift = ilog2((int64_t)d.nzl() * d.ny);
+  xp.chunk_shift = ilog2(d.nxl());
+  xp.chunk_stride = (int64_t)d.nzl() * d.ny * d.nxl();
+  xp.comp_stride = xp.chunk_stride * d.P;
+  return xp;
+}
+// y passes on this rank's kx-slab: a = (C, nz, ny, nxl), b = (C, nz, 2ny, nxl); grid (nxl / TX, C * nz)
+inline ColParams slab_y_params(const SlabDims& d, int TX, const float2* in, float2* out, bool forward,
+                               const float2* tw) {
+  const int64_t nxl = d.nxl(), LY = 2 * d.ny;
+  ColParams yp{};
+  yp.in = in;
+  yp.out = out;
+  yp.in_rs = nxl, yp.in_cs = 1, yp.out_rs = nxl, yp.out_cs = 1;
+  yp.in_bx = TX, yp.out_bx = TX;
+  yp.in_by = (forward ? d.ny : LY) * nxl;
+  yp.out_by = (forward ? LY : d.ny) * nxl;
+  yp.tw = tw;
+  return yp;
+}
+// Nyquist plane (C, nz, ny) <-> (C, nz, 2ny): columns are the (c, z) index; grid (C * nz / TX, 1)
+inline ColParams nyquist_y_params(const SlabDims& d, int TX, const float2* in, float2* out, bool forward,
+                                  const float2* tw) {
+  const int64_t LY = 2 * d.ny;
+  ColParams yn{};
+  yn.in = in;
+  yn.out = out;
+  yn.in_rs = 1, yn.out_rs = 1;
+  yn.in_cs = forward ? d.ny : LY;
+  yn.out_cs = forward ? LY : d.ny;
+  yn.in_bx = TX * yn.in_cs, yn.in_by = 0, yn.out_bx = TX * yn.out_cs, yn.out_by = 0;
+  yn.tw = tw;
+  return yn;
+}
+// z pass on the kx-slab b = (C, nz, 2ny, nxl); gm is the folded G_hat stored as (nz+1, ny+1, g_row) whose
+// column g_kx0 is this rank's first kx bin (whole spectrum: g_row = nx, g_kx0 = rank * nxl; a per-rank slice:
+// g_row = nxl, g_kx0 = 0); grid (nxl / TX, 2ny)
+inline ZParams slab_z_params(const SlabDims& d, int TX, float2* b, const float* gm, int g_row, int g_kx0,
+                             const float2* tw) {
+  const int64_t nxl = d.nxl(), LY = 2 * d.ny;
+  ZParams zp{};
+  zp.data = b;
+  zp.rs = LY * nxl, zp.cs = 1, zp.d_bx = TX, zp.d_by = nxl, zp.d_c = (int64_t)d.nz * LY * nxl;
+  zp.ncomp = d.C;
+  zp.g = gm + g_kx0;
+  zp.g_zs = (int64_t)(d.ny + 1) * g_row;
+  zp.g_ky_stride = g_row;
+  zp.n2y = (int)LY;
+  zp.nyq = 0;
+  zp.tw = tw;
+  return zp;
+}
+// z pass on the Nyquist plane (C, nz, 2ny); gn is (nz+1, ny+1); grid (2ny / TX, 1)
+inline ZParams nyquist_z_params(const SlabDims& d, int TX, float2* b, const float* gn, const float2* tw) {
+  const int64_t LY = 2 * d.ny;
+  ZParams zn{};
+  zn.data = b;
+  zn.rs = LY, zn.cs = 1, zn.d_bx = TX, zn.d_by = 0, zn.d_c = (int64_t)d.nz * LY;
+  zn.ncomp = d.C;
+  zn.g = gn;
+  zn.g_zs = d.ny + 1;
+  zn.g_ky_stride = 1;
+  zn.n2y = (int)LY;
+  zn.nyq = 1;
+  zn.tw = tw;
+  return zn;
+}
 
 }  // namespace p2
 }  // namespace sopht

@@ -218,47 +218,53 @@ struct RampTable {
   double v[3][16];  // per axis: front ramp (w values) then back ramp (w values); w <= 8
 };
 
+// z_faces: bit 0 = the low-z face of this view is a global boundary, bit 1 = the high-z face is (both set
+// for a whole grid; a z-slab of a decomposed grid sets only the faces it owns, its other z side is interior).
 template <typename T>
 __global__ void __launch_bounds__(128)
-    penalise_shell_kernel(View3<T> f, int nz, int ny, int nx, int w, RampTable ramps, int face) {
-  // face 0: z-shell (both z faces of the inner box, all y,x in the box)
+    penalise_shell_kernel(View3<T> f, int nz, int ny, int nx, int w, RampTable ramps, int face, int z_faces) {
+  // face 0: z-shell (the owned z faces of the inner box, all y,x in the box)
   // face 1: y-shell excluding z-shell cells; face 2: x-shell excluding z- and y-shell cells
-  const int lz = nz - 2 * w + 2, ly = ny - 2 * w + 2, lx = nx - 2 * w + 2;  // inner box extent
-  int a, b, c;                                                              // box-local (z,y,x)
+  const bool zlo = z_faces & 1, zhi = z_faces & 2;
+  const int za = zlo ? w - 1 : 0, zb = zhi ? nz - w : nz - 1;  // inner box z extent [za, zb]
+  const int ly = ny - 2 * w + 2, lx = nx - 2 * w + 2;           // inner box extent in y, x
+  const int zin0 = za + (zlo ? 1 : 0), zin1 = zb - (zhi ? 1 : 0);  // z planes not on an owned z-shell
+  int sk, b, c;                                                  // source z index, box-local (y,x)
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int u = blockIdx.y;
   const int s = blockIdx.z;  // 0: front, 1: back
   if (face == 0) {
     if (t >= lx || u >= ly) return;
-    if (s == 1 && lz == 1) return;
-    a = s ? lz - 1 : 0;
+    if (s == 0 && !zlo) return;
+    if (s == 1 && (!zhi || (zlo && zb == za))) return;
+    sk = s ? zb : za;
     b = u;
     c = t;
   } else if (face == 1) {
-    if (t >= lx || u >= lz - 2) return;
+    if (t >= lx || u > zin1 - zin0) return;
     if (s == 1 && ly == 1) return;
-    a = u + 1;
+    sk = zin0 + u;
     b = s ? ly - 1 : 0;
     c = t;
   } else {
-    if (t >= ly - 2 || u >= lz - 2) return;
+    if (t >= ly - 2 || u > zin1 - zin0) return;
     if (s == 1 && lx == 1) return;
-    a = u + 1;
+    sk = zin0 + u;
     b = t + 1;
     c = s ? lx - 1 : 0;
   }
-  const int sk = a + w - 1, sj = b + w - 1, si = c + w - 1;  // source cell
+  const int sj = b + w - 1, si = c + w - 1;  // source cell
   const T val = f(sk, sj, si);
   // target ranges along each axis
   int kz0 = sk, kz1 = sk + 1, jy0 = sj, jy1 = sj + 1, ix0 = si, ix1 = si + 1;
-  if (sk == w - 1) kz0 = 0;
-  if (sk == nz - w) kz1 = nz;
+  if (zlo && sk == w - 1) kz0 = 0;
+  if (zhi && sk == nz - w) kz1 = nz;
   if (sj == w - 1) jy0 = 0;
   if (sj == ny - w) jy1 = ny;
   if (si == w - 1) ix0 = 0;
   if (si == nx - w) ix1 = nx;
   for (int k = kz0; k < kz1; ++k) {
-    const bool zr = k < w || k >= nz - w;
+    const bool zr = (zlo && k < w) || (zhi && k >= nz - w);
     const T rz = zr ? (T)ramps.v[2][k < w ? k : k - (nz - 2 * w)] : T(1);
     for (int j = jy0; j < jy1; ++j) {
       const bool yr = j < w || j >= ny - w;
@@ -277,29 +283,32 @@ __global__ void __launch_bounds__(128)
 
 template <typename T>
 static int penalise3d_impl(const View3<T>& f, int nz, int ny, int nx, int w, const double* rx,
-                           const double* ry, const double* rz, cudaStream_t st) {
+                           const double* ry, const double* rz, int z_faces, cudaStream_t st) {
   RampTable tab;
   for (int q = 0; q < 2 * w; ++q) {
     tab.v[0][q] = rx[q];
     tab.v[1][q] = ry[q];
     tab.v[2][q] = rz[q];
   }
-  const int lz = nz - 2 * w + 2, ly = ny - 2 * w + 2, lx = nx - 2 * w + 2;
+  const bool zlo = z_faces & 1, zhi = z_faces & 2;
+  const int za = zlo ? w - 1 : 0, zb = zhi ? nz - w : nz - 1;
+  const int nin = (zb - (zhi ? 1 : 0)) - (za + (zlo ? 1 : 0)) + 1;  // z planes off the owned z-shells
+  const int ly = ny - 2 * w + 2, lx = nx - 2 * w + 2;
   SOPHT_PROF("penalise_field_boundary", st);
   dim3 block(128, 1, 1);
-  {
+  if (z_faces) {
     dim3 grid((lx + 127) / 128, ly, 2);
-    penalise_shell_kernel<T><<<grid, block, 0, st>>>(f, nz, ny, nx, w, tab, 0);
+    penalise_shell_kernel<T><<<grid, block, 0, st>>>(f, nz, ny, nx, w, tab, 0, z_faces);
     SOPHT_CHECK_LAUNCH();
   }
-  if (lz > 2) {
-    dim3 grid((lx + 127) / 128, lz - 2, 2);
-    penalise_shell_kernel<T><<<grid, block, 0, st>>>(f, nz, ny, nx, w, tab, 1);
+  if (nin > 0) {
+    dim3 grid((lx + 127) / 128, nin, 2);
+    penalise_shell_kernel<T><<<grid, block, 0, st>>>(f, nz, ny, nx, w, tab, 1, z_faces);
     SOPHT_CHECK_LAUNCH();
   }
-  if (lz > 2 && ly > 2) {
-    dim3 grid((ly - 2 + 127) / 128, lz - 2, 2);
-    penalise_shell_kernel<T><<<grid, block, 0, st>>>(f, nz, ny, nx, w, tab, 2);
+  if (nin > 0 && ly > 2) {
+    dim3 grid((ly - 2 + 127) / 128, nin, 2);
+    penalise_shell_kernel<T><<<grid, block, 0, st>>>(f, nz, ny, nx, w, tab, 2, z_faces);
     SOPHT_CHECK_LAUNCH();
   }
   return SOPHT_OK;
@@ -543,35 +552,48 @@ int sopht_laplacian_filter_flux_3d(int dtype, const sopht_field_t* filter_flux,
   return SOPHT_OK;
 }
 
-int sopht_penalise_field_boundary_3d(int dtype, const sopht_field_t* field, int width,
-                                     const double* ramp_x, const double* ramp_y,
-                                     const double* ramp_z, void* stream) {
+static int penalise3d_entry(const char* fn, int dtype, const sopht_field_t* field, int width,
+                            const double* ramp_x, const double* ramp_y, const double* ramp_z, int z_faces,
+                            void* stream) {
   SOPHT_CHECK_DTYPE(dtype);
-  if (width < 0 || width > 8)
-    SOPHT_FAIL(SOPHT_ERR_ARG, "%s: width must be in [0, 8]", __func__);
+  if (width < 0 || width > 8) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: width must be in [0, 8]", fn);
+  if (z_faces < 0 || z_faces > 3) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: z_faces must be in [0, 3]", fn);
   if (width == 0) return SOPHT_OK;
   if (!valid_field(field, 3, 4) || (field->ndim == 4 && field->shape[0] != 3) || !fits_int(field))
-    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: expected (nz,ny,nx) or (3,nz,ny,nx)", __func__);
-  if (!ramp_x || !ramp_y || !ramp_z) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: null ramp table", __func__);
+    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: expected (nz,ny,nx) or (3,nz,ny,nx)", fn);
+  if (!ramp_x || !ramp_y || !ramp_z) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: null ramp table", fn);
   const int nz = (int)field->shape[field->ndim - 3];
   const int ny = (int)field->shape[field->ndim - 2];
   const int nx = (int)field->shape[field->ndim - 1];
-  if (nz < 2 * width || ny < 2 * width || nx < 2 * width)
-    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid smaller than twice the penalisation width", __func__);
+  const int zneed = ((z_faces & 1) ? width : 0) + ((z_faces & 2) ? width : 0);
+  if (nz < zneed || nz < 1 || ny < 2 * width || nx < 2 * width)
+    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid smaller than twice the penalisation width", fn);
   cudaStream_t st = as_stream(stream);
   const int ncomp = field->ndim == 4 ? 3 : 1;
   for (int c = 0; c < ncomp; ++c) {
     int rc;
     if (dtype == SOPHT_F32)
       rc = penalise3d_impl<float>(field->ndim == 4 ? comp3<float>(field, c) : scalar3<float>(field),
-                                  nz, ny, nx, width, ramp_x, ramp_y, ramp_z, st);
+                                  nz, ny, nx, width, ramp_x, ramp_y, ramp_z, z_faces, st);
     else
       rc = penalise3d_impl<double>(
           field->ndim == 4 ? comp3<double>(field, c) : scalar3<double>(field), nz, ny, nx, width,
-          ramp_x, ramp_y, ramp_z, st);
+          ramp_x, ramp_y, ramp_z, z_faces, st);
     if (rc) return rc;
   }
   return SOPHT_OK;
+}
+
+int sopht_penalise_field_boundary_3d(int dtype, const sopht_field_t* field, int width,
+                                     const double* ramp_x, const double* ramp_y,
+                                     const double* ramp_z, void* stream) {
+  return penalise3d_entry(__func__, dtype, field, width, ramp_x, ramp_y, ramp_z, 3, stream);
+}
+
+int sopht_penalise_field_boundary_3d_slab(int dtype, const sopht_field_t* field, int width,
+                                          const double* ramp_x, const double* ramp_y,
+                                          const double* ramp_z, int z_faces, void* stream) {
+  return penalise3d_entry(__func__, dtype, field, width, ramp_x, ramp_y, ramp_z, z_faces, stream);
 }
 
 }  // extern "C"

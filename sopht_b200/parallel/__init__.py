@@ -1,0 +1,16 @@
+"""z-slab decomposition of the 3-D unbounded flow step over the GPUs of one box:
+one process per GPU, torch.distributed (NCCL over NVLink) for the halo exchanges and the two all-to-all
+transposes of the distributed FFT Poisson solve; the compute phases are the same CUDA kernels the
+single-GPU path uses."""
+
+from .slab import SlabPartition, exchange_halos
+from .slab_flow import SlabUnboundedNavierStokesFlowSimulator3D
+from .slab_poisson import SlabTransposePlan, SlabUnboundedPoissonSolver3D
+
+__all__ = [
+    "SlabPartition",
+    "SlabTransposePlan",
+    "SlabUnboundedNavierStokesFlowSimulator3D",
+    "SlabUnboundedPoissonSolver3D",
+    "exchange_halos",
+]

@@ -1,0 +1,142 @@
+"""3-D unbounded Navier-Stokes flow simulator on a z-slab decomposed grid (one process per GPU).
+
+Same step as UnboundedNavierStokesFlowSimulator3D (sopht/simulator/flow/navier_stokes_flow_simulators.py:
+449-498, fused form in sopht_b200/simulator/flow/navier_stokes_flow_simulators.py), per rank on its slab:
+
+    halo(w, u) -> advect -> halo(buf) -> diffuse -> penalise (z faces only on the boundary ranks)
+    -> slab Poisson (two all-to-all transposes) -> halo(psi) -> velocity (+ local max for dt) -> [all-reduce max]
+
+Local arrays are (3, nz/P + 2, ny, nx) with one halo plane per z side; kernels see views chosen so that
+their ghost-ring rule lands on the true global boundary (SlabPartition.stencil_view).
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Any
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from sopht_b200 import _lib
+from sopht_b200.numeric.eulerian_grid_ops.stencil_ops_3d import _sine_ramps
+from sopht_b200.simulator.flow.navier_stokes_flow_simulators import stable_timestep_from_max
+
+from .slab import SlabPartition, exchange_halos
+from .slab_poisson import SlabUnboundedPoissonSolver3D
+
+
+class SlabUnboundedNavierStokesFlowSimulator3D:
+    """Constructor mirrors UnboundedNavierStokesFlowSimulator3D; `grid_size` is the GLOBAL (nz, ny, nx).
+
+    Public field attributes hold this rank's slab INCLUDING the two halo planes; use `owned(field)` for the
+    (3, nz/P, ny, nx) planes this rank owns and `z_slice` for their global z range."""
+
+    def __init__(
+        self,
+        grid_size: tuple[int, int, int],
+        x_range: float,
+        kinematic_viscosity: float,
+        cfl: float = 0.1,
+        real_t: type = np.float32,
+        num_threads: int = 1,
+        time: float = 0.0,
+        with_free_stream_flow: bool = False,
+        group: Any = None,
+        **kwargs: Any,
+    ) -> None:
+        if _lib.dtype_code(real_t) != _lib.SOPHT_F32:
+            msg = "the slab-decomposed simulator is implemented for fp32"
+            raise ValueError(msg)
+        self.grid_dim = 3
+        self.grid_size = tuple(grid_size)
+        self.x_range, self.real_t, self.num_threads, self.time = x_range, real_t, num_threads, time
+        self.kinematic_viscosity, self.cfl = kinematic_viscosity, cfl
+        self.with_free_stream_flow = with_free_stream_flow
+        self.penalty_zone_width = kwargs.get("penalty_zone_width", 2)
+        self.group = group
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.part = SlabPartition(self.grid_size, world, rank, halo=1)
+        if not torch.cuda.is_available():
+            msg = "sopht_b200 flow simulators need a CUDA device (no CPU fallback)"
+            raise _lib.SophtLibraryError(msg)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        nz, ny, nx = self.grid_size
+        self.dx = real_t(x_range / nx)
+        self.z_slice = slice(self.part.z_start, self.part.z_start + self.part.nz_local)
+        # cell-centred coordinates (flow_simulators.py:50-81), only what the ramps need
+        shift = self.dx / 2.0
+        coords = [np.linspace(shift, x_range * n / nx - shift, n).astype(real_t) for n in (nz, ny, nx)]
+        w = self.penalty_zone_width
+        if w:
+            self._ramps = [_sine_ramps(coords[2], w, self.dx, real_t), _sine_ramps(coords[1], w, self.dx, real_t),
+                           _sine_ramps(coords[0], w, self.dx, real_t)]
+            if world > 1 and self.part.nz_local < w:
+                msg = "fewer planes per rank than the penalisation width"
+                raise ValueError(msg)
+        shape = (3, *self.part.local_shape)
+        zeros = lambda: torch.zeros(shape, dtype=torch.float32, device=self.device)  # noqa: E731
+        self.vorticity_field, self.velocity_field = zeros(), zeros()
+        self.buffer_vector_field, self.stream_func_field = zeros(), zeros()
+        self._unbounded_poisson_solver = SlabUnboundedPoissonSolver3D(
+            nz, ny, nx, x_range=x_range, real_t=real_t, num_threads=num_threads, group=group)
+        self._vel_absmax = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._have_absmax = False
+        self.step_mode = "fused-slab"
+
+    # -- helpers ------------------------------------------------------------------------------------------
+    def owned(self, field: torch.Tensor) -> torch.Tensor:
+        return self.part.owned(field)
+
+    def set_owned(self, field: torch.Tensor, global_values: np.ndarray | torch.Tensor) -> None:
+        """Fill this rank's planes (and the halo planes that have a neighbour) from a GLOBAL array."""
+        g = torch.as_tensor(global_values)
+        h, n, z0 = self.part.halo, self.part.nz_local, self.part.z_start
+        lo, hi = max(z0 - h, 0), min(z0 + n + h, self.grid_size[0])
+        field[..., h - (z0 - lo) : h + n + (hi - z0 - n), :, :] = g[..., lo:hi, :, :].to(field.device, field.dtype)
+
+    def _halos(self, *fields: torch.Tensor) -> None:
+        exchange_halos(self.part, fields, self.group)
+
+    # -- the step -----------------------------------------------------------------------------------------
+    def time_step(self, dt: float, free_stream_velocity=(0.0, 0.0, 0.0)) -> None:
+        rt, dc, part = self.real_t, _lib.SOPHT_F32, self.part
+        lib, fd, st = _lib.load(), _lib.field_desc, _lib.current_stream()
+        sv = part.stencil_view
+        self._halos(self.vorticity_field, self.velocity_field)
+        fw, fu, fb = fd(sv(self.vorticity_field), dc), fd(sv(self.velocity_field), dc), fd(sv(self.buffer_vector_field), dc)
+        _lib.check(lib.sopht_ns3d_advect_rotational(
+            dc, ctypes.byref(fb), ctypes.byref(fw), ctypes.byref(fu), float(rt(dt / (2 * self.dx))), st))
+        self._halos(self.buffer_vector_field)
+        _lib.check(lib.sopht_ns3d_diffuse(
+            dc, ctypes.byref(fw), ctypes.byref(fb),
+            float(rt(self.kinematic_viscosity * dt / self.dx / self.dx)), None, st))
+        if self.penalty_zone_width:
+            _lib.call("sopht_penalise_field_boundary_3d_slab", dc, self.owned(self.vorticity_field),
+                      self.penalty_zone_width, self._ramps[0], self._ramps[1], self._ramps[2], part.z_faces)
+        self._unbounded_poisson_solver.vector_field_solve(
+            solution_vector_field=self.owned(self.stream_func_field),
+            rhs_vector_field=self.owned(self.vorticity_field))
+        self._halos(self.stream_func_field)
+        fpsi = fd(sv(self.stream_func_field), dc)
+        fsv = _lib.double_array(free_stream_velocity, 3) if self.with_free_stream_flow else None
+        _lib.check(lib.sopht_ns3d_velocity_from_stream_function(
+            dc, ctypes.byref(fu), ctypes.byref(fpsi), float(rt(0.5 / self.dx)), fsv,
+            ctypes.c_void_p(self._vel_absmax.data_ptr()), st))
+        self._have_absmax = True
+        self.time += dt
+
+    def compute_stable_timestep(self, dt_prefac: float = 1.0) -> float:
+        """min(cfl dx / max sum|u|, 0.9 dx^2 / (6 nu)) with the maximum taken over all ranks
+        (passive_transport_flow_simulators.py:139-155)."""
+        if not self._have_absmax:  # before the first step: the library's sum|u| + max kernel (writes buffer[0])
+            sv = self.part.stencil_view
+            _lib.call("sopht_abs_sum_max", _lib.SOPHT_F32, sv(self.buffer_vector_field)[0],
+                      sv(self.velocity_field), self._vel_absmax.data_ptr())
+        m = self._vel_absmax.clone()
+        if self.part.world_size > 1:
+            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
+        dt = stable_timestep_from_max(self.real_t(m.item()), 3, self.dx, self.cfl, self.kinematic_viscosity, self.real_t)
+        return dt * dt_prefac

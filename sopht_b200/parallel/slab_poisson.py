@@ -1,0 +1,159 @@
+"""Unbounded Poisson solve on a z-slab decomposed grid.
+
+    x forward (local z-slab)  ->  all-to-all per component  ->  y fwd, z fwd x G_hat x z inv, y inv
+    (local kx-slab)           ->  all-to-all back           ->  x inverse (local z-slab)
+
+`SlabTransposePlan` owns the exchange buffers and the choreography (torch.distributed collectives; NCCL on
+the GPUs, gloo in the CPU tests of this host logic); the three compute phases are injected. The product
+binding `SlabUnboundedPoissonSolver3D` plugs in the CUDA phases of libsopht_b200
+(sopht_poisson_slab_*, include/sopht_b200.h). The reference has no distributed solver; what is computed is
+UnboundedPoissonSolverPYFFTW3D.py:111-172 on the global grid.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Any, Callable
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from sopht_b200 import _lib
+from sopht_b200.numeric.eulerian_grid_ops.poisson_solvers import _reflected_axis
+
+from .slab import SlabPartition
+
+
+class SlabTransposePlan:
+    """Buffers + collectives of the slab-transposed spectral solve.
+
+    Layouts (complex, stored as trailing (re, im) pairs of `dtype`):
+      send / recv   (C, P, nz/P, ny, nx/P): chunk q of a component's send goes to rank q; after the
+                    exchange a component's recv is (nz, ny, nx/P), z-major, this rank's kx range.
+      nyq_local     (C, nz/P, ny): the kx = nx bins of this rank's rows; nyq_all (C, nz, ny) after all-gather.
+    """
+
+    def __init__(self, part: SlabPartition, ncomp: int, dtype: torch.dtype, device, group=None) -> None:
+        nz, ny, nx = part.grid_size
+        p = part.world_size
+        if nx % p:
+            msg = f"nx = {nx} is not divisible by the number of ranks ({p})"
+            raise ValueError(msg)
+        self.part, self.ncomp, self.group = part, ncomp, group
+        self.nzl, self.nxl = nz // p, nx // p
+        shape = (ncomp, p, self.nzl, ny, self.nxl, 2)
+        self.send = torch.zeros(shape, dtype=dtype, device=device)
+        self.recv = torch.zeros(shape, dtype=dtype, device=device)
+        self.nyq_local = torch.zeros((ncomp, self.nzl, ny, 2), dtype=dtype, device=device)
+        self.nyq_all = torch.zeros((ncomp, nz, ny, 2), dtype=dtype, device=device)
+
+    def to_kx_slabs(self) -> None:
+        """send (z-slab rows, all kx) -> recv (all z, this rank's kx); Nyquist bins gathered on every rank."""
+        p = self.part.world_size
+        for c in range(self.ncomp):
+            if p == 1:
+                self.recv[c].copy_(self.send[c])
+                self.nyq_all[c].copy_(self.nyq_local[c])
+            else:
+                dist.all_to_all_single(self.recv[c], self.send[c], group=self.group)
+                dist.all_gather_into_tensor(self.nyq_all[c], self.nyq_local[c], group=self.group)
+
+    def to_z_slabs(self) -> None:
+        """recv (all z, this rank's kx) -> send (this rank's z rows, all kx as P chunks); Nyquist slice."""
+        p, r = self.part.world_size, self.part.rank
+        for c in range(self.ncomp):
+            if p == 1:
+                self.send[c].copy_(self.recv[c])
+            else:
+                dist.all_to_all_single(self.send[c], self.recv[c], group=self.group)
+            self.nyq_local[c].copy_(self.nyq_all[c, r * self.nzl : (r + 1) * self.nzl])
+
+    def solve(self, forward_x: Callable[[], None], middle: Callable[[], None], inverse_x: Callable[[], None]) -> None:
+        forward_x()
+        self.to_kx_slabs()
+        middle()
+        self.to_z_slabs()
+        inverse_x()
+
+
+class SlabUnboundedPoissonSolver3D:
+    """Distributed counterpart of UnboundedPoissonSolverPYFFTW3D for fp32 power-of-two grids.
+
+    Constructor takes the GLOBAL grid size like the reference class; `vector_field_solve` takes this
+    rank's (3, nz/P, ny, nx) slabs (strided views of halo-padded arrays are fine)."""
+
+    def __init__(
+        self,
+        grid_size_z: int,
+        grid_size_y: int,
+        grid_size_x: int,
+        x_range: float = 1.0,
+        num_threads: int = 1,
+        real_t: type = np.float32,
+        n_components: int = 3,
+        group: Any = None,
+    ) -> None:
+        if _lib.dtype_code(real_t) != _lib.SOPHT_F32:
+            msg = "the slab-decomposed Poisson solver is implemented for fp32 (power-of-two grids)"
+            raise ValueError(msg)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.grid_size_z, self.grid_size_y, self.grid_size_x = grid_size_z, grid_size_y, grid_size_x
+        self.x_range = x_range
+        self.y_range = x_range * (grid_size_y / grid_size_x)
+        self.z_range = x_range * (grid_size_z / grid_size_x)
+        self.dx = real_t(x_range / grid_size_x)
+        self.real_t, self.num_threads = real_t, num_threads
+        self.part = SlabPartition((grid_size_z, grid_size_y, grid_size_x), world, rank)
+        if not torch.cuda.is_available():
+            msg = "sopht_b200 Poisson solver needs a CUDA device (no CPU fallback)"
+            raise _lib.SophtLibraryError(msg)
+        device = torch.device("cuda", torch.cuda.current_device())
+        lib = _lib.load()
+        mx = _reflected_axis(self.x_range, self.dx, grid_size_x, real_t)
+        my = _reflected_axis(self.y_range, self.dx, grid_size_y, real_t)
+        mz = _reflected_axis(self.z_range, self.dx, grid_size_z, real_t)
+        origin = real_t(1 / (4 * np.pi * self.dx))  # UnboundedPoissonSolverPYFFTW3D.py:79
+        handle = ctypes.c_void_p()
+        _lib.check(lib.sopht_poisson_slab_create(
+            ctypes.byref(handle), n_components, grid_size_z, grid_size_y, grid_size_x, world, rank,
+            float(self.dx), _lib.double_array(mz), _lib.double_array(my), _lib.double_array(mx),
+            float(origin), _lib.current_stream()))
+        self._handle = handle
+        self.path = "pow2-slab"
+        self.plan = SlabTransposePlan(self.part, n_components, torch.float32, device, group)
+        nz, ny = grid_size_z, grid_size_y
+        self._work = torch.zeros((n_components, nz, 2 * ny, self.plan.nxl, 2), dtype=torch.float32, device=device)
+        self._nyq_work = torch.zeros((n_components, nz, 2 * ny, 2), dtype=torch.float32, device=device)
+
+    def __del__(self) -> None:
+        h = getattr(self, "_handle", None)
+        if h is not None and h.value:
+            try:
+                _lib.load().sopht_poisson_slab_destroy(h)
+            except Exception:  # noqa: BLE001 - interpreter shutdown
+                pass
+            self._handle = None
+
+    def vector_field_solve(self, solution_vector_field: torch.Tensor, rhs_vector_field: torch.Tensor) -> None:
+        """-del^2(solution) = rhs on the unbounded global domain; arguments are this rank's z-slabs."""
+        lib, plan, st = _lib.load(), self.plan, _lib.current_stream()
+        p = ctypes.c_void_p
+        fr = _lib.field_desc(rhs_vector_field, _lib.SOPHT_F32)
+        fs = _lib.field_desc(solution_vector_field, _lib.SOPHT_F32)
+
+        def forward_x() -> None:
+            _lib.check(lib.sopht_poisson_slab_forward_x(
+                self._handle, ctypes.byref(fr), p(plan.send.data_ptr()), p(plan.nyq_local.data_ptr()), st))
+
+        def middle() -> None:
+            _lib.check(lib.sopht_poisson_slab_yz(
+                self._handle, p(plan.recv.data_ptr()), p(plan.nyq_all.data_ptr()),
+                p(self._work.data_ptr()), p(self._nyq_work.data_ptr()), st))
+
+        def inverse_x() -> None:
+            _lib.check(lib.sopht_poisson_slab_inverse_x(
+                self._handle, ctypes.byref(fs), p(plan.send.data_ptr()), p(plan.nyq_local.data_ptr()), st))
+
+        plan.solve(forward_x, middle, inverse_x)

@@ -99,10 +99,15 @@ static void fft3_ref(std::vector<cd>& f, int n2z, int n2y, int n2x, int sign) {
     }
 }
 
-template <int NZ, int NY, int NX>
+// P = 1: the whole grid on one GPU. P > 1: the z-slab decomposed solve, every rank emulated in turn and the
+// two all-to-all transposes / the Nyquist all-gather done by plain copies (what parallel/slab_poisson.py does
+// with torch.distributed on the device).
+template <int NZ, int NY, int NX, int P = 1>
 int run_case() {
   constexpr int C = 3, TX = 8, RX = 4;
   constexpr int LX = NX, LY = 2 * NY, LZ = 2 * NZ;
+  constexpr int NZL = NZ / P, NXL = NX / P;
+  static_assert(NZ % P == 0 && NX % P == 0 && NXL % TX == 0, "slab split");
   const size_t ncell = (size_t)NZ * NY * NX;
   std::vector<float> rhs(C * ncell), sol(C * ncell, NAN);
   srand(1234 + NX + 7 * NY + 13 * NZ);
@@ -120,77 +125,71 @@ int run_case() {
         else
           gnyq[(size_t)a * (NY + 1) + b] = v;
       }
-  // buffers
-  const size_t rows = (size_t)C * NZ * NY;
-  std::vector<float2> A(rows * NX, make_float2(NAN, NAN)), nyqA(rows, make_float2(NAN, NAN));
-  std::vector<float2> B((size_t)C * NZ * LY * NX, make_float2(NAN, NAN)), nyqB((size_t)C * NZ * LY, make_float2(NAN, NAN));
   auto twx = twiddles(LX, LX), twx2 = twiddles(LX, 2 * LX), twy = twiddles(LY, LY), twz = twiddles(LZ, LZ);
+  const float2 poison = make_float2(NAN, NAN);
+  // per-rank buffers
+  const size_t slab = (size_t)C * NZL * NY * NX;  // = C * P * NZL * NY * NXL = C * NZ * NY * NXL
+  std::vector<std::vector<float2>> send(P, std::vector<float2>(slab, poison)),
+      recv(P, std::vector<float2>(slab, poison)), nyq_local(P, std::vector<float2>((size_t)C * NZL * NY, poison));
+  std::vector<float2> work((size_t)C * NZ * LY * NXL), nyq_all((size_t)C * NZ * NY), nyq_work((size_t)C * NZ * LY);
 
-  p2::XParams xp{};
-  xp.real_in = rhs.data();
-  xp.real_out = sol.data();
-  xp.sc = (int64_t)ncell;
-  xp.sz = (int64_t)NY * NX;
-  xp.sy = NX;
-  xp.spec = A.data();
-  xp.nyq = nyqA.data();
-  xp.nz = NZ;
-  xp.ny = NY;
-  xp.tw = twx.data();
-  xp.tw2 = twx2.data();
-  emulate<p2::XFwd<LX, RX>>(xp, (int)(rows / RX), 1, 1);
-
-  p2::ColParams yp{};
-  yp.in = A.data();
-  yp.out = B.data();
-  yp.in_rs = NX; yp.in_cs = 1; yp.out_rs = NX; yp.out_cs = 1;
-  yp.in_bx = TX; yp.in_by = (int64_t)NY * NX; yp.out_bx = TX; yp.out_by = (int64_t)LY * NX;
-  yp.tw = twy.data();
-  emulate<p2::YFwd<LY, TX>>(yp, NX / TX, C * NZ, 1);
-  p2::ColParams ynp{};
-  ynp.in = nyqA.data();
-  ynp.out = nyqB.data();
-  ynp.in_rs = 1; ynp.in_cs = NY; ynp.out_rs = 1; ynp.out_cs = LY;
-  ynp.in_bx = (int64_t)TX * NY; ynp.in_by = 0; ynp.out_bx = (int64_t)TX * LY; ynp.out_by = 0;
-  ynp.tw = twy.data();
-  emulate<p2::YFwd<LY, TX>>(ynp, C * NZ / TX, 1, 1);
-
-  p2::ZParams zp{};
-  zp.data = B.data();
-  zp.rs = (int64_t)LY * NX; zp.cs = 1; zp.d_bx = TX; zp.d_by = NX; zp.d_c = (int64_t)NZ * LY * NX;
-  zp.ncomp = C;
-  zp.g = gmain.data();
-  zp.g_zs = (int64_t)(NY + 1) * NX;
-  zp.g_ky_stride = NX;
-  zp.n2y = LY;
-  zp.nyq = 0;
-  zp.tw = twz.data();
-  emulate<p2::ZConv<LZ, TX>>(zp, NX / TX, LY, C);
-  p2::ZParams znp = zp;
-  znp.data = nyqB.data();
-  znp.rs = LY; znp.cs = 1; znp.d_bx = TX; znp.d_by = 0; znp.d_c = (int64_t)NZ * LY;
-  znp.g = gnyq.data();
-  znp.g_zs = NY + 1;
-  znp.g_ky_stride = 1;
-  znp.nyq = 1;
-  emulate<p2::ZConv<LZ, TX>>(znp, LY / TX, 1, C);
-
-  p2::ColParams yi{};
-  yi.in = B.data();
-  yi.out = A.data();
-  yi.in_rs = NX; yi.in_cs = 1; yi.out_rs = NX; yi.out_cs = 1;
-  yi.in_bx = TX; yi.in_by = (int64_t)LY * NX; yi.out_bx = TX; yi.out_by = (int64_t)NY * NX;
-  yi.tw = twy.data();
-  emulate<p2::YInv<LY, TX>>(yi, NX / TX, C * NZ, 1);
-  p2::ColParams yni{};
-  yni.in = nyqB.data();
-  yni.out = nyqA.data();
-  yni.in_rs = 1; yni.in_cs = LY; yni.out_rs = 1; yni.out_cs = NY;
-  yni.in_bx = (int64_t)TX * LY; yni.in_by = 0; yni.out_bx = (int64_t)TX * NY; yni.out_by = 0;
-  yni.tw = twy.data();
-  emulate<p2::YInv<LY, TX>>(yni, C * NZ / TX, 1, 1);
-
-  emulate<p2::XInv<LX, RX>>(xp, (int)(rows / RX), 1, 1);
+  // 1. x forward on every rank's z-slab
+  for (int r = 0; r < P; ++r) {
+    p2::SlabDims d{C, NZ, NY, NX, P, r};
+    auto xp = p2::slab_x_params(d, rhs.data() + (size_t)r * NZL * NY * NX, nullptr, (int64_t)ncell,
+                                (int64_t)NY * NX, NX, send[r].data(), nyq_local[r].data(), twx.data(), twx2.data());
+    emulate<p2::XFwd<LX, RX>>(xp, (int)((size_t)C * NZL * NY / RX), 1, 1);
+  }
+  // 2. all-to-all per component: chunk q of rank r's send[c] -> chunk r of rank q's recv[c]; Nyquist all-gather
+  const size_t chunk = (size_t)NZL * NY * NXL;
+  for (int c = 0; c < C; ++c)
+    for (int r = 0; r < P; ++r)
+      for (int q = 0; q < P; ++q)
+        std::copy(send[r].begin() + ((size_t)c * P + q) * chunk, send[r].begin() + ((size_t)c * P + q + 1) * chunk,
+                  recv[q].begin() + ((size_t)c * P + r) * chunk);
+  for (int c = 0; c < C; ++c)
+    for (int r = 0; r < P; ++r)
+      std::copy(nyq_local[r].begin() + (size_t)c * NZL * NY, nyq_local[r].begin() + (size_t)(c + 1) * NZL * NY,
+                nyq_all.begin() + ((size_t)c * NZ + (size_t)r * NZL) * NY);
+  // 3. y forward, z convolution, y inverse on every rank's kx-slab (recv is (C, NZ, NY, NXL))
+  for (int r = 0; r < P; ++r) {
+    p2::SlabDims d{C, NZ, NY, NX, P, r};
+    for (auto& v : work) v = poison;
+    emulate<p2::YFwd<LY, TX>>(p2::slab_y_params(d, TX, recv[r].data(), work.data(), true, twy.data()), NXL / TX,
+                              C * NZ, 1);
+    emulate<p2::ZConv<LZ, TX>>(p2::slab_z_params(d, TX, work.data(), gmain.data(), NX, r * NXL, twz.data()), NXL / TX, LY, C);
+    emulate<p2::YInv<LY, TX>>(p2::slab_y_params(d, TX, work.data(), recv[r].data(), false, twy.data()), NXL / TX,
+                              C * NZ, 1);
+  }
+  {  // Nyquist plane (every rank would do this redundantly)
+    p2::SlabDims d{C, NZ, NY, NX, P, 0};
+    for (auto& v : nyq_work) v = poison;
+    emulate<p2::YFwd<LY, TX>>(p2::nyquist_y_params(d, TX, nyq_all.data(), nyq_work.data(), true, twy.data()),
+                              C * NZ / TX, 1, 1);
+    emulate<p2::ZConv<LZ, TX>>(p2::nyquist_z_params(d, TX, nyq_work.data(), gnyq.data(), twz.data()), LY / TX, 1, C);
+    emulate<p2::YInv<LY, TX>>(p2::nyquist_y_params(d, TX, nyq_work.data(), nyq_all.data(), false, twy.data()),
+                              C * NZ / TX, 1, 1);
+  }
+  // 4. all-to-all back: z range q of rank r's recv[c] -> chunk r of rank q's send[c]; Nyquist slices
+  for (int r = 0; r < P; ++r)
+    for (auto& v : send[r]) v = poison;
+  for (int c = 0; c < C; ++c)
+    for (int r = 0; r < P; ++r)
+      for (int q = 0; q < P; ++q)
+        std::copy(recv[r].begin() + ((size_t)c * P + q) * chunk, recv[r].begin() + ((size_t)c * P + q + 1) * chunk,
+                  send[q].begin() + ((size_t)c * P + r) * chunk);
+  for (int c = 0; c < C; ++c)
+    for (int r = 0; r < P; ++r)
+      std::copy(nyq_all.begin() + ((size_t)c * NZ + (size_t)r * NZL) * NY,
+                nyq_all.begin() + ((size_t)c * NZ + (size_t)(r + 1) * NZL) * NY,
+                nyq_local[r].begin() + (size_t)c * NZL * NY);
+  // 5. x inverse on every rank's z-slab
+  for (int r = 0; r < P; ++r) {
+    p2::SlabDims d{C, NZ, NY, NX, P, r};
+    auto xp = p2::slab_x_params(d, nullptr, sol.data() + (size_t)r * NZL * NY * NX, (int64_t)ncell,
+                                (int64_t)NY * NX, NX, send[r].data(), nyq_local[r].data(), twx.data(), twx2.data());
+    emulate<p2::XInv<LX, RX>>(xp, (int)((size_t)C * NZL * NY / RX), 1, 1);
+  }
 
   // reference: doubled-domain convolution in double
   double err2 = 0, ref2 = 0;
@@ -221,7 +220,7 @@ int run_case() {
         }
   }
   const double rel = sqrt(err2 / ref2);
-  printf("grid (%d,%d,%d): LX=%d LY=%d LZ=%d rel L2 err = %.3e %s\n", NZ, NY, NX, LX, LY, LZ, rel,
+  printf("grid (%d,%d,%d) ranks %d: LX=%d LY=%d LZ=%d rel L2 err = %.3e %s\n", NZ, NY, NX, P, LX, LY, LZ, rel,
          rel < 2e-6 ? "ok" : "FAIL");
   return rel < 2e-6 ? 0 : 1;
 }
@@ -239,6 +238,8 @@ int main(int argc, char** argv) {
   bad += run_case<16, 32, 64>();   // 32, 64, 64
   bad += run_case<8, 64, 128>();   // 16, 128, 128
   bad += run_case<128, 8, 16>();   // 256 (z)
+  bad += run_case<16, 8, 32, 2>();    // z-slab decomposition over 2 ranks
+  bad += run_case<8, 16, 64, 4>();    // ... over 4 ranks
   if (full) {                      // minutes on one core: every remaining decomposition, incl. three-pass 2048
     bad += run_case<64, 128, 256>();
     bad += run_case<256, 8, 512>();

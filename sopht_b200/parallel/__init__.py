@@ -5,6 +5,7 @@ single-GPU path uses."""
 
 from .slab import SlabPartition, exchange_halos
 from .slab_flow import SlabUnboundedNavierStokesFlowSimulator3D
+from .slab_ib import SlabVirtualBoundaryForcing
 from .slab_poisson import SlabTransposePlan, SlabUnboundedPoissonSolver3D
 
 __all__ = [
@@ -12,5 +13,6 @@ __all__ = [
     "SlabTransposePlan",
     "SlabUnboundedNavierStokesFlowSimulator3D",
     "SlabUnboundedPoissonSolver3D",
+    "SlabVirtualBoundaryForcing",
     "exchange_halos",
 ]

@@ -42,7 +42,9 @@ class SlabUnboundedNavierStokesFlowSimulator3D:
         real_t: type = np.float32,
         num_threads: int = 1,
         time: float = 0.0,
+        with_forcing: bool = False,
         with_free_stream_flow: bool = False,
+        flow_density: float = 1.0,
         group: Any = None,
         **kwargs: Any,
     ) -> None:
@@ -54,6 +56,7 @@ class SlabUnboundedNavierStokesFlowSimulator3D:
         self.x_range, self.real_t, self.num_threads, self.time = x_range, real_t, num_threads, time
         self.kinematic_viscosity, self.cfl = kinematic_viscosity, cfl
         self.with_free_stream_flow = with_free_stream_flow
+        self.with_forcing, self.flow_density = with_forcing, flow_density
         self.penalty_zone_width = kwargs.get("penalty_zone_width", 2)
         self.group = group
         world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -80,6 +83,8 @@ class SlabUnboundedNavierStokesFlowSimulator3D:
         zeros = lambda: torch.zeros(shape, dtype=torch.float32, device=self.device)  # noqa: E731
         self.vorticity_field, self.velocity_field = zeros(), zeros()
         self.buffer_vector_field, self.stream_func_field = zeros(), zeros()
+        if with_forcing:
+            self.eul_grid_forcing_field = zeros()
         self._unbounded_poisson_solver = SlabUnboundedPoissonSolver3D(
             nz, ny, nx, x_range=x_range, real_t=real_t, num_threads=num_threads, group=group)
         self._vel_absmax = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -105,14 +110,20 @@ class SlabUnboundedNavierStokesFlowSimulator3D:
         rt, dc, part = self.real_t, _lib.SOPHT_F32, self.part
         lib, fd, st = _lib.load(), _lib.field_desc, _lib.current_stream()
         sv = part.stencil_view
+        if self.with_forcing:  # w += dt/(2 dx rho) curl(f)   (navier_stokes_flow_simulators.py:487-492)
+            self._halos(self.eul_grid_forcing_field)
+            _lib.call("sopht_update_vorticity_from_velocity_forcing_3d", dc, sv(self.vorticity_field),
+                      sv(self.eul_grid_forcing_field), float(rt(dt / (2 * self.dx * self.flow_density))))
         self._halos(self.vorticity_field, self.velocity_field)
         fw, fu, fb = fd(sv(self.vorticity_field), dc), fd(sv(self.velocity_field), dc), fd(sv(self.buffer_vector_field), dc)
         _lib.check(lib.sopht_ns3d_advect_rotational(
             dc, ctypes.byref(fb), ctypes.byref(fw), ctypes.byref(fu), float(rt(dt / (2 * self.dx))), st))
         self._halos(self.buffer_vector_field)
+        ff = fd(sv(self.eul_grid_forcing_field), dc) if self.with_forcing else None  # f <- 0 in the same pass
         _lib.check(lib.sopht_ns3d_diffuse(
             dc, ctypes.byref(fw), ctypes.byref(fb),
-            float(rt(self.kinematic_viscosity * dt / self.dx / self.dx)), None, st))
+            float(rt(self.kinematic_viscosity * dt / self.dx / self.dx)),
+            ctypes.byref(ff) if ff is not None else None, st))
         if self.penalty_zone_width:
             _lib.call("sopht_penalise_field_boundary_3d_slab", dc, self.owned(self.vorticity_field),
                       self.penalty_zone_width, self._ramps[0], self._ramps[1], self._ramps[2], part.z_faces)

@@ -66,6 +66,16 @@ def test_slab_simulator_single_rank_matches_oracle(rng, grid, with_free_stream):
     assert torch.cuda.is_available()
 
 
+def test_slab_single_rank_with_ib_matches_single_gpu_path():
+    """world_size 1 through torchrun: forcing + SlabVirtualBoundaryForcing against the regular classes."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=1",
+           "--master-addr", "127.0.0.1", "--master-port", "29516",
+           os.path.join(ROOT, "tests", "mgpu_slab_check.py"), "16", "16", "32", "3"]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert "SLAB CHECK OK" in out.stdout
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_slab_multi_rank_nccl(world):
     import torch

@@ -41,6 +41,22 @@ WORKLOADS = {
     "u256": dict(grid=(256, 256, 256), body=None, desc="3D unbounded flow step 256^3 fp32"),
     "u512": dict(grid=(512, 512, 512), body=None, desc="3D unbounded flow step 512^3 fp32"),
 }
+def global_grid(wl, world):
+    """Weak scaling: the per-GPU cell count is fixed, the global grid grows with the number of ranks
+    (z first - the slab axis - then y, then x, each up to the 1024 planes the power-of-two FFT path takes)."""
+    nz, ny, nx = wl["grid"]
+    f = world
+    while f > 1:
+        if nz < 1024:
+            nz *= 2
+        elif ny < 1024:
+            ny *= 2
+        else:
+            nx *= 2
+        f //= 2
+    return (nz, ny, nx)
+
+
 NU = 1e-3
 X_RANGE = 1.0
 U_INF = (1.0, 0.0, 0.0)
@@ -94,7 +110,7 @@ def roofline_from_report(report, steps, cells, forcing, peak, peak_src):
     return roof, kernels
 
 
-def hill_vortex_vorticity(grid, x_range, real_t=np.float32):
+def hill_vortex_vorticity(grid, x_range, real_t=np.float32, z_planes=None):
     """Smooth band-limited initial vorticity: Hill's spherical vortex (R = 0.25 x_range, U = 1) centred
     in the domain (analogue of examples/3d_examples/HillSphericalVortexCase)."""
     nz, ny, nx = grid
@@ -103,8 +119,11 @@ def hill_vortex_vorticity(grid, x_range, real_t=np.float32):
     y = (np.arange(ny) + 0.5) * dx
     x = (np.arange(nx) + 0.5) * dx
     zc, yc, xc = z.mean(), y.mean(), x.mean()
+    if z_planes is not None:  # only these global planes (a rank's slab)
+        z = z[z_planes[0]:z_planes[1]]
+    nz = len(z)
     Z, Y, X = np.meshgrid(z - zc, y - yc, x - xc, indexing="ij")
-    R = 0.25 * min(nz, ny, nx) * dx
+    R = 0.25 * min(grid) * dx
     r2 = X * X + Y * Y + Z * Z
     inside = r2 <= R * R
     # omega = (15 U / 2 R^2) * rho * e_phi about the z axis
@@ -251,7 +270,8 @@ def run_reference_arm(args, wl):
         return
     steps = max(1, min(args.steps, 8))
     warm = 1 if args.warmup > 0 else 0
-    # bound the sample: big grids run fewer steps
+    # same (weak-scaled) global grid as the GPU arm at this rank count; bound the sample: big grids run fewer steps
+    wl = dict(wl, grid=global_grid(wl, max(args.gpus, 1)))
     cells = int(np.prod(wl["grid"]))
     if cells > 2**24:
         steps = min(steps, 2)
@@ -287,28 +307,61 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     _lib.load()
 
-    grid = wl["grid"]
+    grid = global_grid(wl, world)
     forcing = wl["body"] is not None
-    sim = UnboundedNavierStokesFlowSimulator3D(
-        grid_size=grid, x_range=X_RANGE, kinematic_viscosity=NU, real_t=np.float32,
-        with_forcing=forcing, with_free_stream_flow=True, step_mode=args.step_mode)
-    sim.vorticity_field[...] = torch.from_numpy(hill_vortex_vorticity(grid, X_RANGE)).cuda()
-    sim._unbounded_poisson_solver.vector_field_solve(
-        solution_vector_field=sim.stream_func_field, rhs_vector_field=sim.vorticity_field)
-    sim._curl(curl=sim.velocity_field, field=sim.stream_func_field, prefactor=np.float32(0.5 / sim.dx))
+    dt_value = None
+    if world == 1:
+        sim = UnboundedNavierStokesFlowSimulator3D(
+            grid_size=grid, x_range=X_RANGE, kinematic_viscosity=NU, real_t=np.float32,
+            with_forcing=forcing, with_free_stream_flow=True, step_mode=args.step_mode)
+        sim.vorticity_field[...] = torch.from_numpy(hill_vortex_vorticity(grid, X_RANGE)).cuda()
+        sim._unbounded_poisson_solver.vector_field_solve(
+            solution_vector_field=sim.stream_func_field, rhs_vector_field=sim.vorticity_field)
+        sim._curl(curl=sim.velocity_field, field=sim.stream_func_field, prefactor=np.float32(0.5 / sim.dx))
+        own = lambda f: f  # noqa: E731
+        cells_local = int(np.prod(grid))
+    else:
+        from sopht_b200.parallel import SlabUnboundedNavierStokesFlowSimulator3D
+
+        sim = SlabUnboundedNavierStokesFlowSimulator3D(
+            grid_size=grid, x_range=X_RANGE, kinematic_viscosity=NU, real_t=np.float32,
+            with_forcing=forcing, with_free_stream_flow=True)
+        # this rank's planes of the same initial vorticity; one zero-dt-free way to get u0: a first step
+        z0, nzl = sim.part.z_start, sim.part.nz_local
+        w0 = hill_vortex_vorticity(grid, X_RANGE, z_planes=(max(z0 - 1, 0), min(z0 + nzl + 1, grid[0])))
+        lo = 1 - (z0 - max(z0 - 1, 0))
+        sim.vorticity_field[:, lo:lo + w0.shape[1]] = torch.from_numpy(w0).cuda()
+        sim._unbounded_poisson_solver.vector_field_solve(
+            solution_vector_field=sim.owned(sim.stream_func_field), rhs_vector_field=sim.owned(sim.vorticity_field))
+        sim._halos(sim.stream_func_field)
+        lib = _lib.load()
+        fu = _lib.field_desc(sim.part.stencil_view(sim.velocity_field), 0)
+        fpsi = _lib.field_desc(sim.part.stencil_view(sim.stream_func_field), 0)
+        import ctypes
+
+        _lib.check(lib.sopht_ns3d_velocity_from_stream_function(
+            0, ctypes.byref(fu), ctypes.byref(fpsi), float(np.float32(0.5 / sim.dx)), None, None,
+            _lib.current_stream()))
+        own = sim.owned
+        cells_local = int(np.prod(grid)) // world
     dt = float(0.1 * sim.dx)
     cells = int(np.prod(grid))
 
     interactor = None
     if forcing:
-        from sopht_b200.numeric.immersed_boundary_ops import VirtualBoundaryForcing
-
         pos_h = torch.from_numpy(sphere_lag_grid()).pin_memory()
         vel_h = torch.zeros_like(pos_h).pin_memory()
         ds = np.pi * 0.2 / 96
-        interactor = VirtualBoundaryForcing(
-            virtual_boundary_stiffness_coeff=-1.5e5 * ds * ds, virtual_boundary_damping_coeff=-87.5 * ds * ds,
-            grid_dim=3, dx=sim.dx, num_lag_nodes=pos_h.shape[1], real_t=np.float32)
+        vb_kw = dict(virtual_boundary_stiffness_coeff=-1.5e5 * ds * ds, virtual_boundary_damping_coeff=-87.5 * ds * ds,
+                     grid_dim=3, dx=sim.dx, num_lag_nodes=pos_h.shape[1], real_t=np.float32)
+        if world == 1:
+            from sopht_b200.numeric.immersed_boundary_ops import VirtualBoundaryForcing
+
+            interactor = VirtualBoundaryForcing(**vb_kw)
+        else:
+            from sopht_b200.parallel import SlabVirtualBoundaryForcing
+
+            interactor = SlabVirtualBoundaryForcing(**vb_kw, partition=sim.part)
         pos_d, vel_d = pos_h.cuda(), vel_h.cuda()
         force_h = torch.zeros(3, pos_h.shape[1], dtype=torch.float32).pin_memory()
 
@@ -316,7 +369,7 @@ def run_ours(args, wl):
         if interactor is not None:
             interactor.time_step(dt)
             interactor.compute_interaction_force_on_eul_and_lag_grid(
-                sim.eul_grid_forcing_field, sim.velocity_field, pos_d, vel_d)
+                own(sim.eul_grid_forcing_field), own(sim.velocity_field), pos_d, vel_d)
         sim.time_step(dt=dt, free_stream_velocity=U_INF)
 
     h2d = d2h = 0
@@ -332,7 +385,7 @@ def run_ours(args, wl):
             h2d_n += pos_h.numel() * 8 + vel_h.numel() * 8
             interactor.time_step(step_dt)
             interactor.compute_interaction_force_on_eul_and_lag_grid(
-                sim.eul_grid_forcing_field, sim.velocity_field, p, v)
+                own(sim.eul_grid_forcing_field), own(sim.velocity_field), p, v)
             force_h.copy_(interactor.lag_grid_forcing_field, non_blocking=True)
             d2h_n += force_h.numel() * 4
         sim.time_step(dt=step_dt, free_stream_velocity=U_INF)
@@ -364,13 +417,13 @@ def run_ours(args, wl):
     with ClockSampler(local) as clk:
         ms = timed(device_step, args.steps)
     launches = _lib.launch_count() - n0
-    value = cells * world * args.steps / (ms * 1e-3) / 1e9
+    value = cells * args.steps / (ms * 1e-3) / 1e9
 
     # end-to-end through the public API with host-side per-step inputs/outputs
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
-    e2e_val = cells * world * args.steps / (ms_e2e * 1e-3) / 1e9
+    e2e_val = cells * args.steps / (ms_e2e * 1e-3) / 1e9
 
     # roofline of the dominant kernel: the library's per-kernel CUDA-event timers (recorded on the launching
     # stream) switched on for a second K-step region of the same loop
@@ -382,9 +435,9 @@ def run_ours(args, wl):
     barrier()
     report = _lib.profile_report()
     _lib.profile_enable(False)
-    roof, kernels = roofline_from_report(report, args.steps, cells, forcing, peak, peak_src)
+    roof, kernels = roofline_from_report(report, args.steps, cells_local, forcing, peak, peak_src)
     step_bpc = algorithmic_bytes_per_cell(forcing)
-    whole = step_bpc * cells * args.steps / (ms * 1e-3) / 1e9
+    whole = step_bpc * cells_local * args.steps / (ms * 1e-3) / 1e9  # per GPU
 
     if rank != 0:
         return
@@ -399,11 +452,13 @@ def run_ours(args, wl):
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": wl["desc"], "grid": list(grid), "cells_per_gpu": cells,
+        "config": {"workload": wl["desc"] + (f", weak-scaled to {world} z-slabs" if world > 1 else ""),
+                   "grid": list(grid), "cells_per_gpu": cells_local,
+                   "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
                    "lagrangian_nodes": int(pos_h.shape[1]) if forcing else 0,
                    "step_mode": sim.step_mode, "poisson_path": sim._unbounded_poisson_solver.path,
-                   "l2": "working set per step exceeds L2 (fields + FFT workspace > 126 MB)"
-                   if cells * 4 * 15 > 126e6 else "L2 flushed between steps"},
+                   "l2": "inputs larger than L2: per-GPU working set per step (fields + FFT workspace, "
+                         f"{cells_local * 4 * 33 / 1e6:.0f} MB) exceeds the 126 MB L2"},
         "e2e": {"value": e2e_val, "unit": "Gcell/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),

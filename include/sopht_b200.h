@@ -65,6 +65,10 @@ int64_t sopht_launch_count(void);
  * clears them, and returns a JSON object {"label": {"launches": n, "ms": total}, ...} owned by the library. */
 int sopht_profile_enable(int on);
 const char *sopht_profile_report(void);
+/* the same timers around work the host layer enqueues itself (NCCL collectives of the slab path):
+ * begin returns a token for end; both are no-ops (token -1) while the timers are off */
+int sopht_profile_range_begin(const char *label, void *stream);
+int sopht_profile_range_end(int token, void *stream);
 
 /* ------------------------------------------------------------------------ */
 /* Elementwise operations on strided views (1..4-D, 2D and 3D grids alike)   */
@@ -322,6 +326,14 @@ int sopht_poisson_slab_yz(sopht_poisson_slab_t handle, void *recv_buffer, void *
                           void *work_buffer, void *nyquist_work, void *stream);
 int sopht_poisson_slab_inverse_x(sopht_poisson_slab_t handle, const sopht_field_t *solution_field,
                                  void *recv_buffer, void *nyquist_local, void *stream);
+/* Transposes fused into the kernels over peer memory (NVLink): the library allocates the two exchange buffers,
+ * enable_peer_exchange() returns their CUDA IPC handles (2 x 64 bytes: recv, send), the host layer all-gathers
+ * the handles of all ranks (nranks x 128 bytes, rank order) and hands them to open_peers(). Afterwards the phase
+ * functions take NULL for send_buffer / recv_buffer: x forward then stores every kx chunk straight into the
+ * owning rank's buffer, y inverse stores every plane into the buffer of the rank that owns it, and no
+ * all-to-all is issued - the host layer only separates the phases with a collective barrier. */
+int sopht_poisson_slab_enable_peer_exchange(sopht_poisson_slab_t handle, unsigned char *ipc_handles_out);
+int sopht_poisson_slab_open_peers(sopht_poisson_slab_t handle, const unsigned char *all_ipc_handles);
 int sopht_poisson_slab_destroy(sopht_poisson_slab_t handle);
 
 /* ------------------------------------------------------------------------ */

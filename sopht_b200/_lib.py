@@ -105,6 +105,10 @@ def load() -> ctypes.CDLL:
     lib.sopht_profile_enable.argtypes = [ctypes.c_int]
     lib.sopht_profile_report.restype = ctypes.c_char_p
     lib.sopht_profile_report.argtypes = []
+    lib.sopht_profile_range_begin.restype = ctypes.c_int
+    lib.sopht_profile_range_begin.argtypes = [ctypes.c_char_p, ctypes.c_void_p]
+    lib.sopht_profile_range_end.restype = ctypes.c_int
+    lib.sopht_profile_range_end.argtypes = [ctypes.c_int, ctypes.c_void_p]
     for name, kinds in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = ctypes.c_int
@@ -140,6 +144,8 @@ _HANDLE_SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "sopht_poisson_slab_forward_x": (ctypes.c_int, [_P, _F, _P, _P, _P]),
     "sopht_poisson_slab_yz": (ctypes.c_int, [_P, _P, _P, _P, _P, _P]),
     "sopht_poisson_slab_inverse_x": (ctypes.c_int, [_P, _F, _P, _P, _P]),
+    "sopht_poisson_slab_enable_peer_exchange": (ctypes.c_int, [_P, _P]),
+    "sopht_poisson_slab_open_peers": (ctypes.c_int, [_P, _P]),
     "sopht_poisson_slab_destroy": (ctypes.c_int, [_P]),
     # fused 3-D Navier-Stokes passes
     "sopht_ns3d_advect_rotational": (ctypes.c_int, [_I, _F, _F, _F, _D, _P]),
@@ -165,6 +171,8 @@ def exported_symbols() -> list[str]:
         "sopht_launch_count",
         "sopht_profile_enable",
         "sopht_profile_report",
+        "sopht_profile_range_begin",
+        "sopht_profile_range_end",
         *_SIGNATURES.keys(),
         *_HANDLE_SIGNATURES.keys(),
     ]
@@ -174,9 +182,31 @@ def launch_count() -> int:
     return int(load().sopht_launch_count())
 
 
+_profile_on = False
+
+
 def profile_enable(on: bool) -> None:
     """Switch the library's per-kernel CUDA-event timers on or off (include/sopht_b200.h)."""
+    global _profile_on
+    _profile_on = bool(on)
     load().sopht_profile_enable(1 if on else 0)
+
+
+class profile_range:
+    """Times host-enqueued work (collectives) on the current stream with the library's event timers."""
+
+    def __init__(self, label: str) -> None:
+        self.label = label.encode()
+        self.token = -1
+
+    def __enter__(self) -> "profile_range":
+        if _profile_on:
+            self.token = load().sopht_profile_range_begin(self.label, current_stream())
+        return self
+
+    def __exit__(self, *exc) -> None:
+        if self.token >= 0:
+            load().sopht_profile_range_end(self.token, current_stream())
 
 
 def profile_report() -> dict:

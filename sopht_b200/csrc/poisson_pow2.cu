@@ -8,6 +8,7 @@
 // ref: sopht/numeric/eulerian_grid_ops/poisson_solver_3d/UnboundedPoissonSolverPYFFTW3D.py:111-172
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
@@ -334,8 +335,24 @@ struct SlabPow2Poisson {
   p2::SlabDims d{};
   float *gm = nullptr, *gn = nullptr;  // this rank's kx slice of the folded G_hat, and the Nyquist plane's
   float2 *twx = nullptr, *twx2 = nullptr, *twy = nullptr, *twz = nullptr;
+  // peer exchange: library-owned (cudaMalloc, so the IPC handle maps the exact base) buffers
+  // (C, P, nzl, ny, nxl); peer_recv[q] / peer_send[q] are rank q's buffers mapped into this process
+  float2 *xrecv = nullptr, *xsend = nullptr;
+  float2* peer_recv[8] = {};
+  float2* peer_send[8] = {};
+  bool peers_open = false;
+
+  size_t exchange_bytes() const { return sizeof(float2) * (size_t)d.C * d.nz * d.ny * d.nxl(); }
 
   ~SlabPow2Poisson() {
+    if (peers_open)
+      for (int q = 0; q < d.P; ++q)
+        if (q != d.rank) {
+          cudaIpcCloseMemHandle(peer_recv[q]);
+          cudaIpcCloseMemHandle(peer_send[q]);
+        }
+    cudaFree(xrecv);
+    cudaFree(xsend);
     cudaFree(gm);
     cudaFree(gn);
     cudaFree(twx);
@@ -388,17 +405,60 @@ struct SlabPow2Poisson {
     return SOPHT_OK;
   }
 
+  int enable_peer_exchange(unsigned char* handles_out) {
+    if (!xrecv) {
+      if (cudaMalloc(&xrecv, exchange_bytes()) != cudaSuccess || cudaMalloc(&xsend, exchange_bytes()) != cudaSuccess)
+        SOPHT_FAIL(SOPHT_ERR_ALLOC, "poisson(slab): out of device memory for the exchange buffers");
+    }
+    cudaIpcMemHandle_t h0, h1;
+    SOPHT_CUDA(cudaIpcGetMemHandle(&h0, xrecv));
+    SOPHT_CUDA(cudaIpcGetMemHandle(&h1, xsend));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(handles_out, &h0, 64);
+    memcpy(handles_out + 64, &h1, 64);
+    return SOPHT_OK;
+  }
+
+  int open_peers(const unsigned char* all_handles) {
+    if (!xrecv) SOPHT_FAIL(SOPHT_ERR_HANDLE, "poisson(slab): enable_peer_exchange first");
+    for (int q = 0; q < d.P; ++q) {
+      if (q == d.rank) {
+        peer_recv[q] = xrecv;
+        peer_send[q] = xsend;
+        continue;
+      }
+      cudaIpcMemHandle_t h0, h1;
+      memcpy(&h0, all_handles + (size_t)q * 128, 64);
+      memcpy(&h1, all_handles + (size_t)q * 128 + 64, 64);
+      void *p0 = nullptr, *p1 = nullptr;
+      SOPHT_CUDA(cudaIpcOpenMemHandle(&p0, h0, cudaIpcMemLazyEnablePeerAccess));
+      SOPHT_CUDA(cudaIpcOpenMemHandle(&p1, h1, cudaIpcMemLazyEnablePeerAccess));
+      peer_recv[q] = reinterpret_cast<float2*>(p0);
+      peer_send[q] = reinterpret_cast<float2*>(p1);
+    }
+    peers_open = true;
+    return SOPHT_OK;
+  }
+
+  // x forward; send == nullptr: the spectrum chunks go straight into the peers' exchange buffers (NVLink stores)
   int forward_x(const sopht_field_t* rhs, float2* send, float2* nyq_local, cudaStream_t st) const {
     int rc = check_local(__func__, rhs);
     if (rc) return rc;
-    const p2::XParams xp =
+    if (!send && !peers_open) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: peer exchange is not open", __func__);
+    p2::XParams xp =
         p2::slab_x_params(d, reinterpret_cast<const float*>(rhs->data), nullptr, rhs->stride[0], rhs->stride[1],
-                          rhs->stride[2], send, nyq_local, twx, twx2);
+                          rhs->stride[2], send ? send : xrecv, nyq_local, twx, twx2);
+    if (!send) xp = p2::slab_x_params_peer(xp, d, peer_recv);
     return launch_xfwd(d.nx, xp, (int64_t)d.C * d.nzl() * d.ny, st);
   }
 
+  // recv == nullptr: read this rank's own exchange buffer (filled by the peers) and let the y inverse write its
+  // planes straight into the peers' buffers
   int yz(float2* recv, float2* nyq_all, float2* work, float2* nyq_work, cudaStream_t st) const {
     const int LY = 2 * d.ny, LZ = 2 * d.nz, nxl = d.nxl();
+    const bool peer = recv == nullptr;
+    if (peer && !peers_open) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: peer exchange is not open", __func__);
+    if (peer) recv = xrecv;
     int rc;
     if ((rc = launch_yfwd(LY, p2::slab_y_params(d, TX, recv, work, true, twy), dim3(nxl / TX, d.C * d.nz, 1), st)))
       return rc;
@@ -409,8 +469,9 @@ struct SlabPow2Poisson {
       return rc;
     if ((rc = launch_zconv(LZ, p2::nyquist_z_params(d, TX, nyq_work, gn, twz), dim3(LY / TX, 1, 1), st)))
       return rc;
-    if ((rc = launch_yinv(LY, p2::slab_y_params(d, TX, work, recv, false, twy), dim3(nxl / TX, d.C * d.nz, 1), st)))
-      return rc;
+    p2::ColParams yi = p2::slab_y_params(d, TX, work, recv, false, twy);
+    if (peer) yi = p2::slab_yinv_params_peer(yi, d, peer_send);
+    if ((rc = launch_yinv(LY, yi, dim3(nxl / TX, d.C * d.nz, 1), st))) return rc;
     return launch_yinv(LY, p2::nyquist_y_params(d, TX, nyq_work, nyq_all, false, twy),
                        dim3(d.C * d.nz / TX, 1, 1), st);
   }
@@ -418,6 +479,8 @@ struct SlabPow2Poisson {
   int inverse_x(const sopht_field_t* sol, float2* recv2, float2* nyq_local, cudaStream_t st) const {
     int rc = check_local(__func__, sol);
     if (rc) return rc;
+    if (!recv2 && !peers_open) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: peer exchange is not open", __func__);
+    if (!recv2) recv2 = xsend;
     const p2::XParams xp = p2::slab_x_params(d, nullptr, reinterpret_cast<float*>(sol->data), sol->stride[0],
                                              sol->stride[1], sol->stride[2], recv2, nyq_local, twx, twx2);
     return launch_xinv(d.nx, xp, (int64_t)d.C * d.nzl() * d.ny, st);
@@ -483,14 +546,14 @@ int sopht_poisson_slab_create(sopht_poisson_slab_t* handle, int ncomp, int nz, i
 
 int sopht_poisson_slab_forward_x(sopht_poisson_slab_t h, const sopht_field_t* rhs_field, void* send_buffer,
                                  void* nyquist_local, void* stream) {
-  if (!h || !send_buffer || !nyquist_local) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
+  if (!h || !nyquist_local) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
   return h->impl.forward_x(rhs_field, reinterpret_cast<float2*>(send_buffer),
                            reinterpret_cast<float2*>(nyquist_local), as_stream(stream));
 }
 
 int sopht_poisson_slab_yz(sopht_poisson_slab_t h, void* recv_buffer, void* nyquist_all, void* work_buffer,
                           void* nyquist_work, void* stream) {
-  if (!h || !recv_buffer || !nyquist_all || !work_buffer || !nyquist_work)
+  if (!h || !nyquist_all || !work_buffer || !nyquist_work)
     SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
   return h->impl.yz(reinterpret_cast<float2*>(recv_buffer), reinterpret_cast<float2*>(nyquist_all),
                     reinterpret_cast<float2*>(work_buffer), reinterpret_cast<float2*>(nyquist_work),
@@ -499,9 +562,19 @@ int sopht_poisson_slab_yz(sopht_poisson_slab_t h, void* recv_buffer, void* nyqui
 
 int sopht_poisson_slab_inverse_x(sopht_poisson_slab_t h, const sopht_field_t* solution_field, void* recv_buffer,
                                  void* nyquist_local, void* stream) {
-  if (!h || !recv_buffer || !nyquist_local) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
+  if (!h || !nyquist_local) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
   return h->impl.inverse_x(solution_field, reinterpret_cast<float2*>(recv_buffer),
                            reinterpret_cast<float2*>(nyquist_local), as_stream(stream));
+}
+
+int sopht_poisson_slab_enable_peer_exchange(sopht_poisson_slab_t h, unsigned char* ipc_handles_out) {
+  if (!h || !ipc_handles_out) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
+  return h->impl.enable_peer_exchange(ipc_handles_out);
+}
+
+int sopht_poisson_slab_open_peers(sopht_poisson_slab_t h, const unsigned char* all_ipc_handles) {
+  if (!h || !all_ipc_handles) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
+  return h->impl.open_peers(all_ipc_handles);
 }
 
 int sopht_poisson_slab_destroy(sopht_poisson_slab_t h) {

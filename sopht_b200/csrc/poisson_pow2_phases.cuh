@@ -76,6 +76,18 @@ struct ColParams {
   int64_t in_rs, in_cs, out_rs, out_cs;          // row / column strides (complex elements)
   int64_t in_bx, in_by, out_bx, out_by;          // tile origin = base + bx*_bx + by*_by
   const float2* tw;                              // forward twiddles, length L
+  // Peer-memory output (slab-decomposed y inverse): plane by = c * nz + z of the kx-slab goes straight into the
+  // exchange buffer of the rank that owns plane z - (C, P, nz/P, ny, nx/P) there, this rank's kx chunk - over
+  // NVLink, so the reverse transpose is part of this kernel. peer_mode == 0: plain `out + by * out_by`.
+  int peer_mode, log2_nz, log2_nzl;
+  int64_t peer_plane, peer_comp_stride, peer_self_offset;
+  float2* out_peer[8];
+  FFT_HD float2* out_plane(int by) const {
+    if (!peer_mode) return out + by * out_by;
+    const int z = by & ((1 << log2_nz) - 1), c = by >> log2_nz;
+    return out_peer[z >> log2_nzl] + c * peer_comp_stride + peer_self_offset +
+           (int64_t)(z & ((1 << log2_nzl) - 1)) * peer_plane;
+  }
 };
 
 // Row strides travel as 32-bit unsigned: for every eligible grid (nz, ny <= 1024, nx <= 2048) the largest
@@ -197,7 +209,7 @@ struct YInv {
         fft::inv_first<L>(src, sm, t);
       }
     } else if (P == NPHASE - 1) {
-      GlobalStore st{p.out + bx * p.out_bx + by * p.out_by + col * p.out_cs, (unsigned)p.out_rs};
+      GlobalStore st{p.out_plane(by) + bx * p.out_bx + col * p.out_cs, (unsigned)p.out_rs};
       fft::inv_last<L>(sm, t, tw, st);
     } else {
       fft::inv_mid<L>(sm, t, tw);
@@ -322,13 +334,20 @@ struct XParams {
   // One GPU: chunk_len = L, comp_stride = rows_per_component * L (plain (rows, L) rows). Slab-decomposed
   // solve: spec is the all-to-all buffer (C, P, nz_local, ny, nx/P) - the kx range of rank r is chunk r -
   // so the transposes need no pack / unpack pass.
+  // XFwd can write chunk q straight into rank q's exchange buffer over NVLink (peer memory): chunk[q] is then
+  // that buffer's base and self_offset this rank's slot (r * chunk_stride) in it; without peers chunk[q] =
+  // spec + q * chunk_stride and self_offset = 0.
   int rpc_shift, chunk_shift;
-  int64_t comp_stride, chunk_stride;
+  int64_t comp_stride, chunk_stride, self_offset;
+  float2* chunk[8];
   FFT_HD int64_t row_base(int64_t row) const {
     return (row >> rpc_shift) * comp_stride + ((row & (((int64_t)1 << rpc_shift) - 1)) << chunk_shift);
   }
   FFT_HD int64_t bin(int k) const {
     return (int64_t)(k >> chunk_shift) * chunk_stride + (k & ((1 << chunk_shift) - 1));
+  }
+  FFT_HD float2* out_bin(int64_t row_base_, int k) const {
+    return chunk[k >> chunk_shift] + row_base_ + self_offset + (k & ((1 << chunk_shift) - 1));
   }
 };
 
@@ -402,7 +421,7 @@ struct XFwd {
       fft::fwd_last<L>(sm, t, InPlaceSink<L>{sm});
     } else if (P == NP) {
       // X_k = E_k + w^k O_k, E = (Z_k + conj Z_{L-k})/2, O = (Z_k - conj Z_{L-k})/(2i); X_L = E_0 - O_0
-      float2* out = p.spec + p.row_base(row);
+      const int64_t rb = p.row_base(row);
 #pragma unroll
       for (int q = 0; q < Cfg<L>::E; ++q) {
         const int k = t + q * T;
@@ -410,7 +429,7 @@ struct XFwd {
         const float2 b = sm(fft::spectrum_position<L>((L - k) & (L - 1)));
         const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
         const float2 o = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
-        out[p.bin(k)] = fft::cadd(e, fft::cmul(o, tw2[k]));
+        *p.out_bin(rb, k) = fft::cadd(e, fft::cmul(o, tw2[k]));
         if (k == 0) p.nyq[row] = make_float2(e.x - o.x, e.y - o.y);
       }
     } else {
@@ -509,6 +528,14 @@ inline XParams slab_x_params(const SlabDims& d, const float* real_in, float* rea
   xp.chunk_shift = ilog2(d.nxl());
   xp.chunk_stride = (int64_t)d.nzl() * d.ny * d.nxl();
   xp.comp_stride = xp.chunk_stride * d.P;
+  xp.self_offset = 0;
+  for (int q = 0; q < 8; ++q) xp.chunk[q] = q < d.P ? spec + q * xp.chunk_stride : nullptr;
+  return xp;
+}
+// the same with the spectrum chunks written into the peers' exchange buffers (peer[q]: base of rank q's buffer)
+inline XParams slab_x_params_peer(XParams xp, const SlabDims& d, float2* const* peer) {
+  xp.self_offset = (int64_t)d.rank * xp.chunk_stride;
+  for (int q = 0; q < 8; ++q) xp.chunk[q] = q < d.P ? peer[q] : nullptr;
   return xp;
 }
 // y passes on this rank's kx-slab: a = (C, nz, ny, nxl), b = (C, nz, 2ny, nxl); grid (nxl / TX, C * nz)
@@ -523,6 +550,17 @@ inline ColParams slab_y_params(const SlabDims& d, int TX, const float2* in, floa
   yp.in_by = (forward ? d.ny : LY) * nxl;
   yp.out_by = (forward ? LY : d.ny) * nxl;
   yp.tw = tw;
+  return yp;
+}
+// y inverse whose output planes go into the peers' exchange buffers (peer[s]: base of rank s's buffer)
+inline ColParams slab_yinv_params_peer(ColParams yp, const SlabDims& d, float2* const* peer) {
+  yp.peer_mode = 1;
+  yp.log2_nz = ilog2(d.nz);
+  yp.log2_nzl = ilog2(d.nzl());
+  yp.peer_plane = (int64_t)d.ny * d.nxl();
+  yp.peer_comp_stride = yp.peer_plane * d.nzl() * d.P;
+  yp.peer_self_offset = yp.peer_plane * d.nzl() * d.rank;
+  for (int q = 0; q < 8; ++q) yp.out_peer[q] = q < d.P ? peer[q] : nullptr;
   return yp;
 }
 // Nyquist plane (C, nz, ny) <-> (C, nz, 2ny): columns are the (c, z) index; grid (C * nz / TX, 1)

@@ -52,6 +52,29 @@ using namespace sopht;
 
 extern "C" {
 
+/* host-layer ranges (collectives issued by the Python layer between the kernels): label must stay valid */
+int sopht_profile_range_begin(const char* label, void* stream) {
+  if (!g_prof_on) return -1;
+  static std::vector<std::string>* names = new std::vector<std::string>();
+  const char* stable = nullptr;
+  for (auto& n : *names)
+    if (n == label) stable = n.c_str();
+  if (!stable) {
+    names->reserve(256);
+    names->push_back(label);
+    stable = names->back().c_str();
+  }
+  Rec r{stable, take_event(), take_event()};
+  cudaEventRecord(r.e0, as_stream(stream));
+  g_recs.push_back(r);
+  return (int)g_recs.size() - 1;
+}
+
+int sopht_profile_range_end(int index, void* stream) {
+  if (index >= 0 && index < (int)g_recs.size()) cudaEventRecord(g_recs[index].e1, as_stream(stream));
+  return SOPHT_OK;
+}
+
 int sopht_profile_enable(int on) {
   g_prof_on = on != 0;
   return SOPHT_OK;

@@ -3,12 +3,13 @@ one process per GPU, torch.distributed (NCCL over NVLink) for the halo exchanges
 transposes of the distributed FFT Poisson solve; the compute phases are the same CUDA kernels the
 single-GPU path uses."""
 
-from .slab import SlabPartition, exchange_halos
+from .slab import HaloExchanger, SlabPartition, exchange_halos
 from .slab_flow import SlabUnboundedNavierStokesFlowSimulator3D
 from .slab_ib import SlabVirtualBoundaryForcing
 from .slab_poisson import SlabTransposePlan, SlabUnboundedPoissonSolver3D
 
 __all__ = [
+    "HaloExchanger",
     "SlabPartition",
     "SlabTransposePlan",
     "SlabUnboundedNavierStokesFlowSimulator3D",

@@ -77,29 +77,48 @@ class SlabPartition:
         return (1 if self.is_first else 0) | (2 if self.is_last else 0)
 
 
+class HaloExchanger:
+    """Nearest-neighbour exchange of the z halo planes with persistent pack / receive buffers (no allocation
+    per step: temporaries handed to the NCCL stream would otherwise churn the caching allocator)."""
+
+    def __init__(self, part: SlabPartition, group=None) -> None:
+        self.part, self.group = part, group
+        self._bufs: dict = {}
+
+    def _buffers(self, key, like: torch.Tensor):
+        b = self._bufs.get(key)
+        if b is None:
+            b = tuple(torch.empty_like(like) for _ in range(4))  # send-low, recv-low, send-high, recv-high
+            self._bufs[key] = b
+        return b
+
+    def __call__(self, fields) -> None:
+        part = self.part
+        if part.world_size == 1:
+            return
+        h, n = part.halo, part.nz_local
+        ops, unpack = [], []
+        for slot, f in enumerate(fields):
+            lo_src, hi_src = f[..., h : 2 * h, :, :], f[..., n : n + h, :, :]
+            sl, rl, sh, rh = self._buffers((slot, tuple(f.shape), f.dtype, f.device), lo_src)
+            if not part.is_first:  # low neighbour: send my first owned planes, receive its last owned planes
+                sl.copy_(lo_src)
+                ops.append(dist.P2POp(dist.isend, sl, part.rank - 1, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, rl, part.rank - 1, group=self.group))
+                unpack.append((f, slice(0, h), rl))
+            if not part.is_last:
+                sh.copy_(hi_src)
+                ops.append(dist.P2POp(dist.isend, sh, part.rank + 1, group=self.group))
+                ops.append(dist.P2POp(dist.irecv, rh, part.rank + 1, group=self.group))
+                unpack.append((f, slice(n + h, n + 2 * h), rh))
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        for f, sl_, recv in unpack:
+            f[..., sl_, :, :].copy_(recv)
+
+
 def exchange_halos(part: SlabPartition, fields, group=None) -> None:
     """Fill the halo planes of every local array in `fields` from the z neighbours (one batched
-    send/recv group; the outermost halos on the global boundary are left untouched)."""
-    if part.world_size == 1:
-        return
-    h = part.halo
-    n = part.nz_local
-    ops = []
-    keep = []
-    for f in fields:
-        if not part.is_first:  # low neighbour: send my first owned planes, receive its last owned planes
-            send = f[..., h : 2 * h, :, :].contiguous()
-            recv = torch.empty_like(send)
-            ops.append(dist.P2POp(dist.isend, send, part.rank - 1, group=group))
-            ops.append(dist.P2POp(dist.irecv, recv, part.rank - 1, group=group))
-            keep.append((f, slice(0, h), recv))
-        if not part.is_last:
-            send = f[..., n : n + h, :, :].contiguous()
-            recv = torch.empty_like(send)
-            ops.append(dist.P2POp(dist.isend, send, part.rank + 1, group=group))
-            ops.append(dist.P2POp(dist.irecv, recv, part.rank + 1, group=group))
-            keep.append((f, slice(n + h, n + 2 * h), recv))
-    for req in dist.batch_isend_irecv(ops):
-        req.wait()
-    for f, sl, recv in keep:
-        f[..., sl, :, :] = recv
+    send/recv group; the outermost halos on the global boundary are left untouched). One-off form of
+    HaloExchanger (allocates its buffers per call)."""
+    HaloExchanger(part, group)(fields)

@@ -23,7 +23,7 @@ from sopht_b200 import _lib
 from sopht_b200.numeric.eulerian_grid_ops.stencil_ops_3d import _sine_ramps
 from sopht_b200.simulator.flow.navier_stokes_flow_simulators import stable_timestep_from_max
 
-from .slab import SlabPartition, exchange_halos
+from .slab import HaloExchanger, SlabPartition
 from .slab_poisson import SlabUnboundedPoissonSolver3D
 
 
@@ -87,6 +87,7 @@ class SlabUnboundedNavierStokesFlowSimulator3D:
             self.eul_grid_forcing_field = zeros()
         self._unbounded_poisson_solver = SlabUnboundedPoissonSolver3D(
             nz, ny, nx, x_range=x_range, real_t=real_t, num_threads=num_threads, group=group)
+        self._exchangers: dict = {}
         self._vel_absmax = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._have_absmax = False
         self.step_mode = "fused-slab"
@@ -103,7 +104,12 @@ class SlabUnboundedNavierStokesFlowSimulator3D:
         field[..., h - (z0 - lo) : h + n + (hi - z0 - n), :, :] = g[..., lo:hi, :, :].to(field.device, field.dtype)
 
     def _halos(self, *fields: torch.Tensor) -> None:
-        exchange_halos(self.part, fields, self.group)
+        key = tuple(f.data_ptr() for f in fields)  # one persistent exchanger (buffers) per call site
+        ex = self._exchangers.get(key)
+        if ex is None:
+            ex = self._exchangers[key] = HaloExchanger(self.part, self.group)
+        with _lib.profile_range("comm.halo_exchange"):
+            ex(fields)
 
     # -- the step -----------------------------------------------------------------------------------------
     def time_step(self, dt: float, free_stream_velocity=(0.0, 0.0, 0.0)) -> None:

@@ -52,7 +52,8 @@ class SlabVirtualBoundaryForcing(VirtualBoundaryForcing):
             lag_grid_field=self.lag_grid_flow_velocity_field, eul_grid_field=eul_grid_velocity_field,
             interp_weights=self.interp_weights, nearest_eul_grid_index_to_lag_grid=self._local_index)
         if self.part.world_size > 1:
-            dist.all_reduce(self.lag_grid_flow_velocity_field, op=dist.ReduceOp.SUM, group=self.group)
+            with _lib.profile_range("comm.ib_allreduce"):
+                dist.all_reduce(self.lag_grid_flow_velocity_field, op=dist.ReduceOp.SUM, group=self.group)
         self.compute_lag_grid_velocity_mismatch_field(
             self.lag_grid_velocity_mismatch_field, self.lag_grid_flow_velocity_field, lag_grid_velocity_field)
         self.compute_lag_grid_forcing_field(

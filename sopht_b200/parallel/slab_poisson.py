@@ -13,6 +13,7 @@ UnboundedPoissonSolverPYFFTW3D.py:111-172 on the global grid.
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Any, Callable
 
 import numpy as np
@@ -71,9 +72,11 @@ class SlabTransposePlan:
 
     def solve(self, forward_x: Callable[[], None], middle: Callable[[], None], inverse_x: Callable[[], None]) -> None:
         forward_x()
-        self.to_kx_slabs()
+        with _lib.profile_range("comm.transpose_to_kx_slabs"):
+            self.to_kx_slabs()
         middle()
-        self.to_z_slabs()
+        with _lib.profile_range("comm.transpose_to_z_slabs"):
+            self.to_z_slabs()
         inverse_x()
 
 
@@ -93,6 +96,7 @@ class SlabUnboundedPoissonSolver3D:
         real_t: type = np.float32,
         n_components: int = 3,
         group: Any = None,
+        peer_exchange: bool | None = None,
     ) -> None:
         if _lib.dtype_code(real_t) != _lib.SOPHT_F32:
             msg = "the slab-decomposed Poisson solver is implemented for fp32 (power-of-two grids)"
@@ -126,6 +130,29 @@ class SlabUnboundedPoissonSolver3D:
         nz, ny = grid_size_z, grid_size_y
         self._work = torch.zeros((n_components, nz, 2 * ny, self.plan.nxl, 2), dtype=torch.float32, device=device)
         self._nyq_work = torch.zeros((n_components, nz, 2 * ny, 2), dtype=torch.float32, device=device)
+        # transposes fused into the kernels over NVLink peer memory (default on >1 rank; SOPHT_SLAB_PEER=0 or
+        # peer_exchange=False keeps the NCCL all-to-all path)
+        if peer_exchange is None:
+            peer_exchange = world > 1 and os.environ.get("SOPHT_SLAB_PEER", "1") != "0"
+        self.peer_exchange = bool(peer_exchange) and world > 1
+        if self.peer_exchange:
+            self._open_peer_exchange(lib, world, device, group)
+            self.path = "pow2-slab-peer"
+            nzl = self.plan.nzl
+            self._nyq_gather = torch.zeros((world, n_components, nzl, ny, 2), dtype=torch.float32, device=device)
+            self._barrier_flag = torch.zeros(1, dtype=torch.float32, device=device)
+            self.plan.send = self.plan.recv = None  # exchange buffers live in the library
+
+    def _open_peer_exchange(self, lib, world: int, device, group) -> None:
+        mine = (ctypes.c_ubyte * 128)()
+        _lib.check(lib.sopht_poisson_slab_enable_peer_exchange(self._handle, ctypes.cast(mine, ctypes.c_void_p)))
+        local = torch.tensor(list(mine), dtype=torch.uint8, device=device)
+        gathered = torch.zeros(world * 128, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(gathered, local, group=group)
+        blob = bytes(gathered.cpu().tolist())
+        buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        _lib.check(lib.sopht_poisson_slab_open_peers(self._handle, ctypes.cast(buf, ctypes.c_void_p)))
+        dist.barrier(group=group)
 
     def __del__(self) -> None:
         h = getattr(self, "_handle", None)
@@ -156,4 +183,22 @@ class SlabUnboundedPoissonSolver3D:
             _lib.check(lib.sopht_poisson_slab_inverse_x(
                 self._handle, ctypes.byref(fs), p(plan.send.data_ptr()), p(plan.nyq_local.data_ptr()), st))
 
-        plan.solve(forward_x, middle, inverse_x)
+        if not self.peer_exchange:
+            plan.solve(forward_x, middle, inverse_x)
+            return
+        # peer-memory path: the kernels themselves move the spectrum over NVLink; collectives only order the phases
+        part, nzl = self.part, plan.nzl
+        _lib.check(lib.sopht_poisson_slab_forward_x(
+            self._handle, ctypes.byref(fr), None, p(plan.nyq_local.data_ptr()), st))
+        with _lib.profile_range("comm.nyquist_allgather_barrier"):
+            # all ranks have finished writing into each other's buffers once this all-gather completes
+            dist.all_gather_into_tensor(self._nyq_gather, plan.nyq_local, group=plan.group)
+            plan.nyq_all.view(plan.ncomp, part.world_size, nzl, -1, 2).copy_(self._nyq_gather.transpose(0, 1))
+        _lib.check(lib.sopht_poisson_slab_yz(
+            self._handle, None, p(plan.nyq_all.data_ptr()), p(self._work.data_ptr()),
+            p(self._nyq_work.data_ptr()), st))
+        with _lib.profile_range("comm.barrier"):
+            dist.all_reduce(self._barrier_flag, group=plan.group)
+        plan.nyq_local.copy_(plan.nyq_all[:, part.rank * nzl : (part.rank + 1) * nzl])
+        _lib.check(lib.sopht_poisson_slab_inverse_x(
+            self._handle, ctypes.byref(fs), None, p(plan.nyq_local.data_ptr()), st))

@@ -102,7 +102,7 @@ static void fft3_ref(std::vector<cd>& f, int n2z, int n2y, int n2x, int sign) {
 // P = 1: the whole grid on one GPU. P > 1: the z-slab decomposed solve, every rank emulated in turn and the
 // two all-to-all transposes / the Nyquist all-gather done by plain copies (what parallel/slab_poisson.py does
 // with torch.distributed on the device).
-template <int NZ, int NY, int NX, int P = 1>
+template <int NZ, int NY, int NX, int P = 1, bool PEER = false>
 int run_case() {
   constexpr int C = 3, TX = 8, RX = 4;
   constexpr int LX = NX, LY = 2 * NY, LZ = 2 * NZ;
@@ -138,11 +138,16 @@ int run_case() {
     p2::SlabDims d{C, NZ, NY, NX, P, r};
     auto xp = p2::slab_x_params(d, rhs.data() + (size_t)r * NZL * NY * NX, nullptr, (int64_t)ncell,
                                 (int64_t)NY * NX, NX, send[r].data(), nyq_local[r].data(), twx.data(), twx2.data());
+    if (PEER) {  // the kernel writes chunk q straight into rank q's recv buffer ("peer memory")
+      float2* peers[8] = {};
+      for (int q = 0; q < P; ++q) peers[q] = recv[q].data();
+      xp = p2::slab_x_params_peer(xp, d, peers);
+    }
     emulate<p2::XFwd<LX, RX>>(xp, (int)((size_t)C * NZL * NY / RX), 1, 1);
   }
   // 2. all-to-all per component: chunk q of rank r's send[c] -> chunk r of rank q's recv[c]; Nyquist all-gather
   const size_t chunk = (size_t)NZL * NY * NXL;
-  for (int c = 0; c < C; ++c)
+  for (int c = 0; c < C && !PEER; ++c)
     for (int r = 0; r < P; ++r)
       for (int q = 0; q < P; ++q)
         std::copy(send[r].begin() + ((size_t)c * P + q) * chunk, send[r].begin() + ((size_t)c * P + q + 1) * chunk,
@@ -152,14 +157,22 @@ int run_case() {
       std::copy(nyq_local[r].begin() + (size_t)c * NZL * NY, nyq_local[r].begin() + (size_t)(c + 1) * NZL * NY,
                 nyq_all.begin() + ((size_t)c * NZ + (size_t)r * NZL) * NY);
   // 3. y forward, z convolution, y inverse on every rank's kx-slab (recv is (C, NZ, NY, NXL))
+  if (PEER)
+    for (int r = 0; r < P; ++r)
+      for (auto& v : send[r]) v = poison;
   for (int r = 0; r < P; ++r) {
     p2::SlabDims d{C, NZ, NY, NX, P, r};
     for (auto& v : work) v = poison;
     emulate<p2::YFwd<LY, TX>>(p2::slab_y_params(d, TX, recv[r].data(), work.data(), true, twy.data()), NXL / TX,
                               C * NZ, 1);
     emulate<p2::ZConv<LZ, TX>>(p2::slab_z_params(d, TX, work.data(), gmain.data(), NX, r * NXL, twz.data()), NXL / TX, LY, C);
-    emulate<p2::YInv<LY, TX>>(p2::slab_y_params(d, TX, work.data(), recv[r].data(), false, twy.data()), NXL / TX,
-                              C * NZ, 1);
+    auto yi = p2::slab_y_params(d, TX, work.data(), recv[r].data(), false, twy.data());
+    if (PEER) {  // output planes go straight into the owning rank's send buffer
+      float2* peers[8] = {};
+      for (int q = 0; q < P; ++q) peers[q] = send[q].data();
+      yi = p2::slab_yinv_params_peer(yi, d, peers);
+    }
+    emulate<p2::YInv<LY, TX>>(yi, NXL / TX, C * NZ, 1);
   }
   {  // Nyquist plane (every rank would do this redundantly)
     p2::SlabDims d{C, NZ, NY, NX, P, 0};
@@ -171,9 +184,9 @@ int run_case() {
                               C * NZ / TX, 1, 1);
   }
   // 4. all-to-all back: z range q of rank r's recv[c] -> chunk r of rank q's send[c]; Nyquist slices
-  for (int r = 0; r < P; ++r)
+  for (int r = 0; r < P && !PEER; ++r)
     for (auto& v : send[r]) v = poison;
-  for (int c = 0; c < C; ++c)
+  for (int c = 0; c < C && !PEER; ++c)
     for (int r = 0; r < P; ++r)
       for (int q = 0; q < P; ++q)
         std::copy(recv[r].begin() + ((size_t)c * P + q) * chunk, recv[r].begin() + ((size_t)c * P + q + 1) * chunk,
@@ -220,7 +233,7 @@ int run_case() {
         }
   }
   const double rel = sqrt(err2 / ref2);
-  printf("grid (%d,%d,%d) ranks %d: LX=%d LY=%d LZ=%d rel L2 err = %.3e %s\n", NZ, NY, NX, P, LX, LY, LZ, rel,
+  printf("grid (%d,%d,%d) ranks %d%s: LX=%d LY=%d LZ=%d rel L2 err = %.3e %s\n", NZ, NY, NX, P, PEER ? " (peer writes)" : "", LX, LY, LZ, rel,
          rel < 2e-6 ? "ok" : "FAIL");
   return rel < 2e-6 ? 0 : 1;
 }
@@ -240,6 +253,8 @@ int main(int argc, char** argv) {
   bad += run_case<128, 8, 16>();   // 256 (z)
   bad += run_case<16, 8, 32, 2>();    // z-slab decomposition over 2 ranks
   bad += run_case<8, 16, 64, 4>();    // ... over 4 ranks
+  bad += run_case<16, 8, 32, 2, true>();   // transposes fused into the x forward / y inverse kernels (peer writes)
+  bad += run_case<8, 16, 64, 4, true>();
   if (full) {                      // minutes on one core: every remaining decomposition, incl. three-pass 2048
     bad += run_case<64, 128, 256>();
     bad += run_case<256, 8, 512>();

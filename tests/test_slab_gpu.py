@@ -76,8 +76,9 @@ def test_slab_single_rank_with_ib_matches_single_gpu_path():
     assert "SLAB CHECK OK" in out.stdout
 
 
+@pytest.mark.parametrize("peer", ["1", "0"])  # transposes over peer memory (default) / NCCL all-to-all
 @pytest.mark.parametrize("world", [2, 4])
-def test_slab_multi_rank_nccl(world):
+def test_slab_multi_rank_nccl(world, peer):
     import torch
 
     if torch.cuda.device_count() < world:
@@ -85,6 +86,7 @@ def test_slab_multi_rank_nccl(world):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(29517 + world),
            os.path.join(ROOT, "tests", "mgpu_slab_check.py"), "32", "16", "64", "3"]
-    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600,
+                         env=dict(os.environ, SOPHT_SLAB_PEER=peer))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "SLAB CHECK OK" in out.stdout

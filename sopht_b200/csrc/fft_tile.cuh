@@ -71,9 +71,13 @@ FFT_HD float2 rot32(float2 a, int j) {
 template <int R>
 struct Dft;
 
+// run_half: the same transform when the upper half of the input (v[R/2..R-1]) is known to be zero - the first
+// radix-2 stage degenerates into copies. Written out because x + 0.0f is not foldable under IEEE rules
+// (-0.0f + 0.0f = +0.0f), so the compiler keeps those additions when it is merely handed literal zeros.
 template <>
 struct Dft<1> {
   FFT_HD static void run(float2*) {}
+  FFT_HD static void run_half(float2*) {}
 };
 template <>
 struct Dft<2> {
@@ -82,6 +86,7 @@ struct Dft<2> {
     v[0] = cadd(a, b);
     v[1] = csub(a, b);
   }
+  FFT_HD static void run_half(float2* v) { v[1] = v[0]; }
 };
 template <>
 struct Dft<4> {
@@ -93,10 +98,17 @@ struct Dft<4> {
     v[2] = csub(a, c);
     v[3] = csub(b, d);
   }
+  FFT_HD static void run_half(float2* v) {
+    const float2 a = v[0], c = v[1], d = mul_mi(v[1]);
+    v[0] = cadd(a, c);
+    v[1] = cadd(a, d);
+    v[2] = csub(a, c);
+    v[3] = csub(a, d);
+  }
 };
 
-// R = RA*RB: n = RB*a + b, k = ka + RA*kb
-template <int RA, int RB>
+// R = RA*RB: n = RB*a + b, k = ka + RA*kb. HALF: inputs n >= R/2 are zero, i.e. a >= RA/2 in every sub-transform.
+template <int RA, int RB, bool HALF = false>
 FFT_HD void dft_composite(float2* v) {
   constexpr int R = RA * RB;
   float2 u[RB][RA];
@@ -104,7 +116,10 @@ FFT_HD void dft_composite(float2* v) {
   for (int b = 0; b < RB; ++b) {
 #pragma unroll
     for (int a = 0; a < RA; ++a) u[b][a] = v[RB * a + b];
-    Dft<RA>::run(u[b]);
+    if (HALF)
+      Dft<RA>::run_half(u[b]);
+    else
+      Dft<RA>::run(u[b]);
 #pragma unroll
     for (int ka = 1; ka < RA; ++ka)
       if (b > 0) u[b][ka] = rot32(u[b][ka], (32 / R) * b * ka);
@@ -122,14 +137,17 @@ FFT_HD void dft_composite(float2* v) {
 template <>
 struct Dft<8> {
   FFT_HD static void run(float2* v) { dft_composite<4, 2>(v); }
+  FFT_HD static void run_half(float2* v) { dft_composite<4, 2, true>(v); }
 };
 template <>
 struct Dft<16> {
   FFT_HD static void run(float2* v) { dft_composite<4, 4>(v); }
+  FFT_HD static void run_half(float2* v) { dft_composite<4, 4, true>(v); }
 };
 template <>
 struct Dft<32> {
   FFT_HD static void run(float2* v) { dft_composite<8, 4>(v); }
+  FFT_HD static void run_half(float2* v) { dft_composite<8, 4, true>(v); }
 };
 
 template <int R>
@@ -201,7 +219,7 @@ FFT_HD void fwd_first(Load ld, Acc sm, int t, const float2* __restrict__ tw) {
 #pragma unroll
   for (int q = 0; q < NB; ++q) {
     const int j = t + q * C::T;
-    dft<R, false>(v[q]);
+    Dft<R>::run_half(v[q]);  // pruned: the upper half of the padded input is zero
     sm.at(0, j) = v[q][0];
 #pragma unroll
     for (int k = 1; k < R; ++k) sm.at(k * S, j) = cmul(v[q][k], tw[j * k]);

@@ -20,13 +20,27 @@ namespace sopht {
 
 namespace {
 
+// Barrier of a kernel's synchronisation group (K::SYNC_THREADS consecutive threads: the whole CTA, a named
+// barrier per group of warps, or a single warp). Groups share nothing but the read-only tables.
+template <class K>
+__device__ __forceinline__ void group_sync() {
+  if constexpr (K::SYNC_THREADS >= K::THREADS) {
+    __syncthreads();
+  } else if constexpr (K::SYNC_THREADS == 32) {
+    __syncwarp();
+  } else {
+    asm volatile("bar.sync %0, %1;" ::"r"((int)(threadIdx.x / K::SYNC_THREADS) + 1), "n"(K::SYNC_THREADS)
+                 : "memory");
+  }
+}
+
 // phases 1..P of kernel K, a barrier between consecutive phases (phase 0 is issued by the kernel loop)
 template <class K, int P>
 struct DevPhases {
   __device__ __forceinline__ static void run(const typename K::Params& p, int bx, int by, int it,
                                              float2* smem, const float2* stage) {
     DevPhases<K, P - 1>::run(p, bx, by, it, smem, stage);
-    if (P > 1) __syncthreads();
+    if (P > 1) group_sync<K>();
     K::template phase<P>(p, bx, by, it, threadIdx.x, smem, stage);
   }
 };
@@ -76,11 +90,11 @@ __global__ void __launch_bounds__(K::THREADS, MINB) p2_kernel(const typename K::
     }
     const bool has_next = ns < ntile;
     K::template phase<0>(p, bx, by, it, threadIdx.x, p2_smem, stage);
-    __syncthreads();
+    group_sync<K>();
     if (STAGED && has_next) K::prefetch(p, (int)(ns % gx), (int)(ns / gx), nit, threadIdx.x, stage);
     DevPhases<K, K::NPHASE - 1>::run(p, bx, by, it, p2_smem, stage);
     if (!has_next) break;
-    __syncthreads();
+    group_sync<K>();
     s = ns;
     it = nit;
   }

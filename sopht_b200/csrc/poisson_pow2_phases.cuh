@@ -135,6 +135,7 @@ struct StageCopy {
 
 template <int L, int TX>
 struct YFwd {
+  static constexpr int SYNC_THREADS = Cfg<L>::T * TX;  // whole CTA (narrower groups: see profiles/r01_poisson_layout_experiments.txt)
   using Params = ColParams;
   static constexpr int THREADS = Cfg<L>::T * TX;
   static constexpr int NPHASE = Cfg<L>::NP;
@@ -177,6 +178,7 @@ struct YFwd {
 
 template <int L, int TX>
 struct YInv {
+  static constexpr int SYNC_THREADS = Cfg<L>::T * TX;  // whole CTA (narrower groups: see profiles/r01_poisson_layout_experiments.txt)
   using Params = ColParams;
   static constexpr int THREADS = Cfg<L>::T * TX;
   static constexpr int NPHASE = Cfg<L>::NP;
@@ -255,6 +257,7 @@ struct GreenTile {  // from the tile's shared-memory slice gs[f * TX + col], f =
 
 template <int L, int TX>
 struct ZConv {
+  static constexpr int SYNC_THREADS = Cfg<L>::T * TX;  // whole CTA (narrower groups: see profiles/r01_poisson_layout_experiments.txt)
   using Params = ZParams;
   static constexpr int THREADS = Cfg<L>::T * TX;
   static constexpr int NP = Cfg<L>::NP;
@@ -375,6 +378,9 @@ struct XFwd {
   using Params = XParams;
   static constexpr int T = Cfg<L>::T;
   static constexpr int THREADS = T * RX;
+  // rows are independent transforms: the warps of a row synchronise among themselves only (-2 % at 512^3; the
+  // same change made the inverse kernel 7 % slower, which therefore keeps the CTA-wide barrier)
+  static constexpr int SYNC_THREADS = T >= 32 ? T : (THREADS >= 32 ? 32 : THREADS);
   static constexpr int NP = Cfg<L>::NP;
   static constexpr int NPHASE = NP + 1;
   static constexpr int NITER = 1;
@@ -443,6 +449,7 @@ struct XInv {
   using Params = XParams;
   static constexpr int T = Cfg<L>::T;
   static constexpr int THREADS = T * RX;
+  static constexpr int SYNC_THREADS = THREADS;
   static constexpr int NP = Cfg<L>::NP;
   static constexpr int NPHASE = NP + 1;
   static constexpr int NITER = 1;
@@ -474,16 +481,24 @@ struct XInv {
       // Z_k = E_k + i O_k, E = (X_k + conj X_{L-k})/2, O = conj(w^k) (X_k - conj X_{L-k})/2
       const float2* in = stage ? stage + r * (L + 1) : p.spec + p.row_base(row);
       const float2* nq = stage ? stage + r * (L + 1) + L : p.nyq + row;
+      // one chunk (single GPU) or a staged row: bin k is element k, no chunk arithmetic per access
+      const bool plain = stage != nullptr || (1 << p.chunk_shift) >= L;
+      auto combine = [&](auto bin) {
 #pragma unroll
-      for (int q = 0; q < Cfg<L>::E; ++q) {
-        const int k = t + q * T;
-        const float2 a = stage ? in[k] : in[p.bin(k)];
-        const float2 b = k == 0 ? *nq : (stage ? in[L - k] : in[p.bin(L - k)]);
-        const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
-        const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
-        const float2 o = fft::cmul_conj(d, tw2[k]);
-        sm(fft::spectrum_position<L>(k)) = make_float2(e.x - o.y, e.y + o.x);
-      }
+        for (int q = 0; q < Cfg<L>::E; ++q) {
+          const int k = t + q * T;
+          const float2 a = in[bin(k)];
+          const float2 b = k == 0 ? *nq : in[bin(L - k)];
+          const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
+          const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
+          const float2 o = fft::cmul_conj(d, tw2[k]);
+          sm(fft::spectrum_position<L>(k)) = make_float2(e.x - o.y, e.y + o.x);
+        }
+      };
+      if (plain)
+        combine([](int k) { return (int64_t)k; });
+      else
+        combine([&](int k) { return p.bin(k); });
     } else if (P == 1) {
       fft::inv_first<L>(InPlaceSrc<L>{sm}, sm, t);
     } else if (P == NPHASE - 1) {

@@ -30,7 +30,9 @@ def test_cuda_poisson_generic_path_matches_reference_goldens(case, precision):
     case(make_ops("cuda", precision), precision, flags=POISSON_FORCE_GENERIC)
 
 
-@pytest.mark.parametrize("grid", [(8, 8, 16), (16, 32, 64), (32, 16, 128), (64, 128, 256), (128, 128, 256)])
+# the last three reach the radix-32 transform lengths (2ny / 2nz = 512, 1024) and the three-pass L = 2048 row kernel
+@pytest.mark.parametrize("grid", [(8, 8, 16), (16, 32, 64), (32, 16, 128), (64, 128, 256), (128, 128, 256),
+                                  (256, 512, 32), (512, 256, 16), (8, 8, 2048)])
 def test_cuda_poisson_pow2_path_vs_oracle(grid):
     """fp32 power-of-two fast path (hand-written pruned FFT pipeline) against the scipy.fft oracle, which is
     itself pinned to the reference's test restatement; scalar, vector and strided-view solves."""

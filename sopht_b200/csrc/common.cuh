@@ -51,6 +51,11 @@ struct ProfScope {
 };
 #define SOPHT_PROF(label, st) ::sopht::ProfScope prof_scope__(label, st)
 
+// fused_step3d.cu: w += p * curl_c(f) with the 16-byte-vector register-marching kernel; false = views not
+// eligible, nothing launched
+bool ns3d_try_forcing_curl_vec(int dtype, const sopht_field_t* vorticity_field,
+                               const sopht_field_t* velocity_forcing_field, double prefactor, cudaStream_t st);
+
 // ---- device-side views ----------------------------------------------------------------------
 // 3-D scalar view (z, y, x); strides in elements.
 template <typename T>

@@ -201,8 +201,30 @@ FFT_HD int spectrum_position(int k) {
   return (k1 * C::R2 + k2) * C::R3 + k3;
 }
 
+// ---- twiddle table ---------------------------------------------------------------------------------------
+// The passes multiply butterfly output k of butterfly j by w^(j k) (first / last pass) or w^(j k L/SP) (middle
+// pass of the three-pass lengths), w = exp(-2 pi i / L). Read from the natural table w^n the lanes of a warp
+// (consecutive j, one k) would hit addresses k * 8 bytes apart - up to 16-way bank conflicts for even k, 2.6x
+// the shared-memory wavefronts on average. The table is therefore stored per pass, butterfly index fastest:
+//   table[k * S1 + j]     = w^(j k),         k < R1, j < S1 = L / R1            (L entries)
+//   table[L + k * S2 + j] = w^(j k L / SP),  k < R2, j < S2 = L / (R1 R2)       (L / R1 entries, NP = 3 only)
+template <int L>
+struct TwTable {
+  using C = Cfg<L>;
+  static constexpr int S1 = L / C::R1;
+  static constexpr int S2 = L / (C::R1 * C::R2);
+  static constexpr int SIZE = L + (C::NP == 3 ? L / C::R1 : 0);
+  // natural: w^n, n < L (global memory); one call per thread of a THREADS-wide CTA
+  template <int THREADS>
+  FFT_HD static void fill(float2* table, const float2* natural, int tid) {
+    for (int i = tid; i < L; i += THREADS) table[i] = natural[(i % S1) * (i / S1)];
+    if (C::NP == 3)
+      for (int i = tid; i < L / C::R1; i += THREADS) table[L + i] = natural[(i % S2) * (i / S2) * C::R1];
+  }
+};
+
 // ---- passes. `Acc` maps a logical position (0..L-1) of THIS thread's column to a float2& in smem ---------
-// tw: forward twiddles of length L, tw[j] = exp(-2 pi i j / L)
+// tw: the TwTable<L> above
 
 // forward first pass: global (pruned: positions >= L/2 are zero) -> butterfly R1 -> twiddle -> smem
 template <int L, class Load, class Acc>
@@ -222,7 +244,7 @@ FFT_HD void fwd_first(Load ld, Acc sm, int t, const float2* __restrict__ tw) {
     Dft<R>::run_half(v[q]);  // pruned: the upper half of the padded input is zero
     sm.at(0, j) = v[q][0];
 #pragma unroll
-    for (int k = 1; k < R; ++k) sm.at(k * S, j) = cmul(v[q][k], tw[j * k]);
+    for (int k = 1; k < R; ++k) sm.at(k * S, j) = cmul(v[q][k], tw[k * S + j]);
   }
 }
 
@@ -240,7 +262,7 @@ FFT_HD void fwd_mid(Acc sm, int t, const float2* __restrict__ tw) {
     dft<R, false>(v);
     sm.at(0, base) = v[0];
 #pragma unroll
-    for (int k = 1; k < R; ++k) sm.at(k * S, base) = cmul(v[k], tw[j * k * (L / SP)]);
+    for (int k = 1; k < R; ++k) sm.at(k * S, base) = cmul(v[k], tw[L + k * S + j]);
   }
 }
 
@@ -317,7 +339,7 @@ FFT_HD void inv_mid(Acc sm, int t, const float2* __restrict__ tw) {
     float2 v[R];
     v[0] = sm.at(0, base);
 #pragma unroll
-    for (int k = 1; k < R; ++k) v[k] = cmul_conj(sm.at(k * S, base), tw[j * k * (L / SP)]);
+    for (int k = 1; k < R; ++k) v[k] = cmul_conj(sm.at(k * S, base), tw[L + k * S + j]);
     dft<R, true>(v);
 #pragma unroll
     for (int n = 0; n < R; ++n) sm.at(n * S, base) = v[n];
@@ -335,7 +357,7 @@ FFT_HD void inv_last(Acc sm, int t, const float2* __restrict__ tw, Store st) {
     float2 v[R];
     v[0] = sm.at(0, j);
 #pragma unroll
-    for (int k = 1; k < R; ++k) v[k] = cmul_conj(sm.at(k * S, j), tw[j * k]);
+    for (int k = 1; k < R; ++k) v[k] = cmul_conj(sm.at(k * S, j), tw[k * S + j]);
     dft<R, true>(v);
 #pragma unroll
     for (int n = 0; n < R / 2; ++n) st(n * S + j, v[n]);

@@ -463,8 +463,11 @@ __global__ void __launch_bounds__(32 * VBY)
   }
 }
 
-// u = p * curl_c(psi) (ring <- 0) + U_inf; max_cells sum_c |u_c|. 12 B read + 12 B written per cell (fp32).
-template <typename T>
+// ACCUM = false: u = p * curl_c(psi) (ring <- 0) + U_inf; max_cells sum_c |u_c|. 12 B read + 12 B written per
+//                cell (fp32).
+// ACCUM = true : out += p * curl_c(psi) on the interior, ring cells untouched (the forcing update
+//                w += p curl(f), update_vorticity_from_velocity_forcing_3d.py:12-132). 24 B read + 12 B written.
+template <typename T, bool ACCUM>
 __global__ void __launch_bounds__(32 * VBY)
     velocity_vec_kernel(Vec3Out<T> out, Vec3View<T> psi, T p, T fx, T fy, T fz, T* max_out, int nz, int ny,
                         int nx, int kchunk) {
@@ -505,12 +508,22 @@ __global__ void __launch_bounds__(32 * VBY)
     Vec<T> pz_im, pz_ip, py_im, py_ip;
     sv::x_neighbours(pzc, ezl, ezr, lane, pz_im, pz_ip);
     sv::x_neighbours(pyc, eyl, eyr, lane, py_im, py_ip);
-    if (act) {
+    const bool kin = jin && k >= 1 && k < nz - 1;
+    if (act && (!ACCUM || kin)) {  // accumulate mode: a ring plane / ring row keeps its values (warp-uniform)
       Vec<T> ux, uy, uz;
-      const bool kin = jin && k >= 1 && k < nz - 1;
+      const int64_t o = (int64_t)k * out.sz + ocol;
+      if (ACCUM) ux = sv::vload_rw(out.p[0] + o), uy = sv::vload_rw(out.p[1] + o), uz = sv::vload_rw(out.p[2] + o);
 #pragma unroll
       for (int m = 0; m < W; ++m) {
         const int i = i0 + m;
+        if (ACCUM) {
+          if (i >= 1 && i < nx - 1) {
+            ux.v[m] += p * (pz_jp.v[m] - pz_jm.v[m] - pyn.v[m] + pym.v[m]);
+            uy.v[m] += p * (pxn.v[m] - pxm.v[m] - pz_ip.v[m] + pz_im.v[m]);
+            uz.v[m] += p * (py_ip.v[m] - py_im.v[m] - px_jp.v[m] + px_jm.v[m]);
+          }
+          continue;
+        }
         T vx = T(0), vy = T(0), vz = T(0);
         if (kin && i >= 1 && i < nx - 1) {
           const T ccx = pz_jp.v[m] - pz_jm.v[m] - pyn.v[m] + pym.v[m];
@@ -527,7 +540,6 @@ __global__ void __launch_bounds__(32 * VBY)
         const T a = fabs(vx) + fabs(vy) + fabs(vz);
         m_acc = a > m_acc ? a : m_acc;
       }
-      const int64_t o = (int64_t)k * out.sz + ocol;
       sv::vstore(out.p[0] + o, ux);
       sv::vstore(out.p[1] + o, uy);
       sv::vstore(out.p[2] + o, uz);
@@ -535,7 +547,7 @@ __global__ void __launch_bounds__(32 * VBY)
     pxm = pxc, pym = pyc;
     pxc = pxn, pyc = pyn;
   }
-  if (max_out) {
+  if (!ACCUM && max_out) {
     for (int off = 16; off > 0; off >>= 1) {
       const T o = __shfl_xor_sync(0xffffffffu, m_acc, off);
       m_acc = o > m_acc ? o : m_acc;
@@ -630,6 +642,32 @@ int pick_kchunk(int nz, int ny, int nx, int ncomp_grids, int tx, int ty) {
 #undef FTHREADS
 
 }  // namespace
+
+// w += p * curl_c(f) with the register-marching kernel when both views are vector-aligned and distinct;
+// returns false (nothing launched) otherwise and the caller falls back to the one-thread-per-cell kernel.
+bool ns3d_try_forcing_curl_vec(int dtype, const sopht_field_t* vorticity_field,
+                               const sopht_field_t* velocity_forcing_field, double prefactor, cudaStream_t st) {
+  const size_t elem = dtype == SOPHT_F32 ? 4 : 8;
+  if (!vec_ok(vorticity_field, dtype) || !vec_ok(velocity_forcing_field, dtype) ||
+      overlaps(vorticity_field, velocity_forcing_field, elem))
+    return false;
+  const int nz = (int)vorticity_field->shape[1], ny = (int)vorticity_field->shape[2],
+            nx = (int)vorticity_field->shape[3];
+  const int w = dtype == SOPHT_F32 ? 4 : 2;
+  const int kchunk = pick_vec_kchunk(nz, ny, nx, 1, w);
+  dim3 grid((nx + 32 * w - 1) / (32 * w), (ny + VBY - 1) / VBY, (nz + kchunk - 1) / kchunk), block(32, VBY, 1);
+  if (grid.y > 65535 || grid.z > 65535) return false;
+  if (dtype == SOPHT_F32)
+    velocity_vec_kernel<float, true><<<grid, block, 0, st>>>(
+        out_view<float>(vorticity_field), in_view<float>(velocity_forcing_field), (float)prefactor, 0.f, 0.f,
+        0.f, nullptr, nz, ny, nx, kchunk);
+  else
+    velocity_vec_kernel<double, true><<<grid, block, 0, st>>>(
+        out_view<double>(vorticity_field), in_view<double>(velocity_forcing_field), prefactor, 0.0, 0.0, 0.0,
+        nullptr, nz, ny, nx, kchunk);
+  return true;
+}
+
 }  // namespace sopht
 
 using namespace sopht;
@@ -778,11 +816,11 @@ int sopht_ns3d_velocity_from_stream_function(int dtype, const sopht_field_t* vel
     dim3 grid((nx + 32 * w - 1) / (32 * w), (ny + VBY - 1) / VBY, (nz + kchunk - 1) / kchunk), block(32, VBY, 1);
     if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
     if (dtype == SOPHT_F32)
-      velocity_vec_kernel<float><<<grid, block, 0, st>>>(
+      velocity_vec_kernel<float, false><<<grid, block, 0, st>>>(
           out_view<float>(velocity_field), in_view<float>(stream_func_field), (float)prefactor, (float)f0,
           (float)f1, (float)f2, reinterpret_cast<float*>(max_abs_sum_out), nz, ny, nx, kchunk);
     else
-      velocity_vec_kernel<double><<<grid, block, 0, st>>>(
+      velocity_vec_kernel<double, false><<<grid, block, 0, st>>>(
           out_view<double>(velocity_field), in_view<double>(stream_func_field), prefactor, f0, f1, f2,
           reinterpret_cast<double*>(max_abs_sum_out), nz, ny, nx, kchunk);
     SOPHT_CHECK_LAUNCH();

@@ -242,8 +242,16 @@ struct Pow2Poisson : PoissonImpl {
   float2 *A = nullptr, *nyqA = nullptr, *B = nullptr, *nyqB = nullptr;
   float2 *twx = nullptr, *twx2 = nullptr, *twy = nullptr, *twz = nullptr;
   PoissonImpl* generic = nullptr;  // built lazily for views this path cannot take (x-stride != 1, ...)
+  // The kx = nx (Nyquist) plane's three small kernels form a dependency chain of latency-bound launches; they
+  // run on a side stream, forked after the x forward pass and joined before the x inverse, and fill the tails
+  // of the main y / z kernels.
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   ~Pow2Poisson() override {
+    if (side) cudaStreamDestroy(side);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     cudaFree(ghat_natural);
     cudaFree(gm);
     cudaFree(gn);
@@ -288,6 +296,11 @@ struct Pow2Poisson : PoissonImpl {
     if ((rc = upload_twiddles(&twy, 2 * ny, 2 * ny, st))) return rc;
     if ((rc = upload_twiddles(&twz, 2 * nz, 2 * nz, st))) return rc;
     SOPHT_CUDA(cudaStreamSynchronize(st));
+    int lo = 0, hi = 0;
+    SOPHT_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    SOPHT_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));
+    SOPHT_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    SOPHT_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     return SOPHT_OK;
   }
 
@@ -321,17 +334,21 @@ struct Pow2Poisson : PoissonImpl {
                                        vec ? rhs->stride[0] : 0, rhs->stride[o], rhs->stride[o + 1], A, nyqA,
                                        twx, twx2);
     if ((rc = launch_xfwd(nx, xp, rows, st))) return rc;
-    if ((rc = launch_yfwd(LY, p2::slab_y_params(d, TX, A, B, true, twy), dim3(nx / TX, C * nz, 1), st)))
+    SOPHT_CUDA(cudaEventRecord(ev_fork, st));
+    SOPHT_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    if ((rc = launch_yfwd(LY, p2::nyquist_y_params(d, TX, nyqA, nyqB, true, twy), dim3(C * nz / TX, 1, 1), side)))
       return rc;
-    if ((rc = launch_yfwd(LY, p2::nyquist_y_params(d, TX, nyqA, nyqB, true, twy), dim3(C * nz / TX, 1, 1), st)))
+    if ((rc = launch_zconv(LZ, p2::nyquist_z_params(d, TX, nyqB, gn, twz), dim3(LY / TX, 1, 1), side))) return rc;
+    if ((rc = launch_yinv(LY, p2::nyquist_y_params(d, TX, nyqB, nyqA, false, twy), dim3(C * nz / TX, 1, 1), side)))
+      return rc;
+    SOPHT_CUDA(cudaEventRecord(ev_join, side));
+    if ((rc = launch_yfwd(LY, p2::slab_y_params(d, TX, A, B, true, twy), dim3(nx / TX, C * nz, 1), st)))
       return rc;
     if ((rc = launch_zconv(LZ, p2::slab_z_params(d, TX, B, gm, nx, 0, twz), dim3(nx / TX, LY, 1), st)))
       return rc;
-    if ((rc = launch_zconv(LZ, p2::nyquist_z_params(d, TX, nyqB, gn, twz), dim3(LY / TX, 1, 1), st))) return rc;
     if ((rc = launch_yinv(LY, p2::slab_y_params(d, TX, B, A, false, twy), dim3(nx / TX, C * nz, 1), st)))
       return rc;
-    if ((rc = launch_yinv(LY, p2::nyquist_y_params(d, TX, nyqB, nyqA, false, twy), dim3(C * nz / TX, 1, 1), st)))
-      return rc;
+    SOPHT_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     xp = p2::slab_x_params(d, nullptr, reinterpret_cast<float*>(sol->data), vec ? sol->stride[0] : 0,
                            sol->stride[o], sol->stride[o + 1], A, nyqA, twx, twx2);
     return launch_xinv(nx, xp, rows, st);

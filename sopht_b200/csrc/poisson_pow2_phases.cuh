@@ -53,16 +53,12 @@ struct RowAcc {
 };
 
 // ---- shared-memory tables --------------------------------------------------------------------------------
-// The twiddle table (and, in the z pass, the tile's slice of the folded Green's function) live in shared memory
-// right behind the data tile: smem = [data SMEM_ELEMS][tables EXTRA_ELEMS][staging]. Read from global memory
-// they cost one LDG with a 64-bit address register pair per use, and those registers stay scoreboarded until the
-// load has read them - measured as the top stall of the 255-register radix-32 kernels. init() fills the
-// twiddle part once per (persistent) CTA.
-#ifndef SOPHT_P2_NO_SMEM_TABLES
-#define SOPHT_P2_SMEM_TABLES 1
-#else
-#define SOPHT_P2_SMEM_TABLES 0
-#endif
+// The twiddle table (fft::TwTable: per-pass, bank-conflict-free order) and, in the z pass, the tile's slice of the
+// folded Green's function live in shared memory right behind the data tile:
+// smem = [data SMEM_ELEMS][tables EXTRA_ELEMS][staging]. Read from global memory they cost one LDG with a 64-bit
+// address register pair per use, and those registers stay scoreboarded until the load has read them - measured
+// as the top stall of the 255-register radix-32 kernels. init() fills the twiddle part once per (persistent) CTA.
+using fft::TwTable;
 
 template <int THREADS>
 FFT_HD void copy_table(float2* dst, const float2* src, int n, int tid) {
@@ -141,14 +137,14 @@ struct YFwd {
   static constexpr int NPHASE = Cfg<L>::NP;
   static constexpr int NITER = 1;
   static constexpr int SMEM_ELEMS = ColAcc<L, TX>::ROWS * TX;
-  static constexpr int EXTRA_ELEMS = SOPHT_P2_SMEM_TABLES ? L : 0;
+  static constexpr int EXTRA_ELEMS = TwTable<L>::SIZE;
   static constexpr int STAGE_ELEMS = (L / 2) * TX;
   static constexpr bool STAGE_SHARED = false;  // a thread reads back only what it copied itself
   static constexpr bool WANT_STAGE = Cfg<L>::E >= 32;
   static constexpr bool DEFAULT_TWO_CTAS = true, DEFAULT_STAGED = false;
   FFT_HD static int niter(const Params&) { return 1; }
   FFT_HD static void init(const Params& p, int tid, float2* smem) {
-    if (EXTRA_ELEMS) copy_table<THREADS>(smem + SMEM_ELEMS, p.tw, L, tid);
+    TwTable<L>::template fill<THREADS>(smem + SMEM_ELEMS, p.tw, tid);
   }
   FFT_HD static void prefetch(const Params& p, int bx, int by, int, int tid, float2* stage) {
     const int col = tid % TX, t = tid / TX;
@@ -159,7 +155,7 @@ struct YFwd {
   FFT_HD static void phase(const Params& p, int bx, int by, int, int tid, float2* smem, const float2* stage) {
     const int col = tid % TX, t = tid / TX;
     ColAcc<L, TX> sm{smem, col};
-    const float2* tw = EXTRA_ELEMS ? smem + SMEM_ELEMS : p.tw;
+    const float2* tw = smem + SMEM_ELEMS;
     if (P == 0) {
       if (stage) {
         fft::fwd_first<L>(StageLoad<TX>{stage + col}, sm, t, tw);
@@ -184,14 +180,14 @@ struct YInv {
   static constexpr int NPHASE = Cfg<L>::NP;
   static constexpr int NITER = 1;
   static constexpr int SMEM_ELEMS = ColAcc<L, TX>::ROWS * TX;
-  static constexpr int EXTRA_ELEMS = SOPHT_P2_SMEM_TABLES ? L : 0;
+  static constexpr int EXTRA_ELEMS = TwTable<L>::SIZE;
   static constexpr int STAGE_ELEMS = L * TX;
   static constexpr bool STAGE_SHARED = false;
   static constexpr bool WANT_STAGE = Cfg<L>::E >= 32;
   static constexpr bool DEFAULT_TWO_CTAS = true, DEFAULT_STAGED = false;
   FFT_HD static int niter(const Params&) { return 1; }
   FFT_HD static void init(const Params& p, int tid, float2* smem) {
-    if (EXTRA_ELEMS) copy_table<THREADS>(smem + SMEM_ELEMS, p.tw, L, tid);
+    TwTable<L>::template fill<THREADS>(smem + SMEM_ELEMS, p.tw, tid);
   }
   FFT_HD static void prefetch(const Params& p, int bx, int by, int, int tid, float2* stage) {
     const int col = tid % TX, t = tid / TX;
@@ -202,7 +198,7 @@ struct YInv {
   FFT_HD static void phase(const Params& p, int bx, int by, int, int tid, float2* smem, const float2* stage) {
     const int col = tid % TX, t = tid / TX;
     ColAcc<L, TX> sm{smem, col};
-    const float2* tw = EXTRA_ELEMS ? smem + SMEM_ELEMS : p.tw;
+    const float2* tw = smem + SMEM_ELEMS;
     if (P == 0) {
       if (stage) {
         fft::inv_first<L>(StageSrcIdx<TX>{stage + col}, sm, t);
@@ -235,16 +231,6 @@ struct ZParams {
 // G_hat(kz) for one column, kz given as (blk, klast) of the position the forward last pass leaves it at.
 // Whether kz folds (kz > L/2 -> L - kz) depends on klast alone: the spectrum index is
 // rev(blk) + (L/RLAST) * klast with rev(blk) < L/RLAST, and L/2 is a multiple of L/RLAST.
-template <int L>
-struct GreenFold {  // straight from global memory (g already offset to this thread's column)
-  const float* g;
-  int64_t zs;
-  FFT_HD float operator()(int blk, int klast) const {
-    const int kz = fft::spectrum_index<L>(blk, klast);
-    const int f = klast < Cfg<L>::RLAST / 2 ? kz : L - kz;
-    return g[f * zs];
-  }
-};
 template <int L, int TX>
 struct GreenTile {  // from the tile's shared-memory slice gs[f * TX + col], f = 0 .. L/2
   const float* gs;
@@ -265,7 +251,7 @@ struct ZConv {
   static constexpr int NITER = 0;            // runtime: ncomp
   static constexpr int SMEM_ELEMS = ColAcc<L, TX>::ROWS * TX;
   static constexpr int G_FLOATS = (L / 2 + 1) * TX;  // the tile's folded G_hat slice, shared by its components
-  static constexpr int EXTRA_ELEMS = SOPHT_P2_SMEM_TABLES ? L + (G_FLOATS + 1) / 2 : 0;
+  static constexpr int EXTRA_ELEMS = TwTable<L>::SIZE + (G_FLOATS + 1) / 2;
   static constexpr int STAGE_ELEMS = (L / 2) * TX;
   static constexpr bool STAGE_SHARED = false;
   static constexpr bool WANT_STAGE = Cfg<L>::E >= 32;
@@ -273,7 +259,7 @@ struct ZConv {
   static constexpr bool DEFAULT_TWO_CTAS = THREADS < 256, DEFAULT_STAGED = THREADS >= 256;
   FFT_HD static int niter(const Params& p) { return p.ncomp; }
   FFT_HD static void init(const Params& p, int tid, float2* smem) {
-    if (EXTRA_ELEMS) copy_table<THREADS>(smem + SMEM_ELEMS, p.tw, L, tid);
+    TwTable<L>::template fill<THREADS>(smem + SMEM_ELEMS, p.tw, tid);
   }
   FFT_HD static void prefetch(const Params& p, int bx, int by, int c, int tid, float2* stage) {
     const int col = tid % TX, t = tid / TX;
@@ -290,10 +276,10 @@ struct ZConv {
     const int col = tid % TX, t = tid / TX;
     ColAcc<L, TX> sm{smem, col};
     float2* base = p.data + bx * p.d_bx + by * p.d_by + c * p.d_c + col * p.cs;
-    const float2* tw = EXTRA_ELEMS ? smem + SMEM_ELEMS : p.tw;
-    float* gs = reinterpret_cast<float*>(smem + SMEM_ELEMS + L);
+    const float2* tw = smem + SMEM_ELEMS;
+    float* gs = reinterpret_cast<float*>(smem + SMEM_ELEMS + TwTable<L>::SIZE);
     if (P == 0) {
-      if (EXTRA_ELEMS && c == 0) {  // this tile's G_hat slice, asynchronously, behind the first butterflies
+      if (c == 0) {  // this tile's G_hat slice, asynchronously, behind the first butterflies
         const float* g = p.g + green_offset(p, bx, by, col);
         for (int f = t; f <= L / 2; f += Cfg<L>::T) fft::async_copy4(gs + f * TX + col, g + f * p.g_zs);
       }
@@ -303,13 +289,9 @@ struct ZConv {
         GlobalLoad ld{base, (unsigned)p.rs};
         fft::fwd_first<L>(ld, sm, t, tw);
       }
-      if (EXTRA_ELEMS && c == 0) fft::async_commit_wait_all();  // published by the barrier after this phase
+      if (c == 0) fft::async_commit_wait_all();  // published by the barrier after this phase
     } else if (P == NP - 1) {
-      if (EXTRA_ELEMS) {
-        fft::fwd_last_mul_inv_first<L>(sm, t, GreenTile<L, TX>{gs + col});
-      } else {
-        fft::fwd_last_mul_inv_first<L>(sm, t, GreenFold<L>{p.g + green_offset(p, bx, by, col), p.g_zs});
-      }
+      fft::fwd_last_mul_inv_first<L>(sm, t, GreenTile<L, TX>{gs + col});
     } else if (P == NPHASE - 1) {
       GlobalStore st{base, (unsigned)p.rs};
       fft::inv_last<L>(sm, t, tw, st);
@@ -385,17 +367,15 @@ struct XFwd {
   static constexpr int NPHASE = NP + 1;
   static constexpr int NITER = 1;
   static constexpr int SMEM_ELEMS = RowAcc<L>::PITCH * RX;
-  static constexpr int EXTRA_ELEMS = SOPHT_P2_SMEM_TABLES ? 2 * L : 0;  // tw, tw2
+  static constexpr int EXTRA_ELEMS = TwTable<L>::SIZE + L;  // twiddle table, tw2
   static constexpr int STAGE_ELEMS = (L / 2) * RX;
   static constexpr bool STAGE_SHARED = false;
   static constexpr bool WANT_STAGE = false;
   static constexpr bool DEFAULT_TWO_CTAS = false, DEFAULT_STAGED = false;
   FFT_HD static int niter(const Params&) { return 1; }
   FFT_HD static void init(const Params& p, int tid, float2* smem) {
-    if (EXTRA_ELEMS) {
-      copy_table<THREADS>(smem + SMEM_ELEMS, p.tw, L, tid);
-      copy_table<THREADS>(smem + SMEM_ELEMS + L, p.tw2, L, tid);
-    }
+    TwTable<L>::template fill<THREADS>(smem + SMEM_ELEMS, p.tw, tid);
+    copy_table<THREADS>(smem + SMEM_ELEMS + TwTable<L>::SIZE, p.tw2, L, tid);
   }
   FFT_HD static const float2* row_ptr(const Params& p, const float* base, int64_t row) {
     const int y = (int)(row % p.ny);
@@ -414,8 +394,8 @@ struct XFwd {
     const int t = tid % T, r = tid / T;
     const int64_t row = (int64_t)bx * RX + r;
     RowAcc<L> sm{smem + r * RowAcc<L>::PITCH};
-    const float2* tw = EXTRA_ELEMS ? smem + SMEM_ELEMS : p.tw;
-    const float2* tw2 = EXTRA_ELEMS ? smem + SMEM_ELEMS + L : p.tw2;
+    const float2* tw = smem + SMEM_ELEMS;
+    const float2* tw2 = smem + SMEM_ELEMS + TwTable<L>::SIZE;
     if (P == 0) {
       if (stage) {
         fft::fwd_first<L>(StageLoad<1>{stage + r * (L / 2)}, sm, t, tw);
@@ -454,7 +434,7 @@ struct XInv {
   static constexpr int NPHASE = NP + 1;
   static constexpr int NITER = 1;
   static constexpr int SMEM_ELEMS = RowAcc<L>::PITCH * RX;
-  static constexpr int EXTRA_ELEMS = SOPHT_P2_SMEM_TABLES ? 2 * L : 0;  // tw, tw2
+  static constexpr int EXTRA_ELEMS = TwTable<L>::SIZE + L;  // twiddle table, tw2
   static constexpr int STAGE_ELEMS = (L + 1) * RX;  // spectrum row + its Nyquist bin
   static constexpr bool STAGE_SHARED = true;        // bin k is combined with bin L-k, staged by another thread
   static constexpr bool WANT_STAGE = false;
@@ -475,8 +455,8 @@ struct XInv {
     const int t = tid % T, r = tid / T;
     const int64_t row = (int64_t)bx * RX + r;
     RowAcc<L> sm{smem + r * RowAcc<L>::PITCH};
-    const float2* tw = EXTRA_ELEMS ? smem + SMEM_ELEMS : p.tw;
-    const float2* tw2 = EXTRA_ELEMS ? smem + SMEM_ELEMS + L : p.tw2;
+    const float2* tw = smem + SMEM_ELEMS;
+    const float2* tw2 = smem + SMEM_ELEMS + TwTable<L>::SIZE;
     if (P == 0) {
       // Z_k = E_k + i O_k, E = (X_k + conj X_{L-k})/2, O = conj(w^k) (X_k - conj X_{L-k})/2
       const float2* in = stage ? stage + r * (L + 1) : p.spec + p.row_base(row);

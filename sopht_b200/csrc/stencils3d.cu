@@ -220,11 +220,19 @@ struct RampTable {
 
 // z_faces: bit 0 = the low-z face of this view is a global boundary, bit 1 = the high-z face is (both set
 // for a whole grid; a z-slab of a decomposed grid sets only the faces it owns, its other z side is interior).
+// One launch covers every face of every component: blockIdx.z = (component * 3 + face) * 2 + side.
+template <typename T>
+struct ShellViews {
+  View3<T> f[3];
+};
 template <typename T>
 __global__ void __launch_bounds__(128)
-    penalise_shell_kernel(View3<T> f, int nz, int ny, int nx, int w, RampTable ramps, int face, int z_faces) {
+    penalise_shell_kernel(ShellViews<T> views, int nz, int ny, int nx, int w, RampTable ramps, int z_faces) {
   // face 0: z-shell (the owned z faces of the inner box, all y,x in the box)
   // face 1: y-shell excluding z-shell cells; face 2: x-shell excluding z- and y-shell cells
+  const int face = (blockIdx.z >> 1) % 3;
+  const int comp = (blockIdx.z >> 1) / 3;
+  const View3<T> f = comp == 0 ? views.f[0] : (comp == 1 ? views.f[1] : views.f[2]);
   const bool zlo = z_faces & 1, zhi = z_faces & 2;
   const int za = zlo ? w - 1 : 0, zb = zhi ? nz - w : nz - 1;  // inner box z extent [za, zb]
   const int ly = ny - 2 * w + 2, lx = nx - 2 * w + 2;           // inner box extent in y, x
@@ -232,9 +240,10 @@ __global__ void __launch_bounds__(128)
   int sk, b, c;                                                  // source z index, box-local (y,x)
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int u = blockIdx.y;
-  const int s = blockIdx.z;  // 0: front, 1: back
+  const int s = blockIdx.z & 1;  // 0: front, 1: back
   if (face == 0) {
     if (t >= lx || u >= ly) return;
+    if (!z_faces) return;
     if (s == 0 && !zlo) return;
     if (s == 1 && (!zhi || (zlo && zb == za))) return;
     sk = s ? zb : za;
@@ -282,8 +291,8 @@ __global__ void __launch_bounds__(128)
 }
 
 template <typename T>
-static int penalise3d_impl(const View3<T>& f, int nz, int ny, int nx, int w, const double* rx,
-                           const double* ry, const double* rz, int z_faces, cudaStream_t st) {
+static int penalise3d_impl(const ShellViews<T>& views, int ncomp, int nz, int ny, int nx, int w,
+                           const double* rx, const double* ry, const double* rz, int z_faces, cudaStream_t st) {
   RampTable tab;
   for (int q = 0; q < 2 * w; ++q) {
     tab.v[0][q] = rx[q];
@@ -294,23 +303,14 @@ static int penalise3d_impl(const View3<T>& f, int nz, int ny, int nx, int w, con
   const int za = zlo ? w - 1 : 0, zb = zhi ? nz - w : nz - 1;
   const int nin = (zb - (zhi ? 1 : 0)) - (za + (zlo ? 1 : 0)) + 1;  // z planes off the owned z-shells
   const int ly = ny - 2 * w + 2, lx = nx - 2 * w + 2;
+  // thread extents of the three faces: (lx, ly), (lx, nin), (ly - 2, nin); the kernel drops the excess
+  const int ext_t = lx > ly - 2 ? lx : ly - 2;
+  int ext_u = z_faces ? ly : 1;
+  if (nin > ext_u) ext_u = nin;
   SOPHT_PROF("penalise_field_boundary", st);
-  dim3 block(128, 1, 1);
-  if (z_faces) {
-    dim3 grid((lx + 127) / 128, ly, 2);
-    penalise_shell_kernel<T><<<grid, block, 0, st>>>(f, nz, ny, nx, w, tab, 0, z_faces);
-    SOPHT_CHECK_LAUNCH();
-  }
-  if (nin > 0) {
-    dim3 grid((lx + 127) / 128, nin, 2);
-    penalise_shell_kernel<T><<<grid, block, 0, st>>>(f, nz, ny, nx, w, tab, 1, z_faces);
-    SOPHT_CHECK_LAUNCH();
-  }
-  if (nin > 0 && ly > 2) {
-    dim3 grid((ly - 2 + 127) / 128, nin, 2);
-    penalise_shell_kernel<T><<<grid, block, 0, st>>>(f, nz, ny, nx, w, tab, 2, z_faces);
-    SOPHT_CHECK_LAUNCH();
-  }
+  dim3 block(128, 1, 1), grid((ext_t + 127) / 128, ext_u, ncomp * 6);
+  penalise_shell_kernel<T><<<grid, block, 0, st>>>(views, nz, ny, nx, w, tab, z_faces);
+  SOPHT_CHECK_LAUNCH();
   return SOPHT_OK;
 }
 
@@ -367,6 +367,10 @@ static int curl_impl(const sopht_field_t* out, const sopht_field_t* field, doubl
                      cudaStream_t st) {
   GRID_DIMS(field)
   SOPHT_PROF(MODE == 1 ? "update_vorticity_from_velocity_forcing" : "curl", st);
+  if (MODE == 1 && ns3d_try_forcing_curl_vec(sizeof(T) == 4 ? SOPHT_F32 : SOPHT_F64, out, field, p, st)) {
+    SOPHT_CHECK_LAUNCH();
+    return SOPHT_OK;
+  }
   curl_kernel<T, MODE><<<g.grid, g.block, 0, st>>>(
       comp3<T>(out, 0), comp3<T>(out, 1), comp3<T>(out, 2), cview(comp3<T>(field, 0)),
       cview(comp3<T>(field, 1)), cview(comp3<T>(field, 2)), (T)p, nz, ny, nx, reset);
@@ -570,18 +574,15 @@ static int penalise3d_entry(const char* fn, int dtype, const sopht_field_t* fiel
     SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid smaller than twice the penalisation width", fn);
   cudaStream_t st = as_stream(stream);
   const int ncomp = field->ndim == 4 ? 3 : 1;
-  for (int c = 0; c < ncomp; ++c) {
-    int rc;
-    if (dtype == SOPHT_F32)
-      rc = penalise3d_impl<float>(field->ndim == 4 ? comp3<float>(field, c) : scalar3<float>(field),
-                                  nz, ny, nx, width, ramp_x, ramp_y, ramp_z, z_faces, st);
-    else
-      rc = penalise3d_impl<double>(
-          field->ndim == 4 ? comp3<double>(field, c) : scalar3<double>(field), nz, ny, nx, width,
-          ramp_x, ramp_y, ramp_z, z_faces, st);
-    if (rc) return rc;
+  if (dtype == SOPHT_F32) {
+    ShellViews<float> v;
+    for (int c = 0; c < 3; ++c)
+      v.f[c] = field->ndim == 4 ? comp3<float>(field, c) : scalar3<float>(field);
+    return penalise3d_impl<float>(v, ncomp, nz, ny, nx, width, ramp_x, ramp_y, ramp_z, z_faces, st);
   }
-  return SOPHT_OK;
+  ShellViews<double> v;
+  for (int c = 0; c < 3; ++c) v.f[c] = field->ndim == 4 ? comp3<double>(field, c) : scalar3<double>(field);
+  return penalise3d_impl<double>(v, ncomp, nz, ny, nx, width, ramp_x, ramp_y, ramp_z, z_faces, st);
 }
 
 int sopht_penalise_field_boundary_3d(int dtype, const sopht_field_t* field, int width,

@@ -52,6 +52,19 @@ __device__ __forceinline__ Vec<double> vload(const double* p) {
   r.v[0] = q.x, r.v[1] = q.y;
   return r;
 }
+// 16-byte load of data this kernel also writes (plain ld.global, not the read-only path)
+__device__ __forceinline__ Vec<float> vload_rw(const float* p) {
+  const float4 q = *reinterpret_cast<const float4*>(p);
+  Vec<float> r;
+  r.v[0] = q.x, r.v[1] = q.y, r.v[2] = q.z, r.v[3] = q.w;
+  return r;
+}
+__device__ __forceinline__ Vec<double> vload_rw(const double* p) {
+  const double2 q = *reinterpret_cast<const double2*>(p);
+  Vec<double> r;
+  r.v[0] = q.x, r.v[1] = q.y;
+  return r;
+}
 template <typename T>
 __device__ __forceinline__ Vec<T> vload_if(bool pred, const T* p) {
   return pred ? vload(p) : vzero<T>();

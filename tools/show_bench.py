@@ -13,6 +13,7 @@ for f in sys.argv[1:]:
     print(f"{f}: {d['value']:.3f} {d['unit']}  {d['ms_per_step']:.3f} ms/step  e2e {d['e2e']['value']:.3f}  "
           f"step-frac {d.get('step_roofline', {}).get('frac', 0):.3f}  clocks {d.get('clocks')}")
     for k, v in d.get("kernels", {}).items():
-        print(f"  {k:42s} {v['ms_per_step']:8.3f} ms {v['share']*100:5.1f}% {v.get('achieved_gbs') or 0:8.0f} GB/s")
+        share = f"{v['share'] * 100:5.1f}%" if v.get("share") is not None else "  ovl "
+        print(f"  {k:42s} {v['ms_per_step']:8.3f} ms {share} {v.get('achieved_gbs') or 0:8.0f} GB/s")
     if d.get("cpu_baseline"):
         print("  cpu_baseline", d["cpu_baseline"])

@@ -337,6 +337,33 @@ int sopht_poisson_slab_open_peers(sopht_poisson_slab_t handle, const unsigned ch
 int sopht_poisson_slab_destroy(sopht_poisson_slab_t handle);
 
 /* ------------------------------------------------------------------------ */
+/* Peer-memory arena of the z-slab decomposition (one process per GPU, one    */
+/* box): field storage every rank can address over NVLink (CUDA IPC), the     */
+/* halo exchange as one kernel of direct stores into the neighbours' halo     */
+/* planes, and a device-side barrier. The reference has no distributed path;  */
+/* what travels is the ghost ring its stencil kernels read.    */
+/* ------------------------------------------------------------------------ */
+typedef struct sopht_peer_arena *sopht_peer_arena_t;
+
+/* Allocates (and zeroes) payload_bytes of device memory plus a small flag header; ipc_handle_out receives the
+ * 64-byte CUDA IPC handle the host layer all-gathers (nranks x 64 bytes, rank order) for open(). */
+int sopht_peer_arena_create(sopht_peer_arena_t *handle, size_t payload_bytes, int nranks, int rank,
+                            unsigned char *ipc_handle_out);
+int sopht_peer_arena_open(sopht_peer_arena_t handle, const unsigned char *all_ipc_handles);
+/* device pointer to this rank's payload; the host layer lays the same objects out at the same offsets on all ranks */
+void *sopht_peer_arena_payload(sopht_peer_arena_t handle);
+/* Fills the z halo planes of up to 4 local arrays (ncomp[q], nz_local + 2 halo, ny, nx), given by their byte offset
+ * in the payload and the byte stride between components: this rank's first / last owned planes are stored into the
+ * low / high neighbour's halo planes after a ready handshake; the kernel retires when both neighbours have done the
+ * same for this rank. Must be issued in the same order on every rank. */
+int sopht_peer_halo_exchange(sopht_peer_arena_t handle, int nfields, const int64_t *payload_offsets_bytes,
+                             const int64_t *comp_stride_bytes, const int *ncomp, int nz_local, int halo,
+                             int64_t plane_bytes, void *stream);
+/* all-ranks barrier in stream order (everything enqueued before it on every rank is complete and visible) */
+int sopht_peer_barrier(sopht_peer_arena_t handle, void *stream);
+int sopht_peer_arena_destroy(sopht_peer_arena_t handle);
+
+/* ------------------------------------------------------------------------ */
 /* Immersed boundary: Eulerian <-> Lagrangian transfer, 4-point delta kernels */
 /* Lagrangian arrays are (dim, N) with N contiguous; nearest_index is int64;  */
 /* lag_positions / body velocities are of pos_dtype (SOPHT_F32 / SOPHT_F64),  */

@@ -147,6 +147,17 @@ _HANDLE_SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "sopht_poisson_slab_enable_peer_exchange": (ctypes.c_int, [_P, _P]),
     "sopht_poisson_slab_open_peers": (ctypes.c_int, [_P, _P]),
     "sopht_poisson_slab_destroy": (ctypes.c_int, [_P]),
+    # peer-memory arena (halo exchange / barrier over NVLink)
+    "sopht_peer_arena_create": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_size_t, _I, _I, _P]),
+    "sopht_peer_arena_open": (ctypes.c_int, [_P, _P]),
+    "sopht_peer_arena_payload": (_P, [_P]),
+    "sopht_peer_halo_exchange": (
+        ctypes.c_int,
+        [_P, _I, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int), _I, _I,
+         ctypes.c_int64, _P],
+    ),
+    "sopht_peer_barrier": (ctypes.c_int, [_P, _P]),
+    "sopht_peer_arena_destroy": (ctypes.c_int, [_P]),
     # fused 3-D Navier-Stokes passes
     "sopht_ns3d_advect_rotational": (ctypes.c_int, [_I, _F, _F, _F, _D, _P]),
     "sopht_ns3d_diffuse": (ctypes.c_int, [_I, _F, _F, _D, _F, _P]),

@@ -3,6 +3,7 @@ one process per GPU, torch.distributed (NCCL over NVLink) for the halo exchanges
 transposes of the distributed FFT Poisson solve; the compute phases are the same CUDA kernels the
 single-GPU path uses."""
 
+from .peer import PeerArena
 from .slab import HaloExchanger, SlabPartition, exchange_halos
 from .slab_flow import SlabUnboundedNavierStokesFlowSimulator3D
 from .slab_ib import SlabVirtualBoundaryForcing
@@ -10,6 +11,7 @@ from .slab_poisson import SlabTransposePlan, SlabUnboundedPoissonSolver3D
 
 __all__ = [
     "HaloExchanger",
+    "PeerArena",
     "SlabPartition",
     "SlabTransposePlan",
     "SlabUnboundedNavierStokesFlowSimulator3D",

@@ -13,6 +13,7 @@ their ghost-ring rule lands on the true global boundary (SlabPartition.stencil_v
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Any
 
 import numpy as np
@@ -23,6 +24,7 @@ from sopht_b200 import _lib
 from sopht_b200.numeric.eulerian_grid_ops.stencil_ops_3d import _sine_ramps
 from sopht_b200.simulator.flow.navier_stokes_flow_simulators import stable_timestep_from_max
 
+from .peer import PeerArena
 from .slab import HaloExchanger, SlabPartition
 from .slab_poisson import SlabUnboundedPoissonSolver3D
 
@@ -80,13 +82,22 @@ class SlabUnboundedNavierStokesFlowSimulator3D:
                 msg = "fewer planes per rank than the penalisation width"
                 raise ValueError(msg)
         shape = (3, *self.part.local_shape)
-        zeros = lambda: torch.zeros(shape, dtype=torch.float32, device=self.device)  # noqa: E731
+        # Fields live in a peer-memory arena when there are neighbours: the halo exchange is then one kernel of
+        # direct NVLink stores into the neighbours' halo planes (SOPHT_SLAB_PEER=0: torch tensors + NCCL send/recv)
+        self._arena = None
+        if world > 1 and os.environ.get("SOPHT_SLAB_PEER", "1") != "0" and (ny * nx * 4) % 16 == 0:
+            nfields = 5 if with_forcing else 4
+            self._arena = PeerArena(nfields * (int(np.prod(shape)) * 4 + 256), group)
+            zeros = lambda: self._arena.alloc(shape, np.float32)  # noqa: E731
+        else:
+            zeros = lambda: torch.zeros(shape, dtype=torch.float32, device=self.device)  # noqa: E731
         self.vorticity_field, self.velocity_field = zeros(), zeros()
         self.buffer_vector_field, self.stream_func_field = zeros(), zeros()
         if with_forcing:
             self.eul_grid_forcing_field = zeros()
         self._unbounded_poisson_solver = SlabUnboundedPoissonSolver3D(
-            nz, ny, nx, x_range=x_range, real_t=real_t, num_threads=num_threads, group=group)
+            nz, ny, nx, x_range=x_range, real_t=real_t, num_threads=num_threads, group=group,
+            peer_arena=self._arena)
         self._exchangers: dict = {}
         self._vel_absmax = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._have_absmax = False
@@ -104,6 +115,9 @@ class SlabUnboundedNavierStokesFlowSimulator3D:
         field[..., h - (z0 - lo) : h + n + (hi - z0 - n), :, :] = g[..., lo:hi, :, :].to(field.device, field.dtype)
 
     def _halos(self, *fields: torch.Tensor) -> None:
+        if self._arena is not None:
+            self._arena.halo_exchange(fields, self.part.nz_local, self.part.halo)
+            return
         key = tuple(f.data_ptr() for f in fields)  # one persistent exchanger (buffers) per call site
         ex = self._exchangers.get(key)
         if ex is None:

@@ -97,6 +97,7 @@ class SlabUnboundedPoissonSolver3D:
         n_components: int = 3,
         group: Any = None,
         peer_exchange: bool | None = None,
+        peer_arena: Any = None,
     ) -> None:
         if _lib.dtype_code(real_t) != _lib.SOPHT_F32:
             msg = "the slab-decomposed Poisson solver is implemented for fp32 (power-of-two grids)"
@@ -135,6 +136,7 @@ class SlabUnboundedPoissonSolver3D:
         if peer_exchange is None:
             peer_exchange = world > 1 and os.environ.get("SOPHT_SLAB_PEER", "1") != "0"
         self.peer_exchange = bool(peer_exchange) and world > 1
+        self._peer_arena = peer_arena  # its device-side barrier replaces the all-reduce between y inverse and x inverse
         if self.peer_exchange:
             self._open_peer_exchange(lib, world, device, group)
             self.path = "pow2-slab-peer"
@@ -197,8 +199,11 @@ class SlabUnboundedPoissonSolver3D:
         _lib.check(lib.sopht_poisson_slab_yz(
             self._handle, None, p(plan.nyq_all.data_ptr()), p(self._work.data_ptr()),
             p(self._nyq_work.data_ptr()), st))
-        with _lib.profile_range("comm.barrier"):
-            dist.all_reduce(self._barrier_flag, group=plan.group)
+        if self._peer_arena is not None:
+            self._peer_arena.barrier()
+        else:
+            with _lib.profile_range("comm.barrier"):
+                dist.all_reduce(self._barrier_flag, group=plan.group)
         plan.nyq_local.copy_(plan.nyq_all[:, part.rank * nzl : (part.rank + 1) * nzl])
         _lib.check(lib.sopht_poisson_slab_inverse_x(
             self._handle, ctypes.byref(fs), None, p(plan.nyq_local.data_ptr()), st))

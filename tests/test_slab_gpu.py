@@ -90,3 +90,25 @@ def test_slab_multi_rank_nccl(world, peer):
                          env=dict(os.environ, SOPHT_SLAB_PEER=peer))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert "SLAB CHECK OK" in out.stdout
+
+
+def test_peer_arena_single_rank():
+    """Arena-backed tensors are ordinary zero-initialised CUDA tensors; with one rank the exchange and the barrier
+    are no-ops (the multi-rank protocol is covered by test_slab_multi_rank_nccl on boxes with >= 2 GPUs)."""
+    import torch
+
+    from sopht_b200.parallel import PeerArena
+
+    arena = PeerArena(2 * (3 * 6 * 8 * 16 * 4 + 256))
+    a = arena.alloc((3, 6, 8, 16))
+    b = arena.alloc((3, 6, 8, 16))
+    assert a.is_cuda and a.dtype == torch.float32 and float(a.abs().max()) == 0.0
+    assert a.data_ptr() % 256 == 0 and b.data_ptr() >= a.data_ptr() + a.numel() * 4
+    a += 1.0
+    b[:, 1:-1] = 2.0
+    arena.halo_exchange((a, b), nz_local=4, halo=1)
+    arena.barrier()
+    torch.cuda.synchronize()
+    assert float(a.sum()) == a.numel() and float(b[:, 0].abs().max()) == 0.0
+    with pytest.raises(MemoryError):
+        arena.alloc((3, 6, 8, 16))

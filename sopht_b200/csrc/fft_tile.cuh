@@ -406,6 +406,14 @@ FFT_HD void async_copy4(float* smem_dst, const float* gsrc) {
   *smem_dst = *gsrc;
 #endif
 }
+// bring the L2 sector holding *p in from DRAM, no register or shared-memory destination
+FFT_HD void prefetch_l2(const void* p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
 FFT_HD void async_commit_wait_all() {
 #ifdef __CUDA_ARCH__
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");

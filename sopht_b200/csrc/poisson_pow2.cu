@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(K::THREADS, MINB) p2_kernel(const typename K::
     K::template phase<0>(p, bx, by, it, threadIdx.x, p2_smem, stage);
     group_sync<K>();
     if (STAGED && has_next) K::prefetch(p, (int)(ns % gx), (int)(ns / gx), nit, threadIdx.x, stage);
+    if (!STAGED && K::L2_PREFETCH && has_next) K::l2_prefetch(p, (int)(ns % gx), (int)(ns / gx), nit, threadIdx.x);
     DevPhases<K, K::NPHASE - 1>::run(p, bx, by, it, p2_smem, stage);
     if (!has_next) break;
     group_sync<K>();

@@ -129,6 +129,25 @@ struct StageCopy {
   FFT_HD void operator()(int e) const { fft::async_copy8(s + e * TX, g + (unsigned)e * rs); }
 };
 
+// L2 prefetch of the element a thread will load in its next tile's first phase: one request per 32-byte sector
+// (columns are 8 bytes apart, so every fourth column's thread asks). The y kernels run as two unstaged
+// 128-register CTAs per SM and have neither registers nor shared memory left to hold a prefetched tile; pulling it
+// into L2 costs neither and hides the DRAM part of the first-phase latency: y forward 2.02 -> 1.90 ms, y inverse
+// 2.19 -> 1.98 ms at 512^3, x inverse 0.049 -> 0.042 ms at 128x128x256.
+struct L2Prefetch {
+  const float2* g;
+  unsigned rs;
+  bool lead;
+  FFT_HD void operator()(int e) const {
+    if (lead) fft::prefetch_l2(g + (unsigned)e * rs);
+  }
+};
+#ifndef SOPHT_P2_NO_L2_PREFETCH
+#define SOPHT_P2_L2_PREFETCH 1
+#else
+#define SOPHT_P2_L2_PREFETCH 0
+#endif
+
 template <int L, int TX>
 struct YFwd {
   static constexpr int SYNC_THREADS = Cfg<L>::T * TX;  // whole CTA (narrower groups: see profiles/r01_poisson_layout_experiments.txt)
@@ -150,6 +169,14 @@ struct YFwd {
     const int col = tid % TX, t = tid / TX;
     StageCopy<TX> cp{stage + col, p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, (unsigned)p.in_rs};
     fft::fwd_first_elems<L>(t, cp);
+  }
+  // unstaged variants: the next tile's first-phase inputs are pulled into L2 while this tile is transformed
+  static constexpr bool L2_PREFETCH = SOPHT_P2_L2_PREFETCH;
+  FFT_HD static void l2_prefetch(const Params& p, int bx, int by, int, int tid) {
+    const int col = tid % TX, t = tid / TX;
+    L2Prefetch pf{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, (unsigned)p.in_rs,
+                  (col & 3) == 0 && p.in_cs == 1};
+    fft::fwd_first_elems<L>(t, pf);
   }
   template <int P>
   FFT_HD static void phase(const Params& p, int bx, int by, int, int tid, float2* smem, const float2* stage) {
@@ -193,6 +220,13 @@ struct YInv {
     const int col = tid % TX, t = tid / TX;
     StageCopy<TX> cp{stage + col, p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, (unsigned)p.in_rs};
     fft::inv_first_elems<L>(t, cp);
+  }
+  static constexpr bool L2_PREFETCH = SOPHT_P2_L2_PREFETCH;
+  FFT_HD static void l2_prefetch(const Params& p, int bx, int by, int, int tid) {
+    const int col = tid % TX, t = tid / TX;
+    L2Prefetch pf{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, (unsigned)p.in_rs,
+                  (col & 3) == 0 && p.in_cs == 1};
+    fft::inv_first_elems<L>(t, pf);
   }
   template <int P>
   FFT_HD static void phase(const Params& p, int bx, int by, int, int tid, float2* smem, const float2* stage) {
@@ -265,6 +299,14 @@ struct ZConv {
     const int col = tid % TX, t = tid / TX;
     StageCopy<TX> cp{stage + col, p.data + bx * p.d_bx + by * p.d_by + c * p.d_c + col * p.cs, (unsigned)p.rs};
     fft::fwd_first_elems<L>(t, cp);
+  }
+  // measured (B200): the z pass loses with it (L = 512, four unstaged CTAs: 0.62 -> 0.77 ms at 256^3)
+  static constexpr bool L2_PREFETCH = false;
+  FFT_HD static void l2_prefetch(const Params& p, int bx, int by, int c, int tid) {
+    const int col = tid % TX, t = tid / TX;
+    L2Prefetch pf{p.data + bx * p.d_bx + by * p.d_by + c * p.d_c + col * p.cs, (unsigned)p.rs,
+                  (col & 3) == 0 && p.cs == 1};
+    fft::fwd_first_elems<L>(t, pf);
   }
   FFT_HD static int64_t green_offset(const Params& p, int bx, int by, int col) {
     const int ky = p.nyq ? bx * TX + col : by;
@@ -389,6 +431,14 @@ struct XFwd {
     StageCopy<1> cp{stage + r * (L / 2), row_ptr(p, p.real_in, (int64_t)bx * RX + r), 1u};
     fft::fwd_first_elems<L>(t, cp);
   }
+  // next tile's real rows (L / 2 float2 = L / 8 sectors per row, spread over the row's T threads);
+  // measured: 2-5 % slower with it (contiguous rows: the hardware already streams them), so off
+  static constexpr bool L2_PREFETCH = false;
+  FFT_HD static void l2_prefetch(const Params& p, int bx, int, int, int tid) {
+    const int t = tid % T, r = tid / T;
+    const float2* row = row_ptr(p, p.real_in, (int64_t)bx * RX + r);
+    for (int s = t; s < L / 8; s += T) fft::prefetch_l2(row + s * 4);
+  }
   template <int P>
   FFT_HD static void phase(const Params& p, int bx, int, int, int tid, float2* smem, const float2* stage) {
     const int t = tid % T, r = tid / T;
@@ -449,6 +499,13 @@ struct XInv {
 #pragma unroll
     for (int q = 0; q < Cfg<L>::E; ++q) fft::async_copy8(s + t + q * T, in + p.bin(t + q * T));
     if (t == 0) fft::async_copy8(s + L, p.nyq + row);
+  }
+  // next tile's spectrum rows (L float2 = L / 4 sectors per row; chunks are multiples of a sector)
+  static constexpr bool L2_PREFETCH = SOPHT_P2_L2_PREFETCH;
+  FFT_HD static void l2_prefetch(const Params& p, int bx, int, int, int tid) {
+    const int t = tid % T, r = tid / T;
+    const float2* in = p.spec + p.row_base((int64_t)bx * RX + r);
+    for (int s = t; s < L / 4; s += T) fft::prefetch_l2(in + p.bin(s * 4));
   }
   template <int P>
   FFT_HD static void phase(const Params& p, int bx, int, int, int tid, float2* smem, const float2* stage) {

@@ -305,7 +305,7 @@ int sopht_poisson_destroy(sopht_poisson_t handle);
 /* [r nx/P, (r+1) nx/P) of the half spectrum. Buffers are caller-owned device */
 /* memory of complex64 elements:                                              */
 /*   send / recv  (C, P, nz/P, ny, nx/P)  ==  (C, nz, ny, nx/P) after exchange */
-/*   work         (C, nz, 2 ny, nx/P)                                          */
+/*   work         2 x (C, nz, 2 ny, nx/P): x-major spectrum + the z pass's tile-major output */
 /*   nyquist_local (C, nz/P, ny), nyquist_all (C, nz, ny), nyquist_work (C, nz, 2 ny) */
 /* Sequence per solve (sopht_b200/parallel/slab_poisson.py):                  */
 /*   forward_x -> per component all-to-all(send -> recv), all-gather(nyquist)  */

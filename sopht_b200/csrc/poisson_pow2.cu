@@ -64,8 +64,21 @@ constexpr int auto_min_ctas() {
 
 // Persistent kernel: CTA b owns tiles b, b + gridDim.x, ... (neighbouring CTAs work on neighbouring tiles at
 // the same time, which keeps DRAM pages shared); all iterations (components) of a tile stay on one CTA.
+// Tile s -> (bx, by): 2^zb_shift consecutive by first, then bx, then the remaining by (zb_shift = 0: bx fastest).
+// The y inverse uses it: neighbouring by (z planes) are adjacent 64-byte segments of the kx-tile-major spectrum
+// it reads, neighbouring bx adjacent segments of the x-major spectrum it writes.
+struct TileOrder {
+  int gx, zb_shift;
+  __device__ __forceinline__ void operator()(int64_t s, int& bx, int& by) const {
+    const int64_t q = s >> zb_shift;
+    bx = (int)(q % gx);
+    by = (int)((q / gx) << zb_shift) + (int)(s & ((1 << zb_shift) - 1));
+  }
+};
+
 template <class K, int MINB, bool STAGED>
-__global__ void __launch_bounds__(K::THREADS, MINB) p2_kernel(const typename K::Params p, int gx, int gy) {
+__global__ void __launch_bounds__(K::THREADS, MINB)
+    p2_kernel(const typename K::Params p, int gx, int gy, int zb_shift) {
   extern __shared__ float2 p2_smem[];
   float2* stage = STAGED ? p2_smem + K::SMEM_ELEMS + K::EXTRA_ELEMS : nullptr;
   const int niter = K::niter(p);
@@ -75,13 +88,16 @@ __global__ void __launch_bounds__(K::THREADS, MINB) p2_kernel(const typename K::
   if (s >= ntile) return;
   K::init(p, threadIdx.x, p2_smem);  // shared-memory tables (twiddles are read from phase 0 on)
   if (K::EXTRA_ELEMS) __syncthreads();
-  if (STAGED) K::prefetch(p, (int)(s % gx), (int)(s / gx), 0, threadIdx.x, stage);
+  const TileOrder order{gx, zb_shift};
+  int bx, by;
+  order(s, bx, by);
+  if (STAGED) K::prefetch(p, bx, by, 0, threadIdx.x, stage);
   while (true) {
     if (STAGED) {
       fft::async_commit_wait_all();
       if (K::STAGE_SHARED) __syncthreads();
     }
-    const int bx = (int)(s % gx), by = (int)(s / gx);
+    order(s, bx, by);
     int64_t ns = s;
     int nit = it + 1;
     if (nit == niter) {
@@ -91,8 +107,12 @@ __global__ void __launch_bounds__(K::THREADS, MINB) p2_kernel(const typename K::
     const bool has_next = ns < ntile;
     K::template phase<0>(p, bx, by, it, threadIdx.x, p2_smem, stage);
     group_sync<K>();
-    if (STAGED && has_next) K::prefetch(p, (int)(ns % gx), (int)(ns / gx), nit, threadIdx.x, stage);
-    if (!STAGED && K::L2_PREFETCH && has_next) K::l2_prefetch(p, (int)(ns % gx), (int)(ns / gx), nit, threadIdx.x);
+    if (has_next) {
+      int nbx, nby;
+      order(ns, nbx, nby);
+      if (STAGED) K::prefetch(p, nbx, nby, nit, threadIdx.x, stage);
+      if (!STAGED && K::L2_PREFETCH) K::l2_prefetch(p, nbx, nby, nit, threadIdx.x);
+    }
     DevPhases<K, K::NPHASE - 1>::run(p, bx, by, it, p2_smem, stage);
     if (!has_next) break;
     group_sync<K>();
@@ -102,7 +122,7 @@ __global__ void __launch_bounds__(K::THREADS, MINB) p2_kernel(const typename K::
 }
 
 template <class K, int MINB, bool STAGED>
-int launch_variant(const typename K::Params& p, dim3 grid, const char* label, cudaStream_t st) {
+int launch_variant(const typename K::Params& p, dim3 grid, const char* label, cudaStream_t st, int zb_shift) {
   const size_t smem = sizeof(float2) * (K::SMEM_ELEMS + K::EXTRA_ELEMS + (STAGED ? K::STAGE_ELEMS : 0));
   static int ctas_per_sm = 0, num_sm = 0;  // per kernel instantiation
   if (!ctas_per_sm) {
@@ -120,7 +140,8 @@ int launch_variant(const typename K::Params& p, dim3 grid, const char* label, cu
   int64_t g = (int64_t)num_sm * ctas_per_sm;
   if (g > ntile) g = ntile;
   SOPHT_PROF(label, st);
-  p2_kernel<K, MINB, STAGED><<<(unsigned)g, K::THREADS, smem, st>>>(p, (int)grid.x, (int)grid.y);
+  while (zb_shift > 0 && (grid.y & ((1u << zb_shift) - 1))) --zb_shift;
+  p2_kernel<K, MINB, STAGED><<<(unsigned)g, K::THREADS, smem, st>>>(p, (int)grid.x, (int)grid.y, zb_shift);
   SOPHT_CHECK_LAUNCH();
   return SOPHT_OK;
 }
@@ -132,12 +153,12 @@ int env_int(const char* name, int dflt) {
 }
 
 template <class K>
-int launch(const typename K::Params& p, dim3 grid, const char* label, cudaStream_t st) {
+int launch(const typename K::Params& p, dim3 grid, const char* label, cudaStream_t st, int zb_shift = 0) {
   constexpr int AUTO = auto_min_ctas<K>();
   static const int minb = env_int("SOPHT_P2_MINB", 0);
   static const int stg = env_int("SOPHT_P2_STAGE", -1);
   if constexpr (!K::WANT_STAGE) {
-    return launch_variant<K, AUTO, false>(p, grid, label, st);
+    return launch_variant<K, AUTO, false>(p, grid, label, st, zb_shift);
   } else {
   // big radix-32 column kernels: 256 threads per CTA
   // measured defaults (512^3, L = 1024; profiles/): the y passes run best as two 128-register CTAs per SM
@@ -145,11 +166,11 @@ int launch(const typename K::Params& p, dim3 grid, const char* label, cudaStream
   const bool two = minb ? minb >= 2 : K::DEFAULT_TWO_CTAS;
   bool staged = stg >= 0 ? stg != 0 : K::DEFAULT_STAGED;
   if (two) {
-    if (staged && stage_fits<K>(AUTO)) return launch_variant<K, AUTO, true>(p, grid, label, st);
-    return launch_variant<K, AUTO, false>(p, grid, label, st);
+    if (staged && stage_fits<K>(AUTO)) return launch_variant<K, AUTO, true>(p, grid, label, st, zb_shift);
+    return launch_variant<K, AUTO, false>(p, grid, label, st, zb_shift);
   }
-  if (staged && stage_fits<K>(1)) return launch_variant<K, 1, true>(p, grid, label, st);
-  return launch_variant<K, 1, false>(p, grid, label, st);
+  if (staged && stage_fits<K>(1)) return launch_variant<K, 1, true>(p, grid, label, st, zb_shift);
+  return launch_variant<K, 1, false>(p, grid, label, st, zb_shift);
   }
 }
 
@@ -193,6 +214,12 @@ int launch_xinv(int L, const p2::XParams& p, int64_t rows, cudaStream_t st) {
 #undef M
   return SOPHT_OK;
 }
+// y inverse: 2^shift consecutive z planes of one kx tile run on neighbouring CTAs (TileOrder)
+int y_zb_shift() {
+  static const int v = env_int("SOPHT_P2_ZB_SHIFT", 3);
+  return v;
+}
+
 int launch_yfwd(int L, const p2::ColParams& p, dim3 grid, cudaStream_t st) {
 #define M(LL) return launch<p2::YFwd<LL, TX>>(p, grid, grid.y > 1 ? "poisson.y_fwd" : "poisson.y_fwd.nyquist", st);
   P2_SWITCH_L(L, M)
@@ -200,7 +227,8 @@ int launch_yfwd(int L, const p2::ColParams& p, dim3 grid, cudaStream_t st) {
   return SOPHT_OK;
 }
 int launch_yinv(int L, const p2::ColParams& p, dim3 grid, cudaStream_t st) {
-#define M(LL) return launch<p2::YInv<LL, TX>>(p, grid, grid.y > 1 ? "poisson.y_inv" : "poisson.y_inv.nyquist", st);
+#define M(LL) \
+  return launch<p2::YInv<LL, TX>>(p, grid, grid.y > 1 ? "poisson.y_inv" : "poisson.y_inv.nyquist", st, y_zb_shift());
   P2_SWITCH_L(L, M)
 #undef M
   return SOPHT_OK;
@@ -240,7 +268,7 @@ struct Pow2Poisson : PoissonImpl {
   double origin;
   float* ghat_natural = nullptr;  // (2nz, 2ny, nx+1), kept for sopht_poisson_green_hat
   float *gm = nullptr, *gn = nullptr;
-  float2 *A = nullptr, *nyqA = nullptr, *B = nullptr, *nyqB = nullptr;
+  float2 *A = nullptr, *nyqA = nullptr, *B = nullptr, *B2 = nullptr, *nyqB = nullptr;
   float2 *twx = nullptr, *twx2 = nullptr, *twy = nullptr, *twz = nullptr;
   PoissonImpl* generic = nullptr;  // built lazily for views this path cannot take (x-stride != 1, ...)
   // The kx = nx (Nyquist) plane's three small kernels form a dependency chain of latency-bound launches; they
@@ -259,6 +287,7 @@ struct Pow2Poisson : PoissonImpl {
     cudaFree(A);
     cudaFree(nyqA);
     cudaFree(B);
+    cudaFree(B2);
     cudaFree(nyqB);
     cudaFree(twx);
     cudaFree(twx2);
@@ -291,6 +320,7 @@ struct Pow2Poisson : PoissonImpl {
     SOPHT_CUDA(cudaMalloc(&A, sizeof(float2) * rows * nx));
     SOPHT_CUDA(cudaMalloc(&nyqA, sizeof(float2) * rows));
     SOPHT_CUDA(cudaMalloc(&B, sizeof(float2) * rows * 2 * nx));
+    SOPHT_CUDA(cudaMalloc(&B2, sizeof(float2) * rows * 2 * nx));
     SOPHT_CUDA(cudaMalloc(&nyqB, sizeof(float2) * rows * 2));
     if ((rc = upload_twiddles(&twx, nx, nx, st))) return rc;
     if ((rc = upload_twiddles(&twx2, nx, 2 * nx, st))) return rc;
@@ -345,9 +375,9 @@ struct Pow2Poisson : PoissonImpl {
     SOPHT_CUDA(cudaEventRecord(ev_join, side));
     if ((rc = launch_yfwd(LY, p2::slab_y_params(d, TX, A, B, true, twy), dim3(nx / TX, C * nz, 1), st)))
       return rc;
-    if ((rc = launch_zconv(LZ, p2::slab_z_params(d, TX, B, gm, nx, 0, twz), dim3(nx / TX, LY, 1), st)))
+    if ((rc = launch_zconv(LZ, p2::slab_z_params(d, TX, B, B2, gm, nx, 0, twz), dim3(nx / TX, LY, 1), st)))
       return rc;
-    if ((rc = launch_yinv(LY, p2::slab_y_params(d, TX, B, A, false, twy), dim3(nx / TX, C * nz, 1), st)))
+    if ((rc = launch_yinv(LY, p2::slab_y_params(d, TX, B2, A, false, twy), dim3(nx / TX, C * nz, 1), st)))
       return rc;
     SOPHT_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     xp = p2::slab_x_params(d, nullptr, reinterpret_cast<float*>(sol->data), vec ? sol->stride[0] : 0,
@@ -497,11 +527,12 @@ struct SlabPow2Poisson {
     if ((rc = launch_yfwd(LY, p2::nyquist_y_params(d, TX, nyq_all, nyq_work, true, twy),
                           dim3(d.C * d.nz / TX, 1, 1), st)))
       return rc;
-    if ((rc = launch_zconv(LZ, p2::slab_z_params(d, TX, work, gm, nxl, 0, twz), dim3(nxl / TX, LY, 1), st)))
+    float2* work2 = work + (int64_t)d.C * d.nz * LY * nxl;  // second half: the z pass's tile-major output
+    if ((rc = launch_zconv(LZ, p2::slab_z_params(d, TX, work, work2, gm, nxl, 0, twz), dim3(nxl / TX, LY, 1), st)))
       return rc;
     if ((rc = launch_zconv(LZ, p2::nyquist_z_params(d, TX, nyq_work, gn, twz), dim3(LY / TX, 1, 1), st)))
       return rc;
-    p2::ColParams yi = p2::slab_y_params(d, TX, work, recv, false, twy);
+    p2::ColParams yi = p2::slab_y_params(d, TX, work2, recv, false, twy);
     if (peer) yi = p2::slab_yinv_params_peer(yi, d, peer_send);
     if ((rc = launch_yinv(LY, yi, dim3(nxl / TX, d.C * d.nz, 1), st))) return rc;
     return launch_yinv(LY, p2::nyquist_y_params(d, TX, nyq_work, nyq_all, false, twy),

@@ -70,7 +70,10 @@ struct ColParams {
   const float2* in;
   float2* out;
   int64_t in_rs, in_cs, out_rs, out_cs;          // row / column strides (complex elements)
-  int64_t in_bx, in_by, out_bx, out_by;          // tile origin = base + bx*_bx + by*_by
+  // input tile origin = in + bx*in_bx + (by >> log2_bz)*in_bc + (by & (2^log2_bz - 1))*in_by, by = component*nz + z
+  // (two terms because the tile-major spectrum the y inverse reads is not linear in by); output: out + bx*out_bx + by*out_by
+  int64_t in_bx, in_by, in_bc, out_bx, out_by;
+  int log2_bz;
   const float2* tw;                              // forward twiddles, length L
   // Peer-memory output (slab-decomposed y inverse): plane by = c * nz + z of the kx-slab goes straight into the
   // exchange buffer of the rank that owns plane z - (C, P, nz/P, ny, nx/P) there, this rank's kx chunk - over
@@ -78,6 +81,9 @@ struct ColParams {
   int peer_mode, log2_nz, log2_nzl;
   int64_t peer_plane, peer_comp_stride, peer_self_offset;
   float2* out_peer[8];
+  FFT_HD const float2* in_plane(int by) const {
+    return in + (by >> log2_bz) * in_bc + (by & ((1 << log2_bz) - 1)) * in_by;
+  }
   FFT_HD float2* out_plane(int by) const {
     if (!peer_mode) return out + by * out_by;
     const int z = by & ((1 << log2_nz) - 1), c = by >> log2_nz;
@@ -167,14 +173,14 @@ struct YFwd {
   }
   FFT_HD static void prefetch(const Params& p, int bx, int by, int, int tid, float2* stage) {
     const int col = tid % TX, t = tid / TX;
-    StageCopy<TX> cp{stage + col, p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, (unsigned)p.in_rs};
+    StageCopy<TX> cp{stage + col, p.in_plane(by) + bx * p.in_bx + col * p.in_cs, (unsigned)p.in_rs};
     fft::fwd_first_elems<L>(t, cp);
   }
   // unstaged variants: the next tile's first-phase inputs are pulled into L2 while this tile is transformed
   static constexpr bool L2_PREFETCH = SOPHT_P2_L2_PREFETCH;
   FFT_HD static void l2_prefetch(const Params& p, int bx, int by, int, int tid) {
     const int col = tid % TX, t = tid / TX;
-    L2Prefetch pf{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, (unsigned)p.in_rs,
+    L2Prefetch pf{p.in_plane(by) + bx * p.in_bx + col * p.in_cs, (unsigned)p.in_rs,
                   (col & 3) == 0 && p.in_cs == 1};
     fft::fwd_first_elems<L>(t, pf);
   }
@@ -187,7 +193,7 @@ struct YFwd {
       if (stage) {
         fft::fwd_first<L>(StageLoad<TX>{stage + col}, sm, t, tw);
       } else {
-        GlobalLoad ld{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, (unsigned)p.in_rs};
+        GlobalLoad ld{p.in_plane(by) + bx * p.in_bx + col * p.in_cs, (unsigned)p.in_rs};
         fft::fwd_first<L>(ld, sm, t, tw);
       }
     } else if (P == NPHASE - 1) {
@@ -218,13 +224,13 @@ struct YInv {
   }
   FFT_HD static void prefetch(const Params& p, int bx, int by, int, int tid, float2* stage) {
     const int col = tid % TX, t = tid / TX;
-    StageCopy<TX> cp{stage + col, p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, (unsigned)p.in_rs};
+    StageCopy<TX> cp{stage + col, p.in_plane(by) + bx * p.in_bx + col * p.in_cs, (unsigned)p.in_rs};
     fft::inv_first_elems<L>(t, cp);
   }
   static constexpr bool L2_PREFETCH = SOPHT_P2_L2_PREFETCH;
   FFT_HD static void l2_prefetch(const Params& p, int bx, int by, int, int tid) {
     const int col = tid % TX, t = tid / TX;
-    L2Prefetch pf{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, (unsigned)p.in_rs,
+    L2Prefetch pf{p.in_plane(by) + bx * p.in_bx + col * p.in_cs, (unsigned)p.in_rs,
                   (col & 3) == 0 && p.in_cs == 1};
     fft::inv_first_elems<L>(t, pf);
   }
@@ -237,7 +243,7 @@ struct YInv {
       if (stage) {
         fft::inv_first<L>(StageSrcIdx<TX>{stage + col}, sm, t);
       } else {
-        GlobalSrcIdx src{p.in + bx * p.in_bx + by * p.in_by + col * p.in_cs, (unsigned)p.in_rs};
+        GlobalSrcIdx src{p.in_plane(by) + bx * p.in_bx + col * p.in_cs, (unsigned)p.in_rs};
         fft::inv_first<L>(src, sm, t);
       }
     } else if (P == NPHASE - 1) {
@@ -251,8 +257,10 @@ struct YInv {
 
 // ---- Z: forward, Green's function multiply, inverse — in place ----------------------------------------------
 struct ZParams {
-  float2* data;            // tile origin = data + bx*d_bx + by*d_by + c*d_c
+  float2* data;            // input tile origin = data + bx*d_bx + by*d_by + c*d_c, rows rs apart
   int64_t rs, cs, d_bx, d_by, d_c;
+  float2* out;             // output tile origin = out + bx*o_bx + by*o_by + c*o_c, rows o_rs apart (may be `data`)
+  int64_t o_rs, o_bx, o_by, o_c;
   int ncomp;
   const float* g;          // folded G_hat: g[fold(kz)*g_zs + goff]
   int64_t g_zs;
@@ -317,7 +325,7 @@ struct ZConv {
   FFT_HD static void phase(const Params& p, int bx, int by, int c, int tid, float2* smem, const float2* stage) {
     const int col = tid % TX, t = tid / TX;
     ColAcc<L, TX> sm{smem, col};
-    float2* base = p.data + bx * p.d_bx + by * p.d_by + c * p.d_c + col * p.cs;
+    const float2* base = p.data + bx * p.d_bx + by * p.d_by + c * p.d_c + col * p.cs;
     const float2* tw = smem + SMEM_ELEMS;
     float* gs = reinterpret_cast<float*>(smem + SMEM_ELEMS + TwTable<L>::SIZE);
     if (P == 0) {
@@ -335,7 +343,7 @@ struct ZConv {
     } else if (P == NP - 1) {
       fft::fwd_last_mul_inv_first<L>(sm, t, GreenTile<L, TX>{gs + col});
     } else if (P == NPHASE - 1) {
-      GlobalStore st{base, (unsigned)p.rs};
+      GlobalStore st{p.out + bx * p.o_bx + by * p.o_by + c * p.o_c + col * p.cs, (unsigned)p.o_rs};
       fft::inv_last<L>(sm, t, tw, st);
     } else if (P < NP - 1) {
       fft::fwd_mid<L>(sm, t, tw);
@@ -590,17 +598,30 @@ inline XParams slab_x_params_peer(XParams xp, const SlabDims& d, float2* const* 
   for (int q = 0; q < 8; ++q) xp.chunk[q] = q < d.P ? peer[q] : nullptr;
   return xp;
 }
-// y passes on this rank's kx-slab: a = (C, nz, ny, nxl), b = (C, nz, 2ny, nxl); grid (nxl / TX, C * nz)
+// Two layouts of the doubled-in-y spectrum between the y and z passes:
+//   B  (x-major, written by the y forward pass, read by the z pass):  (C, nz, 2ny, nxl)
+//   B2 ("kx-tile-major", written by the z pass, read by the y inverse): element (c, z, ky, kx) at
+//       ((((c * (nxl/TX) + kx/TX) * 2ny + ky) * nz + z) * TX + kx % TX
+// In B2 the nz x TX tile a z-pass CTA produces is one contiguous block, written as a stream instead of nz rows
+// 2ny * nxl * 8 bytes apart; the y inverse reads its 2ny rows nz * TX * 8 bytes apart with adjacent z planes next to
+// each other (its L2 prefetch hides that stride). The y forward pass keeps writing the x-major B: its 64-byte
+// stores lose more in the tile-major layout than the z pass gains (profiles/r01_poisson_layout_experiments.txt).
+// y passes on this rank's kx-slab: a = (C, nz, ny, nxl); forward a -> B, inverse B2 -> a; grid (nxl / TX, C * nz)
 inline ColParams slab_y_params(const SlabDims& d, int TX, const float2* in, float2* out, bool forward,
                                const float2* tw) {
   const int64_t nxl = d.nxl(), LY = 2 * d.ny;
   ColParams yp{};
   yp.in = in;
   yp.out = out;
-  yp.in_rs = nxl, yp.in_cs = 1, yp.out_rs = nxl, yp.out_cs = 1;
-  yp.in_bx = TX, yp.out_bx = TX;
-  yp.in_by = (forward ? d.ny : LY) * nxl;
-  yp.out_by = (forward ? LY : d.ny) * nxl;
+  yp.in_cs = 1, yp.out_cs = 1;
+  yp.log2_bz = ilog2(d.nz);
+  if (forward) {
+    yp.in_rs = nxl, yp.in_bx = TX, yp.in_by = (int64_t)d.ny * nxl, yp.in_bc = (int64_t)d.nz * d.ny * nxl;
+    yp.out_rs = nxl, yp.out_bx = TX, yp.out_by = LY * nxl;
+  } else {
+    yp.in_rs = (int64_t)d.nz * TX, yp.in_bx = LY * d.nz * TX, yp.in_by = TX, yp.in_bc = LY * d.nz * nxl;
+    yp.out_rs = nxl, yp.out_bx = TX, yp.out_by = (int64_t)d.ny * nxl;
+  }
   yp.tw = tw;
   return yp;
 }
@@ -625,19 +646,21 @@ inline ColParams nyquist_y_params(const SlabDims& d, int TX, const float2* in, f
   yn.in_rs = 1, yn.out_rs = 1;
   yn.in_cs = forward ? d.ny : LY;
   yn.out_cs = forward ? LY : d.ny;
-  yn.in_bx = TX * yn.in_cs, yn.in_by = 0, yn.out_bx = TX * yn.out_cs, yn.out_by = 0;
+  yn.in_bx = TX * yn.in_cs, yn.out_bx = TX * yn.out_cs;  // by = 0: no plane offsets
   yn.tw = tw;
   return yn;
 }
-// z pass on the kx-slab b = (C, nz, 2ny, nxl); gm is the folded G_hat stored as (nz+1, ny+1, g_row) whose
-// column g_kx0 is this rank's first kx bin (whole spectrum: g_row = nx, g_kx0 = rank * nxl; a per-rank slice:
-// g_row = nxl, g_kx0 = 0); grid (nxl / TX, 2ny)
-inline ZParams slab_z_params(const SlabDims& d, int TX, float2* b, const float* gm, int g_row, int g_kx0,
-                             const float2* tw) {
+// z pass on the kx-slab: reads the x-major b = (C, nz, 2ny, nxl), writes the kx-tile-major b2 (C, nxl/TX, 2ny, nz, TX);
+// gm is the folded G_hat stored as (nz+1, ny+1, g_row) whose column g_kx0 is this rank's first kx bin (whole
+// spectrum: g_row = nx, g_kx0 = rank * nxl; a per-rank slice: g_row = nxl, g_kx0 = 0); grid (nxl / TX, 2ny)
+inline ZParams slab_z_params(const SlabDims& d, int TX, float2* b, float2* b2, const float* gm, int g_row,
+                             int g_kx0, const float2* tw) {
   const int64_t nxl = d.nxl(), LY = 2 * d.ny;
   ZParams zp{};
   zp.data = b;
   zp.rs = LY * nxl, zp.cs = 1, zp.d_bx = TX, zp.d_by = nxl, zp.d_c = (int64_t)d.nz * LY * nxl;
+  zp.out = b2;
+  zp.o_rs = TX, zp.o_by = (int64_t)d.nz * TX, zp.o_bx = LY * zp.o_by, zp.o_c = LY * d.nz * nxl;
   zp.ncomp = d.C;
   zp.g = gm + g_kx0;
   zp.g_zs = (int64_t)(d.ny + 1) * g_row;
@@ -653,6 +676,7 @@ inline ZParams nyquist_z_params(const SlabDims& d, int TX, float2* b, const floa
   ZParams zn{};
   zn.data = b;
   zn.rs = LY, zn.cs = 1, zn.d_bx = TX, zn.d_by = 0, zn.d_c = (int64_t)d.nz * LY;
+  zn.out = b, zn.o_rs = zn.rs, zn.o_bx = zn.d_bx, zn.o_by = 0, zn.o_c = zn.d_c;  // in place
   zn.ncomp = d.C;
   zn.g = gn;
   zn.g_zs = d.ny + 1;

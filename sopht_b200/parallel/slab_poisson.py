@@ -129,7 +129,8 @@ class SlabUnboundedPoissonSolver3D:
         self.path = "pow2-slab"
         self.plan = SlabTransposePlan(self.part, n_components, torch.float32, device, group)
         nz, ny = grid_size_z, grid_size_y
-        self._work = torch.zeros((n_components, nz, 2 * ny, self.plan.nxl, 2), dtype=torch.float32, device=device)
+        # two halves: the x-major spectrum the y forward pass writes, the kx-tile-major one the z pass writes
+        self._work = torch.zeros((2, n_components, nz, 2 * ny, self.plan.nxl, 2), dtype=torch.float32, device=device)
         self._nyq_work = torch.zeros((n_components, nz, 2 * ny, 2), dtype=torch.float32, device=device)
         # transposes fused into the kernels over NVLink peer memory (default on >1 rank; SOPHT_SLAB_PEER=0 or
         # peer_exchange=False keeps the NCCL all-to-all path)

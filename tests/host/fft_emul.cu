@@ -131,7 +131,7 @@ int run_case() {
   const size_t slab = (size_t)C * NZL * NY * NX;  // = C * P * NZL * NY * NXL = C * NZ * NY * NXL
   std::vector<std::vector<float2>> send(P, std::vector<float2>(slab, poison)),
       recv(P, std::vector<float2>(slab, poison)), nyq_local(P, std::vector<float2>((size_t)C * NZL * NY, poison));
-  std::vector<float2> work((size_t)C * NZ * LY * NXL), nyq_all((size_t)C * NZ * NY), nyq_work((size_t)C * NZ * LY);
+  std::vector<float2> work((size_t)C * NZ * LY * NXL), work2((size_t)C * NZ * LY * NXL), nyq_all((size_t)C * NZ * NY), nyq_work((size_t)C * NZ * LY);
 
   // 1. x forward on every rank's z-slab
   for (int r = 0; r < P; ++r) {
@@ -163,10 +163,11 @@ int run_case() {
   for (int r = 0; r < P; ++r) {
     p2::SlabDims d{C, NZ, NY, NX, P, r};
     for (auto& v : work) v = poison;
+    for (auto& v : work2) v = poison;
     emulate<p2::YFwd<LY, TX>>(p2::slab_y_params(d, TX, recv[r].data(), work.data(), true, twy.data()), NXL / TX,
                               C * NZ, 1);
-    emulate<p2::ZConv<LZ, TX>>(p2::slab_z_params(d, TX, work.data(), gmain.data(), NX, r * NXL, twz.data()), NXL / TX, LY, C);
-    auto yi = p2::slab_y_params(d, TX, work.data(), recv[r].data(), false, twy.data());
+    emulate<p2::ZConv<LZ, TX>>(p2::slab_z_params(d, TX, work.data(), work2.data(), gmain.data(), NX, r * NXL, twz.data()), NXL / TX, LY, C);
+    auto yi = p2::slab_y_params(d, TX, work2.data(), recv[r].data(), false, twy.data());
     if (PEER) {  // output planes go straight into the owning rank's send buffer
       float2* peers[8] = {};
       for (int q = 0; q < P; ++q) peers[q] = send[q].data();

@@ -72,7 +72,7 @@ struct ColParams {
   int64_t in_rs, in_cs, out_rs, out_cs;          // row / column strides (complex elements)
   // input tile origin = in + bx*in_bx + (by >> log2_bz)*in_bc + (by & (2^log2_bz - 1))*in_by, by = component*nz + z
   // (two terms because the tile-major spectrum the y inverse reads is not linear in by); output: out + bx*out_bx + by*out_by
-  int64_t in_bx, in_by, in_bc, out_bx, out_by;
+  int64_t in_bx, in_by, in_bc, out_bx, out_by, out_bc;
   int log2_bz;
   const float2* tw;                              // forward twiddles, length L
   // Peer-memory output (slab-decomposed y inverse): plane by = c * nz + z of the kx-slab goes straight into the
@@ -85,7 +85,7 @@ struct ColParams {
     return in + (by >> log2_bz) * in_bc + (by & ((1 << log2_bz) - 1)) * in_by;
   }
   FFT_HD float2* out_plane(int by) const {
-    if (!peer_mode) return out + by * out_by;
+    if (!peer_mode) return out + (by >> log2_bz) * out_bc + (by & ((1 << log2_bz) - 1)) * out_by;
     const int z = by & ((1 << log2_nz) - 1), c = by >> log2_nz;
     return out_peer[z >> log2_nzl] + c * peer_comp_stride + peer_self_offset +
            (int64_t)(z & ((1 << log2_nzl) - 1)) * peer_plane;
@@ -197,7 +197,7 @@ struct YFwd {
         fft::fwd_first<L>(ld, sm, t, tw);
       }
     } else if (P == NPHASE - 1) {
-      GlobalStoreIdx st{p.out + bx * p.out_bx + by * p.out_by + col * p.out_cs, (unsigned)p.out_rs};
+      GlobalStoreIdx st{p.out_plane(by) + bx * p.out_bx + col * p.out_cs, (unsigned)p.out_rs};
       fft::fwd_last<L>(sm, t, st);
     } else {
       fft::fwd_mid<L>(sm, t, tw);
@@ -617,10 +617,10 @@ inline ColParams slab_y_params(const SlabDims& d, int TX, const float2* in, floa
   yp.log2_bz = ilog2(d.nz);
   if (forward) {
     yp.in_rs = nxl, yp.in_bx = TX, yp.in_by = (int64_t)d.ny * nxl, yp.in_bc = (int64_t)d.nz * d.ny * nxl;
-    yp.out_rs = nxl, yp.out_bx = TX, yp.out_by = LY * nxl;
+    yp.out_rs = nxl, yp.out_bx = TX, yp.out_by = LY * nxl, yp.out_bc = (int64_t)d.nz * LY * nxl;
   } else {
     yp.in_rs = (int64_t)d.nz * TX, yp.in_bx = LY * d.nz * TX, yp.in_by = TX, yp.in_bc = LY * d.nz * nxl;
-    yp.out_rs = nxl, yp.out_bx = TX, yp.out_by = (int64_t)d.ny * nxl;
+    yp.out_rs = nxl, yp.out_bx = TX, yp.out_by = (int64_t)d.ny * nxl, yp.out_bc = (int64_t)d.nz * d.ny * nxl;
   }
   yp.tw = tw;
   return yp;

@@ -273,7 +273,7 @@ struct Pow2Poisson : PoissonImpl {
   PoissonImpl* generic = nullptr;  // built lazily for views this path cannot take (x-stride != 1, ...)
   // The kx = nx (Nyquist) plane's three small kernels form a dependency chain of latency-bound launches; they
   // run on a side stream, forked after the x forward pass and joined before the x inverse, and fill the tails
-  // of the main y / z kernels.
+  // of the main y / z kernels (grids up to 2^25 cells; larger grids keep them on the main stream).
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
@@ -365,21 +365,28 @@ struct Pow2Poisson : PoissonImpl {
                                        vec ? rhs->stride[0] : 0, rhs->stride[o], rhs->stride[o + 1], A, nyqA,
                                        twx, twx2);
     if ((rc = launch_xfwd(nx, xp, rows, st))) return rc;
-    SOPHT_CUDA(cudaEventRecord(ev_fork, st));
-    SOPHT_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    // measured: -3 % per step at 128x128x256, -1.6 % at 256^3, but +4 % at 512^3 (the small high-priority kernels
+    // disturb the persistent main kernels more than their own latency is worth there)
+    static const int side_env = env_int("SOPHT_P2_SIDE_STREAM", -1);
+    const bool use_side = side_env >= 0 ? side_env != 0 : (int64_t)nz * ny * nx <= ((int64_t)1 << 25);
+    cudaStream_t side = use_side ? this->side : st;
+    if (use_side) {
+      SOPHT_CUDA(cudaEventRecord(ev_fork, st));
+      SOPHT_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+    }
     if ((rc = launch_yfwd(LY, p2::nyquist_y_params(d, TX, nyqA, nyqB, true, twy), dim3(C * nz / TX, 1, 1), side)))
       return rc;
     if ((rc = launch_zconv(LZ, p2::nyquist_z_params(d, TX, nyqB, gn, twz), dim3(LY / TX, 1, 1), side))) return rc;
     if ((rc = launch_yinv(LY, p2::nyquist_y_params(d, TX, nyqB, nyqA, false, twy), dim3(C * nz / TX, 1, 1), side)))
       return rc;
-    SOPHT_CUDA(cudaEventRecord(ev_join, side));
+    if (use_side) SOPHT_CUDA(cudaEventRecord(ev_join, side));
     if ((rc = launch_yfwd(LY, p2::slab_y_params(d, TX, A, B, true, twy), dim3(nx / TX, C * nz, 1), st)))
       return rc;
     if ((rc = launch_zconv(LZ, p2::slab_z_params(d, TX, B, B2, gm, nx, 0, twz), dim3(nx / TX, LY, 1), st)))
       return rc;
     if ((rc = launch_yinv(LY, p2::slab_y_params(d, TX, B2, A, false, twy), dim3(nx / TX, C * nz, 1), st)))
       return rc;
-    SOPHT_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+    if (use_side) SOPHT_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     xp = p2::slab_x_params(d, nullptr, reinterpret_cast<float*>(sol->data), vec ? sol->stride[0] : 0,
                            sol->stride[o], sol->stride[o + 1], A, nyqA, twx, twx2);
     return launch_xinv(nx, xp, rows, st);

@@ -265,8 +265,25 @@ def torch_complex_dtype(real_t: Any) -> torch.dtype:
     return _TORCH_COMPLEX[dtype_code(real_t)]
 
 
+# descriptors of recently seen views (a simulator hands the same few tensors over every step); read-only by contract
+_DESC_CACHE: dict[tuple, SophtField] = {}
+
+
 def field_desc(t: torch.Tensor, dt: int, *, is_complex: bool = False) -> SophtField:
     """Describe a CUDA tensor view for the C ABI (strides in elements of its own dtype)."""
+    try:
+        key = (t.data_ptr(), t.shape, t.stride(), t.dtype, dt, is_complex)
+        return _DESC_CACHE[key]
+    except (KeyError, AttributeError):
+        pass
+    f = _field_desc_uncached(t, dt, is_complex)
+    if len(_DESC_CACHE) > 4096:
+        _DESC_CACHE.clear()
+    _DESC_CACHE[key] = f
+    return f
+
+
+def _field_desc_uncached(t: torch.Tensor, dt: int, is_complex: bool) -> SophtField:
     if not isinstance(t, torch.Tensor):
         msg = f"expected a torch.Tensor, got {type(t).__name__}"
         raise TypeError(msg)
@@ -309,7 +326,13 @@ def raw_desc(t: torch.Tensor) -> SophtField:
     return f
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def current_stream() -> ctypes.c_void_p:
+    """torch's current CUDA stream on the current device as a cudaStream_t."""
+    if _raw_stream is not None:  # one C call instead of building a torch.cuda.Stream object
+        return ctypes.c_void_p(_raw_stream(torch.cuda.current_device()))
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 

@@ -330,8 +330,9 @@ int sopht_poisson_slab_inverse_x(sopht_poisson_slab_t handle, const sopht_field_
  * enable_peer_exchange() returns their CUDA IPC handles (2 x 64 bytes: recv, send), the host layer all-gathers
  * the handles of all ranks (nranks x 128 bytes, rank order) and hands them to open_peers(). Afterwards the phase
  * functions take NULL for send_buffer / recv_buffer: x forward then stores every kx chunk straight into the
- * owning rank's buffer, y inverse stores every plane into the buffer of the rank that owns it, and no
- * all-to-all is issued - the host layer only separates the phases with a collective barrier. */
+ * owning rank's buffer (push), y inverse leaves its kx-slab in this rank's second buffer and x inverse reads
+ * chunk q of every spectrum row from rank q's buffer (pull), and no all-to-all is issued - the host layer only
+ * separates the phases with a barrier. */
 int sopht_poisson_slab_enable_peer_exchange(sopht_poisson_slab_t handle, unsigned char *ipc_handles_out);
 int sopht_poisson_slab_open_peers(sopht_poisson_slab_t handle, const unsigned char *all_ipc_handles);
 int sopht_poisson_slab_destroy(sopht_poisson_slab_t handle);

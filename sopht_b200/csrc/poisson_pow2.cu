@@ -204,11 +204,17 @@ int launch_xfwd(int L, const p2::XParams& p, int64_t rows, cudaStream_t st) {
 #undef M
   return SOPHT_OK;
 }
+// With a peer spectrum (slab solve, pull transpose) the next tile's rows are staged with cp.async while the current
+// tile is transformed, so the NVLink reads overlap the butterflies instead of preceding them.
 int launch_xinv(int L, const p2::XParams& p, int64_t rows, cudaStream_t st) {
 #define M(LL)                                                                         \
   {                                                                                   \
     constexpr int RX = rows_per_cta<LL>();                                            \
-    return launch<p2::XInv<LL, RX>>(p, dim3((unsigned)(rows / RX), 1, 1), "poisson.x_inv", st);     \
+    using K = p2::XInv<LL, RX>;                                                       \
+    const dim3 grid((unsigned)(rows / RX), 1, 1);                                     \
+    if (p.peer_read && stage_fits<K>(1))                                              \
+      return launch_variant<K, auto_min_ctas<K>(), true>(p, grid, "poisson.x_inv", st, 0); \
+    return launch<K>(p, grid, "poisson.x_inv", st);                                   \
   }
   P2_SWITCH_L(L, M)
 #undef M
@@ -521,8 +527,8 @@ struct SlabPow2Poisson {
     return launch_xfwd(d.nx, xp, (int64_t)d.C * d.nzl() * d.ny, st);
   }
 
-  // recv == nullptr: read this rank's own exchange buffer (filled by the peers) and let the y inverse write its
-  // planes straight into the peers' buffers
+  // recv == nullptr: read this rank's own exchange buffer (filled by the peers' x forward kernels) and leave the y
+  // inverse's kx-slab (C, nz, ny, nxl) in this rank's second buffer, from where the peers' x inverse kernels pull it
   int yz(float2* recv, float2* nyq_all, float2* work, float2* nyq_work, cudaStream_t st) const {
     const int LY = 2 * d.ny, LZ = 2 * d.nz, nxl = d.nxl();
     const bool peer = recv == nullptr;
@@ -539,8 +545,7 @@ struct SlabPow2Poisson {
       return rc;
     if ((rc = launch_zconv(LZ, p2::nyquist_z_params(d, TX, nyq_work, gn, twz), dim3(LY / TX, 1, 1), st)))
       return rc;
-    p2::ColParams yi = p2::slab_y_params(d, TX, work2, recv, false, twy);
-    if (peer) yi = p2::slab_yinv_params_peer(yi, d, peer_send);
+    const p2::ColParams yi = p2::slab_y_params(d, TX, work2, peer ? xsend : recv, false, twy);
     if ((rc = launch_yinv(LY, yi, dim3(nxl / TX, d.C * d.nz, 1), st))) return rc;
     return launch_yinv(LY, p2::nyquist_y_params(d, TX, nyq_work, nyq_all, false, twy),
                        dim3(d.C * d.nz / TX, 1, 1), st);
@@ -550,9 +555,11 @@ struct SlabPow2Poisson {
     int rc = check_local(__func__, sol);
     if (rc) return rc;
     if (!recv2 && !peers_open) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: peer exchange is not open", __func__);
-    if (!recv2) recv2 = xsend;
-    const p2::XParams xp = p2::slab_x_params(d, nullptr, reinterpret_cast<float*>(sol->data), sol->stride[0],
-                                             sol->stride[1], sol->stride[2], recv2, nyq_local, twx, twx2);
+    const bool pull = recv2 == nullptr;  // chunk q of every spectrum row is read from rank q's buffer over NVLink
+    if (pull) recv2 = xsend;
+    p2::XParams xp = p2::slab_x_params(d, nullptr, reinterpret_cast<float*>(sol->data), sol->stride[0],
+                                       sol->stride[1], sol->stride[2], recv2, nyq_local, twx, twx2);
+    if (pull) xp = p2::slab_x_params_peer(xp, d, peer_send);
     return launch_xinv(d.nx, xp, (int64_t)d.C * d.nzl() * d.ny, st);
   }
 };

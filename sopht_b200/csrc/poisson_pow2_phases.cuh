@@ -75,20 +75,11 @@ struct ColParams {
   int64_t in_bx, in_by, in_bc, out_bx, out_by, out_bc;
   int log2_bz;
   const float2* tw;                              // forward twiddles, length L
-  // Peer-memory output (slab-decomposed y inverse): plane by = c * nz + z of the kx-slab goes straight into the
-  // exchange buffer of the rank that owns plane z - (C, P, nz/P, ny, nx/P) there, this rank's kx chunk - over
-  // NVLink, so the reverse transpose is part of this kernel. peer_mode == 0: plain `out + by * out_by`.
-  int peer_mode, log2_nz, log2_nzl;
-  int64_t peer_plane, peer_comp_stride, peer_self_offset;
-  float2* out_peer[8];
   FFT_HD const float2* in_plane(int by) const {
     return in + (by >> log2_bz) * in_bc + (by & ((1 << log2_bz) - 1)) * in_by;
   }
   FFT_HD float2* out_plane(int by) const {
-    if (!peer_mode) return out + (by >> log2_bz) * out_bc + (by & ((1 << log2_bz) - 1)) * out_by;
-    const int z = by & ((1 << log2_nz) - 1), c = by >> log2_nz;
-    return out_peer[z >> log2_nzl] + c * peer_comp_stride + peer_self_offset +
-           (int64_t)(z & ((1 << log2_nzl) - 1)) * peer_plane;
+    return out + (by >> log2_bz) * out_bc + (by & ((1 << log2_bz) - 1)) * out_by;
   }
 };
 
@@ -384,6 +375,11 @@ struct XParams {
   FFT_HD float2* out_bin(int64_t row_base_, int k) const {
     return chunk[k >> chunk_shift] + row_base_ + self_offset + (k & ((1 << chunk_shift) - 1));
   }
+  // XInv reads through the same table: with peers, chunk[q] is the buffer rank q's y inverse left its kx-slab in
+  // and self_offset this rank's z range in it, so the reverse transpose is a PULL of whole row chunks over NVLink
+  // (nx / P contiguous bins per request; the y inverse's 64-byte segments would make poor NVLink stores).
+  FFT_HD const float2* in_bin(int64_t row_base_, int k) const { return out_bin(row_base_, k); }
+  int peer_read;  // chunk[] are peer mappings: no L2 prefetch (peer lines are not cached in the local L2)
 };
 
 template <int L>
@@ -502,18 +498,19 @@ struct XInv {
   FFT_HD static void prefetch(const Params& p, int bx, int, int, int tid, float2* stage) {
     const int t = tid % T, r = tid / T;
     const int64_t row = (int64_t)bx * RX + r;
-    const float2* in = p.spec + p.row_base(row);
+    const int64_t rb = p.row_base(row);
     float2* s = stage + r * (L + 1);
 #pragma unroll
-    for (int q = 0; q < Cfg<L>::E; ++q) fft::async_copy8(s + t + q * T, in + p.bin(t + q * T));
+    for (int q = 0; q < Cfg<L>::E; ++q) fft::async_copy8(s + t + q * T, p.in_bin(rb, t + q * T));
     if (t == 0) fft::async_copy8(s + L, p.nyq + row);
   }
   // next tile's spectrum rows (L float2 = L / 4 sectors per row; chunks are multiples of a sector)
   static constexpr bool L2_PREFETCH = SOPHT_P2_L2_PREFETCH;
   FFT_HD static void l2_prefetch(const Params& p, int bx, int, int, int tid) {
     const int t = tid % T, r = tid / T;
-    const float2* in = p.spec + p.row_base((int64_t)bx * RX + r);
-    for (int s = t; s < L / 4; s += T) fft::prefetch_l2(in + p.bin(s * 4));
+    if (p.peer_read) return;
+    const int64_t rb = p.row_base((int64_t)bx * RX + r);
+    for (int s = t; s < L / 4; s += T) fft::prefetch_l2(p.in_bin(rb, s * 4));
   }
   template <int P>
   FFT_HD static void phase(const Params& p, int bx, int, int, int tid, float2* smem, const float2* stage) {
@@ -528,22 +525,24 @@ struct XInv {
       const float2* nq = stage ? stage + r * (L + 1) + L : p.nyq + row;
       // one chunk (single GPU) or a staged row: bin k is element k, no chunk arithmetic per access
       const bool plain = stage != nullptr || (1 << p.chunk_shift) >= L;
-      auto combine = [&](auto bin) {
+      auto combine = [&](auto load) {
 #pragma unroll
         for (int q = 0; q < Cfg<L>::E; ++q) {
           const int k = t + q * T;
-          const float2 a = in[bin(k)];
-          const float2 b = k == 0 ? *nq : in[bin(L - k)];
+          const float2 a = load(k);
+          const float2 b = k == 0 ? *nq : load(L - k);
           const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
           const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
           const float2 o = fft::cmul_conj(d, tw2[k]);
           sm(fft::spectrum_position<L>(k)) = make_float2(e.x - o.y, e.y + o.x);
         }
       };
-      if (plain)
-        combine([](int k) { return (int64_t)k; });
-      else
-        combine([&](int k) { return p.bin(k); });
+      if (plain) {
+        combine([&](int k) { return in[k]; });
+      } else {  // chunked (possibly peer) spectrum: through the chunk table
+        const int64_t rb = p.row_base(row);
+        combine([&](int k) { return *p.in_bin(rb, k); });
+      }
     } else if (P == 1) {
       fft::inv_first<L>(InPlaceSrc<L>{sm}, sm, t);
     } else if (P == NPHASE - 1) {
@@ -592,9 +591,11 @@ inline XParams slab_x_params(const SlabDims& d, const float* real_in, float* rea
   for (int q = 0; q < 8; ++q) xp.chunk[q] = q < d.P ? spec + q * xp.chunk_stride : nullptr;
   return xp;
 }
-// the same with the spectrum chunks written into the peers' exchange buffers (peer[q]: base of rank q's buffer)
+// the same with the spectrum chunks addressed in the peers' exchange buffers (peer[q]: base of rank q's buffer):
+// x forward WRITES chunk q into rank q's buffer, x inverse READS chunk q from rank q's buffer
 inline XParams slab_x_params_peer(XParams xp, const SlabDims& d, float2* const* peer) {
   xp.self_offset = (int64_t)d.rank * xp.chunk_stride;
+  xp.peer_read = 1;
   for (int q = 0; q < 8; ++q) xp.chunk[q] = q < d.P ? peer[q] : nullptr;
   return xp;
 }
@@ -623,17 +624,6 @@ inline ColParams slab_y_params(const SlabDims& d, int TX, const float2* in, floa
     yp.out_rs = nxl, yp.out_bx = TX, yp.out_by = (int64_t)d.ny * nxl, yp.out_bc = (int64_t)d.nz * d.ny * nxl;
   }
   yp.tw = tw;
-  return yp;
-}
-// y inverse whose output planes go into the peers' exchange buffers (peer[s]: base of rank s's buffer)
-inline ColParams slab_yinv_params_peer(ColParams yp, const SlabDims& d, float2* const* peer) {
-  yp.peer_mode = 1;
-  yp.log2_nz = ilog2(d.nz);
-  yp.log2_nzl = ilog2(d.nzl());
-  yp.peer_plane = (int64_t)d.ny * d.nxl();
-  yp.peer_comp_stride = yp.peer_plane * d.nzl() * d.P;
-  yp.peer_self_offset = yp.peer_plane * d.nzl() * d.rank;
-  for (int q = 0; q < 8; ++q) yp.out_peer[q] = q < d.P ? peer[q] : nullptr;
   return yp;
 }
 // Nyquist plane (C, nz, ny) <-> (C, nz, 2ny): columns are the (c, z) index; grid (C * nz / TX, 1)

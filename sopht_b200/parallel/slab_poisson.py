@@ -189,7 +189,8 @@ class SlabUnboundedPoissonSolver3D:
         if not self.peer_exchange:
             plan.solve(forward_x, middle, inverse_x)
             return
-        # peer-memory path: the kernels themselves move the spectrum over NVLink; collectives only order the phases
+        # peer-memory path: the kernels themselves move the spectrum over NVLink (x forward pushes its chunks into the
+        # owners' buffers, x inverse pulls its chunks from the y-inverse outputs); collectives only order the phases
         part, nzl = self.part, plan.nzl
         _lib.check(lib.sopht_poisson_slab_forward_x(
             self._handle, ctypes.byref(fr), None, p(plan.nyq_local.data_ptr()), st))

@@ -167,12 +167,8 @@ int run_case() {
     emulate<p2::YFwd<LY, TX>>(p2::slab_y_params(d, TX, recv[r].data(), work.data(), true, twy.data()), NXL / TX,
                               C * NZ, 1);
     emulate<p2::ZConv<LZ, TX>>(p2::slab_z_params(d, TX, work.data(), work2.data(), gmain.data(), NX, r * NXL, twz.data()), NXL / TX, LY, C);
-    auto yi = p2::slab_y_params(d, TX, work2.data(), recv[r].data(), false, twy.data());
-    if (PEER) {  // output planes go straight into the owning rank's send buffer
-      float2* peers[8] = {};
-      for (int q = 0; q < P; ++q) peers[q] = send[q].data();
-      yi = p2::slab_yinv_params_peer(yi, d, peers);
-    }
+    // PEER: the kx-slab stays in this rank's send buffer, from where the x inverse of every rank pulls its chunk
+    auto yi = p2::slab_y_params(d, TX, work2.data(), PEER ? send[r].data() : recv[r].data(), false, twy.data());
     emulate<p2::YInv<LY, TX>>(yi, NXL / TX, C * NZ, 1);
   }
   {  // Nyquist plane (every rank would do this redundantly)
@@ -202,6 +198,11 @@ int run_case() {
     p2::SlabDims d{C, NZ, NY, NX, P, r};
     auto xp = p2::slab_x_params(d, nullptr, sol.data() + (size_t)r * NZL * NY * NX, (int64_t)ncell,
                                 (int64_t)NY * NX, NX, send[r].data(), nyq_local[r].data(), twx.data(), twx2.data());
+    if (PEER) {  // chunk q of a row is read from rank q's send buffer ("peer memory")
+      float2* peers[8] = {};
+      for (int q = 0; q < P; ++q) peers[q] = send[q].data();
+      xp = p2::slab_x_params_peer(xp, d, peers);
+    }
     emulate<p2::XInv<LX, RX>>(xp, (int)((size_t)C * NZL * NY / RX), 1, 1);
   }
 
@@ -234,7 +235,7 @@ int run_case() {
         }
   }
   const double rel = sqrt(err2 / ref2);
-  printf("grid (%d,%d,%d) ranks %d%s: LX=%d LY=%d LZ=%d rel L2 err = %.3e %s\n", NZ, NY, NX, P, PEER ? " (peer writes)" : "", LX, LY, LZ, rel,
+  printf("grid (%d,%d,%d) ranks %d%s: LX=%d LY=%d LZ=%d rel L2 err = %.3e %s\n", NZ, NY, NX, P, PEER ? " (peer push / pull)" : "", LX, LY, LZ, rel,
          rel < 2e-6 ? "ok" : "FAIL");
   return rel < 2e-6 ? 0 : 1;
 }
@@ -254,7 +255,7 @@ int main(int argc, char** argv) {
   bad += run_case<128, 8, 16>();   // 256 (z)
   bad += run_case<16, 8, 32, 2>();    // z-slab decomposition over 2 ranks
   bad += run_case<8, 16, 64, 4>();    // ... over 4 ranks
-  bad += run_case<16, 8, 32, 2, true>();   // transposes fused into the x forward / y inverse kernels (peer writes)
+  bad += run_case<16, 8, 32, 2, true>();   // transposes fused into the x forward / y inverse kernels (peer push / pull)
   bad += run_case<8, 16, 64, 4, true>();
   if (full) {                      // minutes on one core: every remaining decomposition, incl. three-pass 2048
     bad += run_case<64, 128, 256>();

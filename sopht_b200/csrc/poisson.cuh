@@ -22,6 +22,12 @@ template <typename T>
 int build_green_hat(T** g_out, int dim, int nz, int ny, int nx, double dx, const double* mz_h,
                     const double* my_h, const double* mx_h, double origin_value, cudaStream_t st);
 
+// fp32, 3-D: the folded spectrum (nz+1, ny+1, nxl) of the kx range [kx0, kx0 + nxl) and the kx = nx plane
+// (nz+1, ny+1), both x2 like fold_green_kernel's, built plane batch by plane batch (poisson_generic.cu)
+int build_green_folded_slice(float* gm, float* gn, int nz, int ny, int nx, int kx0, int nxl, double dx,
+                             const double* mz_h, const double* my_h, const double* mx_h, double origin_value,
+                             cudaStream_t st);
+
 // fp32, 3-D, power-of-two grids: pruned + fused shared-memory FFT pipeline (poisson_pow2.cu)
 bool pow2_poisson_eligible(int dtype, int dim, int nz, int ny, int nx);
 PoissonImpl* make_pow2_poisson(int nz, int ny, int nx, double dx, const double* mz, const double* my,

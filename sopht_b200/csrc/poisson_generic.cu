@@ -228,6 +228,147 @@ int build_green_hat(T** g_out, int dim, int nz, int ny, int nx, double dx, const
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// Folded G_hat of ONE rank's kx range, built without ever holding the doubled domain (z-slab decomposed solve:
+// at 1024^3 the full double-precision transform above needs 137 GB, this one ~9 GB per rank):
+//   x: planes z = 0..nz of the (even) Green's function in batches, batched 1-D D2Z along x, keep the bins
+//      [kx0, kx0 + nxl) and kx = nx          -> S[z][y][k], k <= nxl
+//   y: Z2Z along y per plane;  mirror planes z -> 2nz - z (G is even in z);  z: one batched Z2Z along z
+//   fold: gm[fz][fy][k] = 2 scale Re S[fz][fy][k], gn[fz][fy] = 2 scale Re S[fz][fy][nxl]   (fz <= nz, fy <= ny)
+// Same arithmetic as build_green_hat (Green's function in float with the reference's operation order, transform in
+// double), so the two agree to the rounding of the FFT factorisation.
+__global__ void __launch_bounds__(256)
+    greens_rows_kernel(double* g, const float* mz, const float* my, const float* mx, int z0, int nzb, int n2y,
+                       int n2x, float denom, float origin_value) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int j = blockIdx.y * blockDim.y + threadIdx.y;
+  if (i >= n2x || j >= n2y) return;
+  using R = RnOps<float>;
+  for (int k = blockIdx.z; k < nzb; k += gridDim.z) {
+    const float zc = mz[z0 + k];
+    const float r2 = R::add(R::add(R::mul(mx[i], mx[i]), R::mul(my[j], my[j])), R::mul(zc, zc));
+    float v = R::div(R::div(1.0f, R::sqrt_(r2)), denom);
+    if (i == 0 && j == 0 && z0 + k == 0) v = origin_value;
+    g[((int64_t)k * n2y + j) * n2x + i] = (double)v;
+  }
+}
+// S[z0 + k][y][q] = row_spectrum[k][y][kx0 + q] (q < nxl), S[..][nxl] = row_spectrum[..][nx]
+__global__ void __launch_bounds__(256)
+    keep_bins_kernel(cufftDoubleComplex* S, const cufftDoubleComplex* rows, int64_t nrows, int nkx, int kx0,
+                     int nxl, int nx) {
+  const int64_t total = nrows * (nxl + 1);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(q % (nxl + 1));
+    const int64_t r = q / (nxl + 1);
+    S[q] = rows[r * nkx + (k < nxl ? kx0 + k : nx)];
+  }
+}
+__global__ void __launch_bounds__(256)
+    fold_slice_kernel(float* gm, float* gn, const cufftDoubleComplex* S, int nz, int ny, int nxl, double scale2) {
+  const int64_t total = (int64_t)(nz + 1) * (ny + 1) * (nxl + 1);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(q % (nxl + 1));
+    const int64_t r = q / (nxl + 1);
+    const int fy = (int)(r % (ny + 1)), fz = (int)(r / (ny + 1));
+    // same rounding as the single-GPU path: scale in double, narrow to float, then the fold's factor 2
+    const float v = 2.0f * (float)(S[((int64_t)fz * 2 * ny + fy) * (nxl + 1) + k].x * scale2);
+    if (k == nxl)
+      gn[(int64_t)fz * (ny + 1) + fy] = v;
+    else
+      gm[((int64_t)fz * (ny + 1) + fy) * nxl + k] = v;
+  }
+}
+
+int build_green_folded_slice(float* gm, float* gn, int nz, int ny, int nx, int kx0, int nxl, double dx,
+                             const double* mz_h, const double* my_h, const double* mx_h, double origin_value,
+                             cudaStream_t st) {
+  const int n2z = 2 * nz, n2y = 2 * ny, n2x = 2 * nx, nkx = nx + 1, nk = nxl + 1;
+  std::vector<float> hz(n2z), hy(n2y), hx(n2x);
+  for (int q = 0; q < n2z; ++q) hz[q] = (float)mz_h[q];
+  for (int q = 0; q < n2y; ++q) hy[q] = (float)my_h[q];
+  for (int q = 0; q < n2x; ++q) hx[q] = (float)mx_h[q];
+  // z planes per batch: about 256 MB of real rows
+  int zb = (int)(((int64_t)32 << 20) / ((int64_t)n2y * n2x));
+  if (zb < 1) zb = 1;
+  if (zb > nz + 1) zb = nz + 1;
+  float *dz = nullptr, *dy = nullptr, *dxp = nullptr;
+  double* rows = nullptr;
+  cufftDoubleComplex *rspec = nullptr, *S = nullptr;
+  cufftHandle px = 0, py = 0, pz = 0;
+  int rc = SOPHT_OK;
+  auto cleanup = [&]() {
+    cudaFree(dz);
+    cudaFree(dy);
+    cudaFree(dxp);
+    cudaFree(rows);
+    cudaFree(rspec);
+    cudaFree(S);
+    if (px) cufftDestroy(px);
+    if (py) cufftDestroy(py);
+    if (pz) cufftDestroy(pz);
+  };
+#define SLICE_TRY(expr)       \
+  do {                        \
+    rc = [&]() -> int {       \
+      expr;                   \
+      return SOPHT_OK;        \
+    }();                      \
+    if (rc) {                 \
+      cleanup();              \
+      return rc;              \
+    }                         \
+  } while (0)
+  const int64_t plane = (int64_t)n2y * nk;  // complex elements of one z plane of S
+  SLICE_TRY(SOPHT_CUDA(cudaMalloc(&dz, sizeof(float) * n2z)));
+  SLICE_TRY(SOPHT_CUDA(cudaMalloc(&dy, sizeof(float) * n2y)));
+  SLICE_TRY(SOPHT_CUDA(cudaMalloc(&dxp, sizeof(float) * n2x)));
+  SLICE_TRY(SOPHT_CUDA(cudaMalloc(&rows, sizeof(double) * (size_t)zb * n2y * n2x)));
+  SLICE_TRY(SOPHT_CUDA(cudaMalloc(&rspec, sizeof(cufftDoubleComplex) * (size_t)zb * n2y * nkx)));
+  SLICE_TRY(SOPHT_CUDA(cudaMalloc(&S, sizeof(cufftDoubleComplex) * (size_t)n2z * plane)));
+  SLICE_TRY(SOPHT_CUDA(cudaMemcpyAsync(dz, hz.data(), sizeof(float) * n2z, cudaMemcpyHostToDevice, st)));
+  SLICE_TRY(SOPHT_CUDA(cudaMemcpyAsync(dy, hy.data(), sizeof(float) * n2y, cudaMemcpyHostToDevice, st)));
+  SLICE_TRY(SOPHT_CUDA(cudaMemcpyAsync(dxp, hx.data(), sizeof(float) * n2x, cudaMemcpyHostToDevice, st)));
+  {
+    int n1[1] = {n2x};
+    SLICE_TRY(SOPHT_CUFFT(cufftPlanMany(&px, 1, n1, nullptr, 1, n2x, nullptr, 1, nkx, CUFFT_D2Z, zb * n2y)));
+    SLICE_TRY(SOPHT_CUFFT(cufftSetStream(px, st)));
+    int ny1[1] = {n2y};
+    SLICE_TRY(SOPHT_CUFFT(cufftPlanMany(&py, 1, ny1, ny1, nk, 1, ny1, nk, 1, CUFFT_Z2Z, nk)));
+    SLICE_TRY(SOPHT_CUFFT(cufftSetStream(py, st)));
+    int nz1[1] = {n2z};
+    SLICE_TRY(SOPHT_CUFFT(cufftPlanMany(&pz, 1, nz1, nz1, (int)plane, 1, nz1, (int)plane, 1, CUFFT_Z2Z, (int)plane)));
+    SLICE_TRY(SOPHT_CUFFT(cufftSetStream(pz, st)));
+  }
+  const float four_pi = (float)(4 * 3.14159265358979323846);
+  for (int z0 = 0; z0 <= nz; z0 += zb) {
+    const int nzb = z0 + zb <= nz + 1 ? zb : nz + 1 - z0;
+    Grid3 g = cell_grid(nzb, n2y, n2x);
+    greens_rows_kernel<<<g.grid, g.block, 0, st>>>(rows, dz, dy, dxp, z0, nzb, n2y, n2x, four_pi,
+                                                   (float)origin_value);
+    SLICE_TRY(SOPHT_CHECK_LAUNCH());
+    // the plan transforms zb planes; a short last batch leaves stale rows behind that are not kept
+    SLICE_TRY(SOPHT_CUFFT(cufftExecD2Z(px, rows, rspec)));
+    keep_bins_kernel<<<148 * 4, 256, 0, st>>>(S + (int64_t)z0 * plane, rspec, (int64_t)nzb * n2y, nkx, kx0, nxl, nx);
+    SLICE_TRY(SOPHT_CHECK_LAUNCH());
+  }
+  for (int z = 0; z <= nz; ++z) SLICE_TRY(SOPHT_CUFFT(cufftExecZ2Z(py, S + z * plane, S + z * plane, CUFFT_FORWARD)));
+  for (int z = 1; z < nz; ++z)
+    SLICE_TRY(SOPHT_CUDA(cudaMemcpyAsync(S + (int64_t)(n2z - z) * plane, S + (int64_t)z * plane,
+                                         sizeof(cufftDoubleComplex) * plane, cudaMemcpyDeviceToDevice, st)));
+  SLICE_TRY(SOPHT_CUFFT(cufftExecZ2Z(pz, S, S, CUFFT_FORWARD)));
+  {
+    const float dxT = (float)dx;
+    const float dx3 = dxT * dxT * dxT;
+    const double scale = (double)dx3 / ((double)n2z * n2y * n2x);
+    fold_slice_kernel<<<148 * 4, 256, 0, st>>>(gm, gn, S, nz, ny, nxl, scale);
+    SLICE_TRY(SOPHT_CHECK_LAUNCH());
+  }
+  SLICE_TRY(SOPHT_CUDA(cudaStreamSynchronize(st)));
+#undef SLICE_TRY
+  cleanup();
+  return SOPHT_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 template <typename T>
 struct GenericPoisson : PoissonImpl {
   using C = typename FFTTypes<T>::C;

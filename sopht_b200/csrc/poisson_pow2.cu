@@ -438,25 +438,12 @@ struct SlabPow2Poisson {
 
   int init(double dx, const double* mz, const double* my, const double* mx, double origin, cudaStream_t st) {
     const int nz = d.nz, ny = d.ny, nx = d.nx, nxl = d.nxl();
-    float* ghat = nullptr;
-    int rc = build_green_hat<float>(&ghat, 3, nz, ny, nx, dx, mz, my, mx, origin, st);
-    if (rc) return rc;
-    auto fail = [&](int code) {
-      cudaFree(ghat);
-      return code;
-    };
     if (cudaMalloc(&gm, sizeof(float) * (size_t)(nz + 1) * (ny + 1) * nxl) != cudaSuccess ||
-        cudaMalloc(&gn, sizeof(float) * (size_t)(nz + 1) * (ny + 1)) != cudaSuccess) {
-      set_error("poisson(slab): out of device memory for the Green's function slice");
-      return fail(SOPHT_ERR_ALLOC);
-    }
-    fold_green_kernel<<<148 * 8, 256, 0, st>>>(gm, gn, ghat, nz, ny, nx, d.rank * nxl, nxl);
-    g_launch_count++;
-    if (cudaStreamSynchronize(st) != cudaSuccess) {
-      set_error("poisson(slab): folding the Green's function failed");
-      return fail(SOPHT_ERR_CUDA);
-    }
-    cudaFree(ghat);
+        cudaMalloc(&gn, sizeof(float) * (size_t)(nz + 1) * (ny + 1)) != cudaSuccess)
+      SOPHT_FAIL(SOPHT_ERR_ALLOC, "poisson(slab): out of device memory for the Green's function slice");
+    // only this rank's kx range of G_hat is ever formed (the full doubled-domain transform does not fit at 1024^3)
+    int rc = build_green_folded_slice(gm, gn, nz, ny, nx, d.rank * nxl, nxl, dx, mz, my, mx, origin, st);
+    if (rc) return rc;
     if ((rc = Pow2Poisson::upload_twiddles(&twx, nx, nx, st))) return rc;
     if ((rc = Pow2Poisson::upload_twiddles(&twx2, nx, 2 * nx, st))) return rc;
     if ((rc = Pow2Poisson::upload_twiddles(&twy, 2 * ny, 2 * ny, st))) return rc;

@@ -15,6 +15,8 @@
 // ref: sopht/simulator/flow/navier_stokes_flow_simulators.py:449-498 (step order),
 //      stencil_ops_3d/{elementwise_ops_3d.py:390-449, update_vorticity_from_velocity_forcing_3d.py:12-132,
 //      diffusion_timestep_3d.py:12-80, curl_3d.py:13-132}, passive_transport_flow_simulators.py:139-155
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "stream_vec.cuh"
 
@@ -586,6 +588,8 @@ int resident_ctas(Kernel kernel, int threads) {
   return num_sm * per_sm;
 }
 int pick_vec_kchunk(int nz, int ny, int nx, int ncomp_grids, int w, int slots) {
+  static const char* force = getenv("SOPHT_VEC_KCHUNK");  // experiments
+  if (force && atoi(force) > 0) return atoi(force) < nz ? atoi(force) : nz;
   const int64_t xy = (int64_t)((nx + 32 * w - 1) / (32 * w)) * ((ny + VBY - 1) / VBY) * ncomp_grids;
   int best_k = nz;
   double best_cost = 1e30;

@@ -82,3 +82,59 @@ def test_navier_stokes_2d_step(rng, precision, with_forcing, grid):
     for name in ["vorticity_field", "velocity_field", "stream_func_field"]:
         err = rel_l2(getattr(sim, name).cpu().numpy(), getattr(ref, name))
         assert err < REL_L2_TOL[precision], (name, err)
+
+
+# ---- BASELINE.json sizes: size-independent properties (the oracle takes minutes there) ------------------------------
+@pytest.mark.parametrize("grid", [(128, 128, 256), (256, 256, 256)])
+def test_poisson_full_size_pow2_vs_cufft_path_and_linearity(grid):
+    """C2 / 256^3: the hand-written pruned FFT pipeline against the cuFFT-based generic path of the same library
+    (independent code: padded doubled domain, cuFFT transforms), plus linearity of the solve."""
+    import torch
+
+    from sopht_b200.numeric.eulerian_grid_ops import UnboundedPoissonSolverPYFFTW3D
+    from sopht_b200.numeric.eulerian_grid_ops.poisson_solvers import POISSON_FORCE_GENERIC
+
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    rhs = torch.randn(3, *grid, device="cuda", generator=gen)
+    fast = UnboundedPoissonSolverPYFFTW3D(*grid, x_range=1.0, real_t=np.float32)
+    slow = UnboundedPoissonSolverPYFFTW3D(*grid, x_range=1.0, real_t=np.float32, flags=POISSON_FORCE_GENERIC)
+    assert fast.path == "pow2" and slow.path != "pow2"
+    a, b = torch.zeros_like(rhs), torch.zeros_like(rhs)
+    fast.vector_field_solve(solution_vector_field=a, rhs_vector_field=rhs)
+    slow.vector_field_solve(solution_vector_field=b, rhs_vector_field=rhs)
+    assert float((a - b).norm() / b.norm()) < 1e-5
+    # linearity: solve(2 f0 - 3 f1) = 2 solve(f0) - 3 solve(f1)
+    mix = torch.zeros(*grid, device="cuda")
+    fast.solve(solution_field=mix, rhs_field=2 * rhs[0] - 3 * rhs[1])
+    want = 2 * a[0] - 3 * a[1]
+    assert float((mix - want).norm() / want.norm()) < 1e-5
+
+
+def test_c2_step_fused_vs_unfused_and_forcing_reset():
+    """BASELINE configs[1] size (128x128x256, forcing + free stream): the fused step (register-marching kernels,
+    pruned FFT Poisson, side-stream Nyquist plane) against the one-kernel-per-reference-call step of the same
+    library, two steps from the same random state; both paths are pinned to the oracle at small sizes above."""
+    import torch
+
+    from sopht_b200.simulator import UnboundedNavierStokesFlowSimulator3D
+
+    grid = (128, 128, 256)
+    kw = dict(grid_size=grid, x_range=1.0, kinematic_viscosity=1e-3, real_t=np.float32, with_forcing=True,
+              with_free_stream_flow=True)
+    sims = [UnboundedNavierStokesFlowSimulator3D(step_mode=m, **kw) for m in ("fused", "unfused")]
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    state = {n: torch.randn(3, *grid, device="cuda", generator=gen)
+             for n in ("vorticity_field", "velocity_field", "eul_grid_forcing_field")}
+    for s in sims:
+        for n, v in state.items():
+            getattr(s, n)[...] = v
+    dt = sims[0].compute_stable_timestep(dt_prefac=0.5)
+    assert sims[1].compute_stable_timestep(dt_prefac=0.5) == pytest.approx(dt, rel=1e-6)
+    for _ in range(2):
+        for s in sims:
+            s.time_step(dt=dt, free_stream_velocity=[1.0, 0.0, 0.0])
+            s.eul_grid_forcing_field[...] = state["eul_grid_forcing_field"]
+    for n in ("vorticity_field", "velocity_field", "stream_func_field"):
+        a, b = getattr(sims[0], n), getattr(sims[1], n)
+        assert float((a - b).norm() / b.norm()) < 1e-5, n
+    assert sims[0].compute_stable_timestep() == pytest.approx(sims[1].compute_stable_timestep(), rel=1e-5)

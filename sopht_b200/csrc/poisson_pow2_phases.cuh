@@ -460,17 +460,28 @@ struct XFwd {
     } else if (P == NP - 1) {
       fft::fwd_last<L>(sm, t, InPlaceSink<L>{sm});
     } else if (P == NP) {
-      // X_k = E_k + w^k O_k, E = (Z_k + conj Z_{L-k})/2, O = (Z_k - conj Z_{L-k})/(2i); X_L = E_0 - O_0
+      // X_k = E_k + w^k O_k, E = (Z_k + conj Z_{L-k})/2, O = (Z_k - conj Z_{L-k})/(2i); X_L = E_0 - O_0.
+      // Bins k and L - k come from the same pair: X_{L-k} = conj(E_k - w^k O_k) (E_{L-k} = conj E_k, O_{L-k} =
+      // conj O_k, w^{L-k} = -conj w^k), so a thread owns k < L/2 and produces both - half the shared-memory reads and
+      // twiddle products of the one-bin-per-read form; k = L/2 (its own partner: X = conj Z) rides with thread 0.
       const int64_t rb = p.row_base(row);
 #pragma unroll
-      for (int q = 0; q < Cfg<L>::E; ++q) {
+      for (int q = 0; q < Cfg<L>::E / 2; ++q) {
         const int k = t + q * T;
         const float2 a = sm(fft::spectrum_position<L>(k));
         const float2 b = sm(fft::spectrum_position<L>((L - k) & (L - 1)));
         const float2 e = make_float2(0.5f * (a.x + b.x), 0.5f * (a.y - b.y));
         const float2 o = make_float2(0.5f * (a.y + b.y), -0.5f * (a.x - b.x));
-        *p.out_bin(rb, k) = fft::cadd(e, fft::cmul(o, tw2[k]));
-        if (k == 0) p.nyq[row] = make_float2(e.x - o.x, e.y - o.y);
+        const float2 w = fft::cmul(o, tw2[k]);
+        *p.out_bin(rb, k) = fft::cadd(e, w);
+        if (k == 0)
+          p.nyq[row] = make_float2(e.x - o.x, e.y - o.y);
+        else
+          *p.out_bin(rb, L - k) = make_float2(e.x - w.x, w.y - e.y);
+      }
+      if (t == 0) {
+        const float2 a = sm(fft::spectrum_position<L>(L / 2));
+        *p.out_bin(rb, L / 2) = make_float2(a.x, -a.y);
       }
     } else {
       fft::fwd_mid<L>(sm, t, tw);
@@ -525,9 +536,11 @@ struct XInv {
       const float2* nq = stage ? stage + r * (L + 1) + L : p.nyq + row;
       // one chunk (single GPU) or a staged row: bin k is element k, no chunk arithmetic per access
       const bool plain = stage != nullptr || (1 << p.chunk_shift) >= L;
+      // Z_{L-k} = conj(E_k - i O_k) from the same pair (E_{L-k} = conj E_k, O_{L-k} = conj O_k): a thread owns
+      // k < L/2 and writes both; k = L/2 (Z = conj X) rides with thread 0
       auto combine = [&](auto load) {
 #pragma unroll
-        for (int q = 0; q < Cfg<L>::E; ++q) {
+        for (int q = 0; q < Cfg<L>::E / 2; ++q) {
           const int k = t + q * T;
           const float2 a = load(k);
           const float2 b = k == 0 ? *nq : load(L - k);
@@ -535,6 +548,11 @@ struct XInv {
           const float2 d = make_float2(0.5f * (a.x - b.x), 0.5f * (a.y + b.y));
           const float2 o = fft::cmul_conj(d, tw2[k]);
           sm(fft::spectrum_position<L>(k)) = make_float2(e.x - o.y, e.y + o.x);
+          if (k != 0) sm(fft::spectrum_position<L>(L - k)) = make_float2(e.x + o.y, o.x - e.y);
+        }
+        if (t == 0) {
+          const float2 a = load(L / 2);
+          sm(fft::spectrum_position<L>(L / 2)) = make_float2(a.x, -a.y);
         }
       };
       if (plain) {

@@ -92,13 +92,14 @@ def ncu_traffic(kernel, grid):
         return None
 
 
-def roofline_from_report(report, steps, cells, forcing, peak, peak_src, grid):
+def roofline_from_report(report, steps, cells, forcing, peak, peak_src, grid, side_stream):
     """Per-kernel achieved GB/s from the library's event timers; the roofline object describes the kernel
     with the largest share of the step."""
     kernels = {}
     # the Nyquist-plane kernels run on the solver's side stream underneath the main y / z kernels: their event
     # time is mostly waiting for SM slots and overlaps the main stream, so it is not part of the step's sum
-    overlapped = {k for k in report if k.endswith(".nyquist")}
+    # (single-GPU solver, grids up to 2^25 cells; elsewhere they run on the main stream and count like any kernel)
+    overlapped = {k for k in report if k.endswith(".nyquist")} if side_stream else set()
     total = sum(v["ms"] for k, v in report.items() if k not in overlapped) or 1.0
     for label, v in report.items():
         per_launch_ms = v["ms"] / max(v["launches"], 1)
@@ -450,7 +451,8 @@ def run_ours(args, wl):
     barrier()
     report = _lib.profile_report()
     _lib.profile_enable(False)
-    roof, kernels = roofline_from_report(report, args.steps, cells_local, forcing, peak, peak_src, grid)
+    roof, kernels = roofline_from_report(report, args.steps, cells_local, forcing, peak, peak_src, grid,
+                                         side_stream=world == 1 and cells <= 2**25)
     step_bpc = algorithmic_bytes_per_cell(forcing)
     whole = step_bpc * cells_local * args.steps / (ms * 1e-3) / 1e9  # per GPU
 

@@ -338,6 +338,23 @@ int sopht_poisson_slab_open_peers(sopht_poisson_slab_t handle, const unsigned ch
 int sopht_poisson_slab_destroy(sopht_poisson_slab_t handle);
 
 /* ------------------------------------------------------------------------ */
+/* Real <-> half-spectrum FFT over all axes of a (nz, ny, nx) or (ny, nx)     */
+/* grid: the plan objects of FFTPyFFTW{2,3}D and the scipy rfftn/irfftn       */
+/* helper. Arrays are contiguous: real (nz, ny, nx), complex (nz, ny, nx/2+1). */
+/* ref: poisson_solver_3d/FFTPyFFTW3D.py:7-67, poisson_solver_2d/             */
+/*      FFTPyFFTW2D.py:7-65, poisson_solver_3d/scipy_fft_3d.py:7-15           */
+/* ------------------------------------------------------------------------ */
+typedef struct sopht_fft *sopht_fft_t;
+int sopht_fft_create(sopht_fft_t *handle, int dtype, int dim, int nz, int ny, int nx);
+/* fourier_field = rfftn(field)                       (fft_plan(input_array=field, output_array=fourier_field)) */
+int sopht_fft_forward(sopht_fft_t handle, const sopht_field_t *field, const sopht_field_t *fourier_field,
+                      void *stream);
+/* field = irfftn(fourier_field), normalised; fourier_field is destroyed like the input of an FFTW c2r plan */
+int sopht_fft_inverse(sopht_fft_t handle, const sopht_field_t *fourier_field, const sopht_field_t *field,
+                      void *stream);
+int sopht_fft_destroy(sopht_fft_t handle);
+
+/* ------------------------------------------------------------------------ */
 /* Peer-memory arena of the z-slab decomposition (one process per GPU, one    */
 /* box): field storage every rank can address over NVLink (CUDA IPC), the     */
 /* halo exchange as one kernel of direct stores into the neighbours' halo     */

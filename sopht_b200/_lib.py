@@ -147,6 +147,11 @@ _HANDLE_SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "sopht_poisson_slab_enable_peer_exchange": (ctypes.c_int, [_P, _P]),
     "sopht_poisson_slab_open_peers": (ctypes.c_int, [_P, _P]),
     "sopht_poisson_slab_destroy": (ctypes.c_int, [_P]),
+    # plain rfftn / irfftn plans (FFTPyFFTW{2,3}D)
+    "sopht_fft_create": (ctypes.c_int, [ctypes.POINTER(_P), _I, _I, _I, _I, _I]),
+    "sopht_fft_forward": (ctypes.c_int, [_P, _F, _F, _P]),
+    "sopht_fft_inverse": (ctypes.c_int, [_P, _F, _F, _P]),
+    "sopht_fft_destroy": (ctypes.c_int, [_P]),
     # peer-memory arena (halo exchange / barrier over NVLink)
     "sopht_peer_arena_create": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_size_t, _I, _I, _P]),
     "sopht_peer_arena_open": (ctypes.c_int, [_P, _P]),

@@ -97,6 +97,31 @@ class _UnboundedPoissonSolverBase:
         """Solve -del^2(solution_field) = rhs_field on the unbounded domain (Hockney-Eastwood)."""
         self._solve(solution_field, rhs_field)
 
+    def _greens_function_hat(self) -> torch.Tensor:
+        """rfftn(G) * dx^dim on the doubled grid as a complex tensor (2nz, 2ny, nx + 1) / (2ny, nx + 1), rebuilt from
+        the real, pre-normalised copy the library keeps (G is real and even, so its transform is real). The reference
+        holds this array as `fourier_greens_function_times_dx_cubed` / `..._squared`
+        (UnboundedPoissonSolverPYFFTW3D.py:47-49, ...2D.py:42-44) and multiplies the spectrum with it."""
+        ptr = ctypes.c_void_p()
+        _lib.check(_lib.load().sopht_poisson_green_hat(self._handle, ctypes.byref(ptr)))
+        if not ptr.value:
+            msg = "this solver path does not keep the Green's function spectrum in natural order"
+            raise _lib.SophtLibraryError(msg)
+        shape = ((2 * self.grid_size_z,) if self._dim == 3 else ()) + (2 * self.grid_size_y, self.grid_size_x + 1)
+        count = int(np.prod(shape))
+
+        class _Span:  # raw device memory -> torch (zero copy); the solver object keeps the memory alive
+            pass
+
+        span = _Span()
+        span.owner = self
+        span.__cuda_array_interface__ = {
+            "shape": (count,), "typestr": np.dtype(self.real_t).str, "data": (ptr.value, True), "version": 2,
+            "strides": None}
+        real = torch.as_tensor(span, device=torch.device("cuda", torch.cuda.current_device())).view(*shape)
+        doubled_cells = float(np.prod([2 * n for n in shape[:-1]]) * 2 * self.grid_size_x)
+        return torch.complex(real * doubled_cells, torch.zeros_like(real))
+
 
 class UnboundedPoissonSolverPYFFTW3D(_UnboundedPoissonSolverBase):
     """3-D unbounded Poisson solver (same ctor as the reference class of this name)."""
@@ -129,6 +154,10 @@ class UnboundedPoissonSolverPYFFTW3D(_UnboundedPoissonSolverBase):
         """Three component solves, -del^2(solution_vector_field) = rhs_vector_field."""
         self._solve(solution_vector_field, rhs_vector_field)
 
+    @property
+    def fourier_greens_function_times_dx_cubed(self) -> torch.Tensor:
+        return self._greens_function_hat()
+
 
 class UnboundedPoissonSolverPYFFTW2D(_UnboundedPoissonSolverBase):
     """2-D unbounded Poisson solver (same ctor as the reference class of this name)."""
@@ -152,3 +181,7 @@ class UnboundedPoissonSolverPYFFTW2D(_UnboundedPoissonSolverBase):
         self.num_threads = num_threads
         self.real_t = real_t
         self._create(flags)
+
+    @property
+    def fourier_greens_function_times_dx_squared(self) -> torch.Tensor:
+        return self._greens_function_hat()

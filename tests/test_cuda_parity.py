@@ -122,3 +122,75 @@ def test_cuda_fused_ns3d_passes_vs_oracle(precision, grid):
         dc, fd(dout), fd(dw), float(p), _lib.double_array(fsv), ctypes.c_void_p(vmax.data_ptr()), st))
     assert rel_l2(dout.cpu().numpy(), want) < REL_L2_TOL[precision]
     assert float(vmax.item()) == pytest.approx(float(np.abs(want).sum(axis=0).max()), rel=1e-5)
+
+
+# ---- FFTPyFFTW{2,3}D plan objects and the scipy-named helper -------------------------------
+# mirrors tests/test_numeric/test_eulerian_grid_ops/test_poisson_solver_{2,3}d/test_fft_kernel_{2,3}d.py of the reference
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("shape", [(8, 8, 8), (6, 10, 18), (8, 8), (12, 20)])
+def test_cuda_fft_plans_match_scipy(shape, precision):
+    import numpy as np
+    from conftest import real_t_of
+    from scipy.fft import irfftn, rfftn
+
+    from sopht_b200.numeric.eulerian_grid_ops import (
+        FFTPyFFTW2D,
+        FFTPyFFTW3D,
+        fft_ifft_via_scipy_kernel_2d,
+        fft_ifft_via_scipy_kernel_3d,
+    )
+
+    real_t = real_t_of(precision)
+    tol = 1e-4 if precision == "single" else 1e-11  # get_test_tol of the reference scaled to these sizes
+    rng = np.random.default_rng(42)
+    field = rng.standard_normal(shape).astype(real_t)
+    ref_f = rfftn(field)
+    ref_i = irfftn(ref_f, s=shape)
+    cls, helper = (FFTPyFFTW3D, fft_ifft_via_scipy_kernel_3d) if len(shape) == 3 else (FFTPyFFTW2D, fft_ifft_via_scipy_kernel_2d)
+    plan = cls(*shape, num_threads=4, real_t=real_t)
+    assert tuple(plan.field_pyfftw_buffer.shape) == shape
+    assert tuple(plan.fourier_field_pyfftw_buffer.shape) == ref_f.shape
+    fourier = np.zeros_like(ref_f)
+    inv = np.zeros_like(ref_i)
+    plan.fft_plan(input_array=field, output_array=fourier)
+    np.testing.assert_allclose(fourier, ref_f, atol=tol * np.abs(ref_f).max())
+    plan.ifft_plan(input_array=fourier.copy(), output_array=inv)  # a copy: complex-to-real plans destroy their input
+    np.testing.assert_allclose(inv, ref_i, atol=tol)
+    fourier2, inv2 = np.zeros_like(ref_f), np.zeros_like(ref_i)
+    helper(fourier2, inv2, field, num_threads=4)
+    np.testing.assert_allclose(fourier2, ref_f, atol=tol * np.abs(ref_f).max())
+    np.testing.assert_allclose(inv2, field, atol=tol)
+    # device tensors and the plan's own buffers
+    import torch
+
+    plan.field_pyfftw_buffer[...] = torch.from_numpy(field).cuda()
+    plan.fft_plan()
+    np.testing.assert_allclose(plan.fourier_field_pyfftw_buffer.cpu().numpy(), ref_f, atol=tol * np.abs(ref_f).max())
+    plan.ifft_plan()
+    np.testing.assert_allclose(plan.field_pyfftw_buffer.cpu().numpy(), field, atol=tol)
+    with pytest.raises(ValueError):
+        plan.fft_plan(input_array=torch.zeros(*shape[:-1], 2 * shape[-1], device="cuda",
+                                              dtype=plan.field_pyfftw_buffer.dtype)[..., ::2])
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_cuda_poisson_exposes_greens_function_spectrum(precision):
+    """fourier_greens_function_times_dx_cubed / _squared (UnboundedPoissonSolverPYFFTW3D.py:47-49, ...2D.py:42-44)."""
+    import numpy as np
+    from conftest import real_t_of, rel_l2
+
+    from oracle import poisson as opoisson
+    from sopht_b200.numeric.eulerian_grid_ops import UnboundedPoissonSolverPYFFTW2D, UnboundedPoissonSolverPYFFTW3D
+
+    real_t = real_t_of(precision)
+    tol = 1e-5 if precision == "single" else 1e-12
+    s3 = UnboundedPoissonSolverPYFFTW3D(8, 16, 32, x_range=1.0, real_t=real_t)
+    r3 = opoisson.UnboundedPoissonSolver3D(8, 16, 32, x_range=1.0, real_t=real_t)
+    g3 = s3.fourier_greens_function_times_dx_cubed
+    assert tuple(g3.shape) == (16, 32, 33) and g3.is_complex()
+    assert rel_l2(g3.real.cpu().numpy(), np.real(r3.fourier_greens_function_times_dx_cubed)) < tol
+    s2 = UnboundedPoissonSolverPYFFTW2D(12, 20, x_range=1.0, real_t=real_t)
+    r2 = opoisson.UnboundedPoissonSolver2D(12, 20, x_range=1.0, real_t=real_t)
+    g2 = s2.fourier_greens_function_times_dx_squared
+    assert tuple(g2.shape) == (24, 21)
+    assert rel_l2(g2.real.cpu().numpy(), np.real(r2.fourier_greens_function_times_dx_squared)) < tol

@@ -116,10 +116,10 @@ class _UnboundedPoissonSolverBase:
         span = _Span()
         span.owner = self
         span.__cuda_array_interface__ = {
-            "shape": (count,), "typestr": np.dtype(self.real_t).str, "data": (ptr.value, True), "version": 2,
+            "shape": (count,), "typestr": np.dtype(self.real_t).str, "data": (ptr.value, False), "version": 2,
             "strides": None}
         real = torch.as_tensor(span, device=torch.device("cuda", torch.cuda.current_device())).view(*shape)
-        doubled_cells = float(np.prod([2 * n for n in shape[:-1]]) * 2 * self.grid_size_x)
+        doubled_cells = float(np.prod(shape[:-1]) * 2 * self.grid_size_x)  # shape[:-1] is already doubled
         return torch.complex(real * doubled_cells, torch.zeros_like(real))
 
 

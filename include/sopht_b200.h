@@ -433,6 +433,26 @@ int sopht_ib_virtual_boundary_forcing(int dtype, int dim, const sopht_field_t *e
                                       double dx_pow_dim, double stiffness, double damping, void *stream);
 
 /* ------------------------------------------------------------------------ */
+/* Rigid-body forcing grids. Grid fields are float64 (dim, N) */
+/* device arrays; the body state travels as host 3-vectors / a 3x3 matrix.    */
+/* ------------------------------------------------------------------------ */
+
+/* r_g = rotation * r_l (local_frame_relative_position_field may be NULL: r_g is used as stored, the sphere's case),
+ * position = centre + r_g, velocity = velocity + global_frame_omega x r_g. rotation: row-major 3x3 (director^T).
+ * ref: simulator/immersed_body/rigid_body/rigid_body_forcing_grids.py:28-55 (2-D), :128-149 (3-D), :291-300 */
+int sopht_rigid_forcing_grid_kinematics(int dim, const sopht_field_t *position_field,
+                                        const sopht_field_t *velocity_field,
+                                        const sopht_field_t *global_frame_relative_position_field,
+                                        const sopht_field_t *local_frame_relative_position_field,
+                                        const double *rotation, const double *centre, const double *velocity,
+                                        const double *global_frame_omega, void *stream);
+/* sums_out (device, 6 doubles) = [sum_i f_i (3), sum_i r_g,i x f_i (3)]; the caller negates and applies the
+ * director like the reference (:57-78, :151-169). lag_grid_forcing_field is of forcing_dtype. */
+int sopht_rigid_forcing_grid_force_sums(int forcing_dtype, int dim,
+                                        const sopht_field_t *global_frame_relative_position_field,
+                                        const sopht_field_t *lag_grid_forcing_field, void *sums_out, void *stream);
+
+/* ------------------------------------------------------------------------ */
 /* Fused passes of the 3-D Navier-Stokes step (simulator-level path).         */
 /* Vector fields (3, nz, ny, nx) with unit x-stride; outputs must not alias   */
 /* inputs (neighbouring cells are read).                                      */

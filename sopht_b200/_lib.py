@@ -152,6 +152,9 @@ _HANDLE_SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "sopht_fft_forward": (ctypes.c_int, [_P, _F, _F, _P]),
     "sopht_fft_inverse": (ctypes.c_int, [_P, _F, _F, _P]),
     "sopht_fft_destroy": (ctypes.c_int, [_P]),
+    # rigid-body forcing grids
+    "sopht_rigid_forcing_grid_kinematics": (ctypes.c_int, [_I, _F, _F, _F, _F, _PD, _PD, _PD, _PD, _P]),
+    "sopht_rigid_forcing_grid_force_sums": (ctypes.c_int, [_I, _I, _F, _F, _P, _P]),
     # peer-memory arena (halo exchange / barrier over NVLink)
     "sopht_peer_arena_create": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_size_t, _I, _I, _P]),
     "sopht_peer_arena_open": (ctypes.c_int, [_P, _P]),

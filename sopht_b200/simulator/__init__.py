@@ -1,4 +1,5 @@
-"""Simulator-level call sites of the hot path (step sequencers), same names as sopht.simulator."""
+"""Simulator-level call sites of the hot path (step sequencers, rigid-body forcing grids), same names as
+sopht.simulator."""
 
 from .flow import (
     FlowSimulator,
@@ -6,9 +7,25 @@ from .flow import (
     UnboundedNavierStokesFlowSimulator3D,
     compute_advection_diffusion_stable_timestep,
 )
+from .immersed_body import (
+    CircularCylinderForcingGrid,
+    ImmersedBodyForcingGrid,
+    OpenEndCircularCylinderForcingGrid,
+    RigidBodyState,
+    SphereForcingGrid,
+    ThreeDimensionalRigidBodyForcingGrid,
+    TwoDimensionalCylinderForcingGrid,
+)
 
 __all__ = [
+    "CircularCylinderForcingGrid",
     "FlowSimulator",
+    "ImmersedBodyForcingGrid",
+    "OpenEndCircularCylinderForcingGrid",
+    "RigidBodyState",
+    "SphereForcingGrid",
+    "ThreeDimensionalRigidBodyForcingGrid",
+    "TwoDimensionalCylinderForcingGrid",
     "UnboundedNavierStokesFlowSimulator2D",
     "UnboundedNavierStokesFlowSimulator3D",
     "compute_advection_diffusion_stable_timestep",

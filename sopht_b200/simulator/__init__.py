@@ -3,9 +3,12 @@ sopht.simulator."""
 
 from .flow import (
     FlowSimulator,
+    PassiveTransportFlowSimulator,
     UnboundedNavierStokesFlowSimulator2D,
     UnboundedNavierStokesFlowSimulator3D,
     compute_advection_diffusion_stable_timestep,
+    create_unbounded_flow_simulator_2d,
+    create_unbounded_flow_simulator_3d,
 )
 from .immersed_body import (
     CircularCylinderForcingGrid,
@@ -22,6 +25,7 @@ __all__ = [
     "FlowSimulator",
     "ImmersedBodyForcingGrid",
     "OpenEndCircularCylinderForcingGrid",
+    "PassiveTransportFlowSimulator",
     "RigidBodyState",
     "SphereForcingGrid",
     "ThreeDimensionalRigidBodyForcingGrid",
@@ -29,4 +33,6 @@ __all__ = [
     "UnboundedNavierStokesFlowSimulator2D",
     "UnboundedNavierStokesFlowSimulator3D",
     "compute_advection_diffusion_stable_timestep",
+    "create_unbounded_flow_simulator_2d",
+    "create_unbounded_flow_simulator_3d",
 ]

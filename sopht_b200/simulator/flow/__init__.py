@@ -1,4 +1,4 @@
-"""Flow simulators (step sequencers of the hot path)."""
+"""Flow simulators (step sequencers of the hot path), same names as sopht.simulator.flow."""
 
 from .flow_simulators import FlowSimulator
 from .navier_stokes_flow_simulators import (
@@ -6,10 +6,18 @@ from .navier_stokes_flow_simulators import (
     UnboundedNavierStokesFlowSimulator3D,
     compute_advection_diffusion_stable_timestep,
 )
+from .passive_transport_flow_simulators import (
+    PassiveTransportFlowSimulator,
+    create_unbounded_flow_simulator_2d,
+    create_unbounded_flow_simulator_3d,
+)
 
 __all__ = [
     "FlowSimulator",
+    "PassiveTransportFlowSimulator",
     "UnboundedNavierStokesFlowSimulator2D",
     "UnboundedNavierStokesFlowSimulator3D",
     "compute_advection_diffusion_stable_timestep",
+    "create_unbounded_flow_simulator_2d",
+    "create_unbounded_flow_simulator_3d",
 ]

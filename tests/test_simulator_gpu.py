@@ -138,3 +138,64 @@ def test_c2_step_fused_vs_unfused_and_forcing_reset():
         a, b = getattr(sims[0], n), getattr(sims[1], n)
         assert float((a - b).norm() / b.norm()) < 1e-5, n
     assert sims[0].compute_stable_timestep() == pytest.approx(sims[1].compute_stable_timestep(), rel=1e-5)
+
+
+# ---- passive transport and the backward-compatibility factories ----------------------------------
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("case", [(2, (24, 40), "scalar"), (3, (12, 20, 36), "scalar"), (3, (12, 20, 36), "vector")])
+def test_passive_transport_step(rng, precision, case):
+    """PassiveTransportFlowSimulator (passive_transport_flow_simulators.py:14-136): ENO3 advection + diffusion of the
+    primary field against the oracle's restatement of the same two composite kernels, three steps."""
+    import torch
+
+    from oracle import flow as oflow
+    from oracle import stencils as ost
+    from sopht_b200.simulator import PassiveTransportFlowSimulator
+
+    grid_dim, grid, field_type = case
+    real_t = real_t_of(precision)
+    sim = PassiveTransportFlowSimulator(kinematic_viscosity=1e-2, grid_dim=grid_dim, grid_size=grid, x_range=1.0,
+                                        real_t=real_t, field_type=field_type)
+    primary = rng.standard_normal(tuple(sim.primary_field.shape)).astype(real_t)
+    velocity = rng.standard_normal(tuple(sim.velocity_field.shape)).astype(real_t)
+    sim.primary_field[...] = torch.from_numpy(primary).cuda()
+    sim.velocity_field[...] = torch.from_numpy(velocity).cuda()
+    buf = np.zeros(grid, dtype=real_t)
+    dx = real_t(1.0 / grid[-1])
+    dt_ref = oflow.compute_advection_diffusion_stable_timestep(
+        velocity_field=velocity, velocity_magnitude_field=buf, grid_dim=grid_dim, dx=dx, cfl=0.1,
+        kinematic_viscosity=1e-2, real_t=real_t) * 0.5
+    assert sim.compute_stable_timestep(dt_prefac=0.5) == pytest.approx(dt_ref, rel=1e-6 if precision == "single" else 1e-13)
+    adv = (ost.advection_timestep_euler_forward_conservative_eno3_vector if field_type == "vector"
+           else ost.advection_timestep_euler_forward_conservative_eno3)
+    dif = ost.diffusion_timestep_euler_forward_vector if field_type == "vector" else ost.diffusion_timestep_euler_forward
+    for _ in range(3):
+        sim.time_step(dt=dt_ref)
+        adv(primary, buf, velocity, real_t(dt_ref / dx))
+        dif(primary, buf, real_t(1e-2 * dt_ref / dx / dx))
+    assert sim.time == pytest.approx(3 * dt_ref)
+    assert rel_l2(sim.primary_field.cpu().numpy(), primary) < REL_L2_TOL[precision]
+    with pytest.raises(ValueError, match="Invalid field type"):
+        PassiveTransportFlowSimulator(1e-2, 3, (8, 8, 8), 1.0, field_type="tensor")
+    with pytest.raises(ValueError, match="vector 2D fields not supported"):
+        PassiveTransportFlowSimulator(1e-2, 2, (8, 8), 1.0, field_type="vector")
+
+
+def test_create_unbounded_flow_simulator_factories():
+    from sopht_b200.simulator import (
+        UnboundedNavierStokesFlowSimulator2D,
+        UnboundedNavierStokesFlowSimulator3D,
+        create_unbounded_flow_simulator_2d,
+        create_unbounded_flow_simulator_3d,
+    )
+
+    s2 = create_unbounded_flow_simulator_2d(grid_size=(16, 32), x_range=1.0, kinematic_viscosity=1e-2,
+                                            flow_type="navier_stokes_with_forcing")
+    assert isinstance(s2, UnboundedNavierStokesFlowSimulator2D) and s2.with_forcing
+    s3 = create_unbounded_flow_simulator_3d(grid_size=(8, 16, 32), x_range=1.0, kinematic_viscosity=1e-2,
+                                            flow_type="navier_stokes", with_free_stream_flow=True)
+    assert isinstance(s3, UnboundedNavierStokesFlowSimulator3D) and not s3.with_forcing and s3.with_free_stream_flow
+    for make in (create_unbounded_flow_simulator_2d, create_unbounded_flow_simulator_3d):
+        with pytest.raises(ValueError, match="Invalid flow type given"):
+            make(grid_size=(8, 8, 8)[: 2 if make is create_unbounded_flow_simulator_2d else 3], x_range=1.0,
+                 kinematic_viscosity=1e-2, flow_type="passive_scalar")

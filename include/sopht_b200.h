@@ -453,6 +453,36 @@ int sopht_rigid_forcing_grid_force_sums(int forcing_dtype, int dim,
                                         const sopht_field_t *lag_grid_forcing_field, void *sums_out, void *stream);
 
 /* ------------------------------------------------------------------------ */
+/* Cosserat-rod forcing grids. grid_kind: 0 nodal, 1 element  */
+/* centric, 2 edge (dim 2 only), 3 surface (dim 3 only). rod_state is a DEVICE */
+/* block of sopht_rod_state_doubles(n_elems) doubles, rows contiguous:         */
+/*   position_collection (3, n+1) | velocity_collection (3, n+1) | mass (n+1)  */
+/*   | director_collection (3, 3, n) | omega_collection (3, n) | radius (n)    */
+/*   | tangents (3, n)                                                          */
+/* ------------------------------------------------------------------------ */
+
+int64_t sopht_rod_state_doubles(int64_t n_elems);
+/* position_field / velocity_field: float64 (dim, N_lag) device arrays, N_lag = n+1 | n | 3n | number of surface
+ * nodes. moment_arm: float64 (3, n) for the edge grid, (3, N_lag) for the surface grid (written), NULL otherwise.
+ * Surface tables (device): node_element int32 (N_lag), local_points float64 (2, N_lag) = (cos, sin) of the node's
+ * angle or (0, 0) for a centre node, radius_ratio float64 (N_lag).
+ * ref: simulator/immersed_body/cosserat_rod/cosserat_rod_forcing_grids.py:25-33 (nodal), :96-109 (element centric),
+ *      :179-237 (edge), :408-467 (surface) */
+int sopht_rod_forcing_grid_kinematics(int grid_kind, int dim, int64_t n_elems, const void *rod_state,
+                                      const sopht_field_t *position_field, const sopht_field_t *velocity_field,
+                                      const sopht_field_t *moment_arm, const void *surface_node_element,
+                                      const void *surface_local_points, const void *surface_radius_ratio,
+                                      void *stream);
+/* forces_torques_out (device, 3 (n+1) + 3 n doubles) = body_flow_forces (3, n+1) | body_flow_torques (3, n), the
+ * torques in the elements' material frames; the element-centric grid leaves the torques at 0 (the reference does not
+ * touch them). moment_arm: (3, n) written by the nodal grid, read by the edge grid; (3, N_lag) read by the surface
+ * grid; NULL for the element-centric grid. surface_element_start: int32 (n+1) windows of the surface nodes.
+ * ref: cosserat_rod_forcing_grids.py:35-73, :111-124, :239-284, :469-497 */
+int sopht_rod_forcing_grid_transfer(int forcing_dtype, int grid_kind, int dim, int64_t n_elems, const void *rod_state,
+                                    const sopht_field_t *lag_grid_forcing_field, const sopht_field_t *moment_arm,
+                                    const void *surface_element_start, void *forces_torques_out, void *stream);
+
+/* ------------------------------------------------------------------------ */
 /* Fused passes of the 3-D Navier-Stokes step (simulator-level path).         */
 /* Vector fields (3, nz, ny, nx) with unit x-stride; outputs must not alias   */
 /* inputs (neighbouring cells are read).                                      */

@@ -155,6 +155,9 @@ _HANDLE_SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     # rigid-body forcing grids
     "sopht_rigid_forcing_grid_kinematics": (ctypes.c_int, [_I, _F, _F, _F, _F, _PD, _PD, _PD, _PD, _P]),
     "sopht_rigid_forcing_grid_force_sums": (ctypes.c_int, [_I, _I, _F, _F, _P, _P]),
+    "sopht_rod_state_doubles": (ctypes.c_int64, [ctypes.c_int64]),
+    "sopht_rod_forcing_grid_kinematics": (ctypes.c_int, [_I, _I, ctypes.c_int64, _P, _F, _F, _F, _P, _P, _P, _P]),
+    "sopht_rod_forcing_grid_transfer": (ctypes.c_int, [_I, _I, _I, ctypes.c_int64, _P, _F, _F, _P, _P, _P]),
     # peer-memory arena (halo exchange / barrier over NVLink)
     "sopht_peer_arena_create": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.c_size_t, _I, _I, _P]),
     "sopht_peer_arena_open": (ctypes.c_int, [_P, _P]),

@@ -204,6 +204,53 @@ class OpenEndCircularCylinderForcingGrid(ThreeDimensionalRigidBodyForcingGrid):
                    self.rigid_body.length / self.num_forcing_points_along_length)
 
 
+class RectangularPlane:
+    """derived_rigid_bodies.py:12-69: a rigid rectangle with imposed motion (its dynamics are not tracked): directors
+    (tangent along the length, normal x tangent, normal), centre at `origin`, zero velocity and angular velocity."""
+
+    def __init__(self, origin: np.ndarray, plane_normal: np.ndarray, plane_tangent_along_length: np.ndarray,
+                 plane_length: float, plane_breadth: float) -> None:
+        logger.warning("Initialising rectangular plane object: tracking its dynamics in pyelastica is not supported, "
+                       "do not add the plane to the pyelastica simulator!")
+        self.n_elems = 1
+        self.length = plane_length
+        self.breadth = plane_breadth
+        normal = np.asarray(plane_normal, dtype=np.float64).reshape(3, 1)
+        tangent = np.asarray(plane_tangent_along_length, dtype=np.float64).reshape(3, 1)
+        binormal = np.cross(normal, tangent, axis=0)
+        self.director_collection = np.zeros((3, 3, 1))
+        self.director_collection[0, ...] = tangent / np.linalg.norm(tangent)
+        self.director_collection[1, ...] = binormal / np.linalg.norm(binormal)
+        self.director_collection[2, ...] = normal / np.linalg.norm(normal)
+        self.position_collection = np.asarray(origin, dtype=np.float64).reshape(3, 1)
+        self.velocity_collection = np.zeros((3, 1))
+        self.omega_collection = np.zeros((3, 1))
+
+
+class RectangularPlaneForcingGrid(ThreeDimensionalRigidBodyForcingGrid):
+    """rigid_body_forcing_grids.py:303-351: a length x breadth lattice in the plane's d1-d2 frame."""
+
+    def __init__(self, grid_dim: int, rigid_body: Any, num_forcing_points_along_length: int) -> None:
+        self.num_forcing_points_along_length = num_forcing_points_along_length
+        self.num_forcing_points_along_breadth = int(
+            num_forcing_points_along_length * rigid_body.breadth / rigid_body.length)
+        self.grid_spacing = rigid_body.length / self.num_forcing_points_along_length
+        n = self.num_forcing_points_along_length * self.num_forcing_points_along_breadth
+        super().__init__(grid_dim=grid_dim, num_lag_nodes=n, rigid_body=rigid_body)
+        along_length = np.linspace(-0.5 * rigid_body.length, 0.5 * rigid_body.length,
+                                   self.num_forcing_points_along_length)
+        along_breadth = np.linspace(-0.5 * rigid_body.breadth, 0.5 * rigid_body.breadth,
+                                    self.num_forcing_points_along_breadth)
+        length_grid, breadth_grid = np.meshgrid(along_length, along_breadth)
+        local = np.stack([length_grid.reshape(-1), breadth_grid.reshape(-1), np.zeros(n)])
+        self.local_frame_relative_position_field[...] = torch.from_numpy(local).to(self.position_field.device)
+        self.compute_lag_grid_position_field()
+        self.compute_lag_grid_velocity_field()
+
+    def get_maximum_lagrangian_grid_spacing(self) -> float:
+        return self.grid_spacing
+
+
 class SphereForcingGrid(ThreeDimensionalRigidBodyForcingGrid):
     """rigid_body_forcing_grids.py:236-300: latitude rings with equal point density; the local frame is redundant
     for a sphere, positions are centre + the stored global-frame offsets (:291-300)."""

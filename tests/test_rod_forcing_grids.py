@@ -293,7 +293,7 @@ def test_cuda_nodal_and_element_centric_grids(grid_dim, n_elems):
     np.testing.assert_allclose(_np(grid.velocity_field), rod.velocity_collection[:grid_dim])
     forces, torques = _transfer(grid, n_elems, np.tile(uniform, (1, n_elems + 1)))
     _check_nodal_transfer(rod, grid_dim, forces, torques)
-    assert grid.get_maximum_lagrangian_grid_spacing() == rod.lengths[0]
+    assert grid.get_maximum_lagrangian_grid_spacing() == np.amax(rod.lengths)
 
     grid = CosseratRodElementCentricForcingGrid(grid_dim=grid_dim, cosserat_rod=rod)
     assert grid.cosserat_rod is rod and grid.num_lag_nodes == n_elems
@@ -302,7 +302,7 @@ def test_cuda_nodal_and_element_centric_grids(grid_dim, n_elems):
     forces, torques = _transfer(grid, n_elems, np.tile(uniform, (1, n_elems)))
     _check_half_weighted_forces(forces, grid_dim, uniform, per_element=1)
     np.testing.assert_allclose(torques, 0.0)
-    assert grid.get_maximum_lagrangian_grid_spacing() == rod.lengths[0]
+    assert grid.get_maximum_lagrangian_grid_spacing() == np.amax(rod.lengths)
 
 
 @pytest.mark.gpu
@@ -326,7 +326,7 @@ def test_cuda_edge_grid(n_elems):
     forces, torques = _transfer(grid, n_elems, np.tile(uniform, (1, 3 * n_elems)))
     _check_half_weighted_forces(forces, 2, uniform, per_element=3)
     np.testing.assert_allclose(torques, 0.0, atol=1e-15)
-    assert grid.get_maximum_lagrangian_grid_spacing() == rod.lengths[0]
+    assert grid.get_maximum_lagrangian_grid_spacing() == np.amax(rod.lengths)
 
 
 @pytest.mark.gpu
@@ -351,7 +351,7 @@ def test_cuda_surface_grid(n_elems, density, taper, with_cap):
     uniform = np.array([[1.0], [2.0], [3.0]])
     forces, torques = _transfer(grid, n_elems, np.tile(uniform, (1, grid.num_lag_nodes)))
     _check_surface_uniform_transfer(counts, forces, torques)
-    spacing = max(rod.lengths[0], np.max(radius) * (2 * np.pi / density))
+    spacing = max(np.amax(rod.lengths), np.max(radius) * (2 * np.pi / density))
     np.testing.assert_allclose(grid.get_maximum_lagrangian_grid_spacing(), spacing)
 
 

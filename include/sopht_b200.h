@@ -280,6 +280,15 @@ int sopht_poisson_create(sopht_poisson_t *handle, int dtype, int dim, int nz, in
                          double x_range, double dx, const double *mz, const double *my,
                          const double *mx, double origin_value, int flags, void *stream);
 
+/* Handle for -laplacian(solution) = rhs with homogeneous Neumann conditions on all walls of the cell-centred grid
+ * (second-order three-point Laplacian with mirror ghost cells), the mean mode of the solution set to zero: the
+ * reference's fast-diagonalisation solver in closed form (DCT-II eigenbasis -> mirror extension + FFT). The handle is
+ * used with sopht_poisson_solve / sopht_poisson_path / sopht_poisson_destroy; sopht_poisson_green_hat returns NULL.
+ * ref: poisson_solver_3d/FastDiagPoissonSolver3D.py:15-181 (ctor, solve), :183-208 (vector_field_solve),
+ *      poisson_solver_2d/FastDiagPoissonSolver2D.py:13-119 */
+int sopht_poisson_neumann_create(sopht_poisson_t *handle, int dtype, int dim, int nz, int ny, int nx, double dx,
+                                 void *stream);
+
 /* -laplacian(solution) = rhs on the unbounded domain. Fields: scalar grid fields, or vector fields
  * with a leading component axis (each component solved independently).
  * ref: UnboundedPoissonSolverPYFFTW3D.py:111-172 (solve, vector_field_solve),

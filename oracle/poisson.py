@@ -84,3 +84,45 @@ class UnboundedPoissonSolver2D:
         spec = rfftn(buf, workers=self.workers)
         spec = spec * self.fourier_greens_function_times_dx_squared
         solution_field[...] = irfftn(spec, s=buf.shape, workers=self.workers)[: self.ny, : self.nx]
+
+
+class FastDiagPoissonSolver:
+    """Restatement of FastDiagPoissonSolver{2,3}D (poisson_solver_3d/FastDiagPoissonSolver3D.py:15-181,
+    poisson_solver_2d/FastDiagPoissonSolver2D.py:13-119), homogeneous Neumann walls: per axis the matrix
+    tridiag(-1, 2, -1) / dx^2 with both corner entries 1 / dx^2 (:51-100), its eigen-decomposition sorted by decreasing
+    eigenvalue (:108-133), the mean mode's eigenvalue set to inf (:143-146), then forward transform with V^-1 along
+    every axis, division by the eigenvalue sums, backward transform with V (:150-181). Pinned against the reference
+    classes themselves, run in the build container (tests/golden/fastdiag_*.npz)."""
+
+    def __init__(self, grid_size, dx, real_t=np.float64):
+        self.grid_size = tuple(grid_size)  # (nz, ny, nx) or (ny, nx)
+        self.real_t = real_t
+        inv_dx2 = real_t(1 / dx / dx)
+        self.eig_vecs, self.inv_eig_vecs, vals = [], [], []
+        for n in self.grid_size:
+            mat = (2.0 * np.eye(n) - np.eye(n, k=1) - np.eye(n, k=-1)).astype(real_t) * inv_dx2
+            mat[0, 0] = inv_dx2
+            mat[-1, -1] = inv_dx2
+            w, v = np.linalg.eig(mat)
+            order = w.argsort()[::-1]
+            self.eig_vecs.append(v[:, order])
+            self.inv_eig_vecs.append(np.linalg.inv(v[:, order]))
+            vals.append(w[order])
+        dim = len(self.grid_size)
+        total = sum(w.reshape([-1 if a == d else 1 for a in range(dim)]) for d, w in enumerate(vals))
+        total = np.array(np.broadcast_to(total, self.grid_size))
+        total[(-1,) * dim] = np.inf
+        self.inv_eig_val_matrix = (real_t(1) / total).astype(real_t)
+
+    def _apply(self, mats, field):
+        for axis, m in enumerate(mats):
+            field = np.moveaxis(np.tensordot(m, field, axes=(1, axis)), 0, axis)
+        return field
+
+    def solve(self, solution_field, rhs_field):
+        spectral = self._apply(self.inv_eig_vecs, rhs_field) * self.inv_eig_val_matrix
+        solution_field[...] = self._apply(self.eig_vecs, spectral)
+
+    def vector_field_solve(self, solution_vector_field, rhs_vector_field):
+        for c in range(len(self.grid_size)):
+            self.solve(solution_vector_field[c], rhs_vector_field[c])

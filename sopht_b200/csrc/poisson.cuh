@@ -33,4 +33,8 @@ bool pow2_poisson_eligible(int dtype, int dim, int nz, int ny, int nx);
 PoissonImpl* make_pow2_poisson(int nz, int ny, int nx, double dx, const double* mz, const double* my,
                                const double* mx, double origin, cudaStream_t st, int* rc);
 
+// Homogeneous Neumann walls on the cell-centred grid (the reference's FastDiagPoissonSolver{2,3}D): mirror
+// extension + periodic three-point symbol (poisson_neumann.cu)
+PoissonImpl* make_neumann_poisson(int dtype, int dim, int nz, int ny, int nx, double dx, cudaStream_t st, int* rc);
+
 }  // namespace sopht

@@ -185,3 +185,73 @@ class UnboundedPoissonSolverPYFFTW2D(_UnboundedPoissonSolverBase):
     @property
     def fourier_greens_function_times_dx_squared(self) -> torch.Tensor:
         return self._greens_function_hat()
+
+
+class _FastDiagPoissonSolverBase(_UnboundedPoissonSolverBase):
+    """Homogeneous-Neumann Poisson solve behind the same handle type (sopht_poisson_neumann_create). The reference
+    diagonalises tridiag(-1, 2, -1) / dx^2 (corner entries 1 / dx^2) per axis with numpy.linalg.eig and applies
+    V diag(1 / lambda) V^-1 as dense tensordots; that product does not depend on the eigenvector scaling or order, and
+    its closed form (DCT-II basis) is evaluated here as a mirror extension + FFT, so the `eig_vecs_*` /
+    `inv_of_eig_vecs_*` / `inv_eig_val_matrix` / `spectral_field_buffer` arrays of the reference do not exist."""
+
+    def _create_neumann(self) -> None:
+        if not torch.cuda.is_available():
+            msg = "sopht_b200 Poisson solver needs a CUDA device (no CPU fallback)"
+            raise _lib.SophtLibraryError(msg)
+        lib = _lib.load()
+        dt = _lib.dtype_code(self.real_t)
+        handle = ctypes.c_void_p()
+        nz = self.grid_size_z if self._dim == 3 else 1
+        _lib.check(lib.sopht_poisson_neumann_create(
+            ctypes.byref(handle), dt, self._dim, nz, self.grid_size_y, self.grid_size_x, float(self.dx),
+            _lib.current_stream()))
+        self._handle = handle
+        self._dt = dt
+        self.path = lib.sopht_poisson_path(handle).decode()
+
+    def solve(self, solution_field: Any, rhs_field: Any) -> None:
+        """Solve -del^2(solution_field) = rhs_field with zero normal derivative on every wall; the mean of the
+        solution is zero (the reference drops the null mode, FastDiagPoissonSolver3D.py:143-146)."""
+        self._solve(solution_field, rhs_field)
+
+
+class FastDiagPoissonSolver3D(_FastDiagPoissonSolverBase):
+    """FastDiagPoissonSolver3D.py:12-208 (same ctor, `solve`, `vector_field_solve`)."""
+
+    _dim = 3
+
+    def __init__(self, grid_size_z: int, grid_size_y: int, grid_size_x: int, dx: float, real_t: type = np.float64,
+                 bc_type: str = "homogenous_neumann_along_xyz") -> None:
+        if bc_type != "homogenous_neumann_along_xyz":
+            msg = f"unsupported bc_type {bc_type!r}: only 'homogenous_neumann_along_xyz' is defined"
+            raise ValueError(msg)
+        self.dx = dx
+        self.grid_size_z = grid_size_z
+        self.grid_size_y = grid_size_y
+        self.grid_size_x = grid_size_x
+        self.real_t = real_t
+        self.bc_type = bc_type
+        self.x_axis_idx, self.y_axis_idx, self.z_axis_idx = 0, 1, 2
+        self._create_neumann()
+
+    def vector_field_solve(self, solution_vector_field: Any, rhs_vector_field: Any) -> None:
+        """Three component solves (:183-208)."""
+        self._solve(solution_vector_field, rhs_vector_field)
+
+
+class FastDiagPoissonSolver2D(_FastDiagPoissonSolverBase):
+    """FastDiagPoissonSolver2D.py:10-119 (same ctor and `solve`)."""
+
+    _dim = 2
+
+    def __init__(self, grid_size_y: int, grid_size_x: int, dx: float, real_t: type = np.float64,
+                 bc_type: str = "homogenous_neumann_along_xy") -> None:
+        if bc_type != "homogenous_neumann_along_xy":
+            msg = f"unsupported bc_type {bc_type!r}: only 'homogenous_neumann_along_xy' is defined"
+            raise ValueError(msg)
+        self.dx = dx
+        self.grid_size_y = grid_size_y
+        self.grid_size_x = grid_size_x
+        self.real_t = real_t
+        self.bc_type = bc_type
+        self._create_neumann()

@@ -97,10 +97,6 @@ class UnboundedNavierStokesFlowSimulator3D(FlowSimulator):
         if poisson_solver_type not in ["greens_function_convolution", "fast_diagonalisation"]:
             msg = "Invalid Poisson solver type given"
             raise ValueError(msg)
-        if poisson_solver_type == "fast_diagonalisation":
-            msg = ("fast_diagonalisation (dense eigen-transform Neumann solver) is outside the "
-                   "FFT hot path this library implements (SURVEY.md §2 row 5)")
-            raise NotImplementedError(msg)
         self.step_mode = kwargs.get("step_mode", "auto")
         if self.step_mode not in ("auto", "fused", "unfused"):
             msg = "step_mode must be 'auto', 'fused' or 'unfused'"
@@ -126,9 +122,14 @@ class UnboundedNavierStokesFlowSimulator3D(FlowSimulator):
         self._diffusion_timestep = spne.gen_diffusion_timestep_euler_forward_pyst_kernel_3d(
             real_t=rt, fixed_grid_size=gs, num_threads=nt, field_type="vector")
         nz, ny, nx = gs
-        self._unbounded_poisson_solver = spne.UnboundedPoissonSolverPYFFTW3D(
-            grid_size_z=nz, grid_size_y=ny, grid_size_x=nx, x_range=self.x_range, real_t=rt,
-            num_threads=nt, flags=self._poisson_flags)
+        if self.poisson_solver_type == "greens_function_convolution":
+            self._unbounded_poisson_solver = spne.UnboundedPoissonSolverPYFFTW3D(
+                grid_size_z=nz, grid_size_y=ny, grid_size_x=nx, x_range=self.x_range, real_t=rt,
+                num_threads=nt, flags=self._poisson_flags)
+        else:  # "fast_diagonalisation": Neumann walls (navier_stokes_flow_simulators.py:349-358)
+            self._unbounded_poisson_solver = spne.FastDiagPoissonSolver3D(
+                grid_size_z=nz, grid_size_y=ny, grid_size_x=nx, dx=self.dx, real_t=rt,
+                bc_type="homogenous_neumann_along_xyz")
         self._curl = spne.gen_curl_pyst_kernel_3d(real_t=rt, num_threads=nt, fixed_grid_size=gs)
         self._penalise_field_towards_boundary = spne.gen_penalise_field_boundary_pyst_kernel_3d(
             width=self.penalty_zone_width, dx=self.dx,

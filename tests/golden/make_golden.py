@@ -1,6 +1,6 @@
 """Generate the golden fixtures in tests/golden/*.npz FROM THE REFERENCE (run in the build container only).
 
-    NUMBA_CACHE_DIR=/tmp/numba_cache python tests/golden/make_golden.py [/root/reference]
+    NUMBA_CACHE_DIR=/tmp/numba_cache python tests/golden/make_golden.py [/root/reference [fastdiag]]
 
 What is executed:
   * stencils / Poisson: the numpy reference functions and seeded ``*Solution`` classes that live inside
@@ -10,6 +10,7 @@ What is executed:
     none of the stubbed code is executed, only the pure-numpy references are.
   * immersed boundary: the reference's OWN implementation (numba) —
     EulerianLagrangianGridCommunicator{2,3}D and VirtualBoundaryForcing — is run on seeded inputs.
+  * Neumann (fast-diagonalisation) Poisson: the reference's OWN FastDiagPoissonSolver{2,3}D (numpy + scipy.sparse).
 Every fixture stores inputs and expected outputs; tests/test_oracle_golden.py pins oracle/ against them
 and the gpu tests pin the CUDA path against them. /root/reference is NOT needed to run the tests.
 """
@@ -282,10 +283,44 @@ def ib_goldens():
         _save(f"ib_{precision}", out)
 
 
+def fastdiag_goldens():
+    """Run the reference's OWN FastDiagPoissonSolver{2,3}D (numpy / scipy.sparse only) on seeded right-hand sides:
+    non-cubic grids, one zero-mean and one general rhs, scalar and vector solves."""
+    from sopht.numeric.eulerian_grid_ops.poisson_solver_2d.FastDiagPoissonSolver2D import FastDiagPoissonSolver2D
+    from sopht.numeric.eulerian_grid_ops.poisson_solver_3d.FastDiagPoissonSolver3D import FastDiagPoissonSolver3D
+
+    for precision in ("single", "double"):
+        real_t = np.float32 if precision == "single" else np.float64
+        rng = np.random.default_rng(SEED)
+        out = {}
+        nz, ny, nx = 12, 10, 16
+        dx = real_t(1.0 / nx)
+        solver = FastDiagPoissonSolver3D(grid_size_z=nz, grid_size_y=ny, grid_size_x=nx, dx=dx, real_t=real_t)
+        rhs = rng.standard_normal((3, nz, ny, nx)).astype(real_t)
+        rhs[1] -= rhs[1].mean()
+        sol = np.zeros_like(rhs)
+        solver.vector_field_solve(solution_vector_field=sol, rhs_vector_field=rhs)
+        scalar = np.zeros((nz, ny, nx), dtype=real_t)
+        solver.solve(solution_field=scalar, rhs_field=rhs[2])
+        out["neumann3d"] = {"dx": np.asarray(dx), "rhs": rhs, "solution": sol, "scalar_solution_of_rhs2": scalar}
+        ny, nx = 14, 24
+        dx = real_t(1.0 / nx)
+        solver2 = FastDiagPoissonSolver2D(grid_size_y=ny, grid_size_x=nx, dx=dx, real_t=real_t)
+        rhs2 = rng.standard_normal((ny, nx)).astype(real_t)
+        sol2 = np.zeros_like(rhs2)
+        solver2.solve(solution_field=sol2, rhs_field=rhs2)
+        out["neumann2d"] = {"dx": np.asarray(dx), "rhs": rhs2, "solution": sol2}
+        _save(f"fastdiag_{precision}", out)
+
+
 if __name__ == "__main__":
     os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/numba_cache")
     _setup_imports()
+    if len(sys.argv) > 2 and sys.argv[2] == "fastdiag":  # regenerate this fixture only
+        fastdiag_goldens()
+        sys.exit(0)
     stencil_goldens(SOLUTION_CASES_3D, "stencils3d")
     stencil_goldens(SOLUTION_CASES_2D, "stencils2d")
     poisson_goldens()
     ib_goldens()
+    fastdiag_goldens()

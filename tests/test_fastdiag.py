@@ -1,0 +1,168 @@
+"""Neumann (fast-diagonalisation) Poisson solver.
+
+Fixtures: the reference's own FastDiagPoissonSolver{2,3}D run in the build container (tests/golden/make_golden.py ->
+fastdiag_*.npz). CPU: the oracle restatement against them, and a numpy emulation of the algorithm the CUDA path uses
+(mirror extension + periodic three-point symbol) against them. GPU: the CUDA classes through the C ABI against the
+fixtures, against the oracle on other sizes, and residual / mean properties at a BASELINE-size grid."""
+
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL = {"single": 1e-5, "double": 1e-12}  # north_star: per-kernel relative L2 error
+
+
+def _golden(precision):
+    z = np.load(os.path.join(GOLDEN, f"fastdiag_{precision}.npz"))
+    return {k: z[k] for k in z.files}
+
+
+def _rel_l2(a, b):
+    return float(np.linalg.norm((np.asarray(a, dtype=np.float64) - b).ravel()) / np.linalg.norm(np.ravel(b)))
+
+
+def _mirror_fft_solve(rhs, dx):
+    """numpy emulation of csrc/poisson_neumann.cu (float64): even extension about every wall, periodic solve with the
+    three-point symbol, mean mode dropped."""
+    ext = rhs.astype(np.float64)
+    for axis in range(rhs.ndim):
+        ext = np.concatenate([ext, np.flip(ext, axis=axis)], axis=axis)
+    spec = np.fft.fftn(ext)
+    lam = np.zeros(ext.shape)
+    for axis, n2 in enumerate(ext.shape):
+        k = np.arange(n2).reshape([-1 if a == axis else 1 for a in range(rhs.ndim)])
+        lam = lam + 4.0 * np.sin(np.pi * k / n2) ** 2 / (dx * dx)
+    lam[(0,) * rhs.ndim] = np.inf
+    sol = np.fft.ifftn(spec / lam).real
+    return sol[tuple(slice(0, n) for n in rhs.shape)]
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_oracle_matches_reference_fixtures(precision):
+    from oracle.poisson import FastDiagPoissonSolver
+
+    g = _golden(precision)
+    real_t = np.float32 if precision == "single" else np.float64
+    tol = 2e-4 if precision == "single" else 1e-10  # two float32 eigen-decompositions differ by their conditioning
+    rhs = g["neumann3d/rhs"]
+    solver = FastDiagPoissonSolver(rhs.shape[1:], g["neumann3d/dx"], real_t)
+    sol = np.zeros_like(rhs)
+    solver.vector_field_solve(sol, rhs)
+    assert _rel_l2(sol, g["neumann3d/solution"]) < tol
+    rhs2 = g["neumann2d/rhs"]
+    sol2 = np.zeros_like(rhs2)
+    FastDiagPoissonSolver(rhs2.shape, g["neumann2d/dx"], real_t).solve(sol2, rhs2)
+    assert _rel_l2(sol2, g["neumann2d/solution"]) < tol
+
+
+def test_mirror_fft_algorithm_matches_reference_fixtures():
+    """The closed form the CUDA path evaluates is the reference's dense eigen-solve (double-precision fixtures)."""
+    g = _golden("double")
+    for c in range(3):
+        sol = _mirror_fft_solve(g["neumann3d/rhs"][c], float(g["neumann3d/dx"]))
+        assert _rel_l2(sol, g["neumann3d/solution"][c]) < 1e-11
+    np.testing.assert_allclose(g["neumann3d/scalar_solution_of_rhs2"], g["neumann3d/solution"][2], rtol=0, atol=1e-12)
+    sol2 = _mirror_fft_solve(g["neumann2d/rhs"], float(g["neumann2d/dx"]))
+    assert _rel_l2(sol2, g["neumann2d/solution"]) < 1e-11
+    assert abs(sol2.mean()) < 1e-13  # the null (mean) mode is dropped
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["single", "double"])
+def test_cuda_fastdiag_matches_reference_fixtures(precision):
+    import torch
+
+    import sopht_b200.numeric.eulerian_grid_ops as spne
+
+    g = _golden(precision)
+    real_t = np.float32 if precision == "single" else np.float64
+    # fp32: the fixture itself carries the rounding of the reference's float32 eigen-decomposition, so it is compared
+    # at the float64 fixture's level of agreement with it; the 1e-5 bar is checked against the double fixture below
+    tol = 2e-4 if precision == "single" else TOL["double"]
+    rhs = torch.from_numpy(g["neumann3d/rhs"]).cuda()
+    nz, ny, nx = rhs.shape[1:]
+    solver = spne.FastDiagPoissonSolver3D(grid_size_z=nz, grid_size_y=ny, grid_size_x=nx,
+                                          dx=real_t(g["neumann3d/dx"]), real_t=real_t)
+    assert solver.path == "neumann_mirror_fft"
+    sol = torch.zeros_like(rhs)
+    solver.vector_field_solve(solution_vector_field=sol, rhs_vector_field=rhs)
+    assert _rel_l2(sol.cpu().numpy(), g["neumann3d/solution"]) < tol
+    scalar = torch.zeros_like(rhs[2])
+    solver.solve(solution_field=scalar, rhs_field=rhs[2])  # strided component view in, contiguous out
+    assert _rel_l2(scalar.cpu().numpy(), g["neumann3d/scalar_solution_of_rhs2"]) < tol
+    # numpy arrays are staged through the device like everywhere else in the package
+    sol_np = np.zeros_like(g["neumann3d/rhs"][0])
+    solver.solve(solution_field=sol_np, rhs_field=g["neumann3d/rhs"][0])
+    assert _rel_l2(sol_np, g["neumann3d/solution"][0]) < tol
+
+    rhs2 = torch.from_numpy(g["neumann2d/rhs"]).cuda()
+    solver2 = spne.FastDiagPoissonSolver2D(grid_size_y=rhs2.shape[0], grid_size_x=rhs2.shape[1],
+                                           dx=real_t(g["neumann2d/dx"]), real_t=real_t)
+    sol2 = torch.zeros_like(rhs2)
+    solver2.solve(solution_field=sol2, rhs_field=rhs2)
+    assert _rel_l2(sol2.cpu().numpy(), g["neumann2d/solution"]) < tol
+    if precision == "single":  # fp32 CUDA path vs the double-precision reference run on the same rhs values
+        gd = _golden("double")
+        assert np.array_equal(gd["neumann2d/rhs"].astype(np.float32), g["neumann2d/rhs"])
+        assert _rel_l2(sol2.cpu().numpy(), gd["neumann2d/solution"]) < TOL["single"]
+        assert _rel_l2(sol.cpu().numpy(), gd["neumann3d/solution"]) < TOL["single"]
+    with pytest.raises(ValueError, match="bc_type"):
+        spne.FastDiagPoissonSolver3D(grid_size_z=4, grid_size_y=4, grid_size_x=4, dx=0.25, bc_type="periodic")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("grid", [(17, 19, 23), (16, 16, 16), (9, 30)])
+def test_cuda_fastdiag_matches_oracle(precision, grid):
+    import torch
+
+    import sopht_b200.numeric.eulerian_grid_ops as spne
+    from oracle.poisson import FastDiagPoissonSolver
+
+    real_t = np.float32 if precision == "single" else np.float64
+    rng = np.random.default_rng(7)
+    dx = 1.0 / grid[-1]
+    rhs = rng.standard_normal(grid).astype(real_t)
+    ref = np.zeros(grid)
+    FastDiagPoissonSolver(grid, dx, np.float64).solve(ref, rhs.astype(np.float64))
+    if len(grid) == 3:
+        solver = spne.FastDiagPoissonSolver3D(*grid, dx=real_t(dx), real_t=real_t)
+    else:
+        solver = spne.FastDiagPoissonSolver2D(*grid, dx=real_t(dx), real_t=real_t)
+    sol = torch.zeros(grid, dtype=torch.float32 if precision == "single" else torch.float64, device="cuda")
+    solver.solve(solution_field=sol, rhs_field=torch.from_numpy(rhs).cuda())
+    assert _rel_l2(sol.cpu().numpy(), ref) < TOL[precision]
+
+
+@pytest.mark.gpu
+def test_cuda_fastdiag_residual_at_baseline_size():
+    """128 x 128 x 256 (BASELINE config 2): -Lap_neumann(solution) reproduces the zero-mean rhs, the solution has no
+    mean, and the 3-D simulator steps with poisson_solver_type='fast_diagonalisation'."""
+    import torch
+
+    import sopht_b200.numeric.eulerian_grid_ops as spne
+    from sopht_b200.simulator import UnboundedNavierStokesFlowSimulator3D
+
+    grid = (128, 128, 256)
+    dx = 1.0 / 256
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    rhs = torch.randn(grid, device="cuda", dtype=torch.float64, generator=gen)
+    rhs -= rhs.mean()
+    solver = spne.FastDiagPoissonSolver3D(*grid, dx=dx, real_t=np.float64)
+    sol = torch.zeros_like(rhs)
+    solver.solve(solution_field=sol, rhs_field=rhs)
+    padded = torch.nn.functional.pad(sol[None, None], (1, 1, 1, 1, 1, 1), mode="replicate")[0, 0]
+    lap = (padded[2:, 1:-1, 1:-1] + padded[:-2, 1:-1, 1:-1] + padded[1:-1, 2:, 1:-1] + padded[1:-1, :-2, 1:-1]
+           + padded[1:-1, 1:-1, 2:] + padded[1:-1, 1:-1, :-2] - 6 * sol) / (dx * dx)
+    assert float(torch.linalg.vector_norm(-lap - rhs) / torch.linalg.vector_norm(rhs)) < 1e-10
+    assert abs(float(sol.mean())) < 1e-12 * float(sol.abs().max())
+
+    sim = UnboundedNavierStokesFlowSimulator3D(grid_size=(32, 32, 64), x_range=1.0, kinematic_viscosity=1e-3,
+                                               real_t=np.float32, poisson_solver_type="fast_diagonalisation")
+    z, y, x = (sim.position_field[i] for i in (2, 1, 0))
+    sim.vorticity_field[2] = torch.exp(-((x - 0.5) ** 2 + (y - 0.25) ** 2 + (z - 0.25) ** 2) / 0.01)
+    for _ in range(3):
+        sim.time_step(dt=sim.compute_stable_timestep())
+    assert bool(torch.isfinite(sim.velocity_field).all()) and float(sim.velocity_field.abs().max()) > 0

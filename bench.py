@@ -38,6 +38,11 @@ import numpy as np  # noqa: E402
 
 WORKLOADS = {
     "c2": dict(grid=(128, 128, 256), body="sphere", desc="3D flow past rigid sphere, unbounded Poisson, 128x128x256 fp32"),
+    # the rod is held straight and fixed: 40 elements x 16 surface points = 640 Lagrangian nodes,
+    # order-5 convolution filter of the vorticity every step (flow_past_rod_case.py:94-121, :282-290)
+    "c3": dict(grid=(256, 128, 128), body="rod", x_range=1.8, filter={"order": 5, "type": "convolution"},
+               desc="3D Cosserat rod (straight, fixed) in cross-flow with IB forcing, 256x128x128 fp32, "
+                    "order-5 convolution filter"),
     "u256": dict(grid=(256, 256, 256), body=None, desc="3D unbounded flow step 256^3 fp32"),
     "u512": dict(grid=(512, 512, 512), body=None, desc="3D unbounded flow step 512^3 fp32"),
 }
@@ -62,9 +67,9 @@ X_RANGE = 1.0
 U_INF = (1.0, 0.0, 0.0)
 
 
-def algorithmic_bytes_per_cell(with_forcing: bool) -> int:
-    """SURVEY.md §8(d) / BASELINE.md §2: 3D unbounded NS step, fp32."""
-    return 408 if with_forcing else 384
+def algorithmic_bytes_per_cell(with_forcing: bool, with_filter: bool = False) -> int:
+    """SURVEY.md §8(d) / BASELINE.md §2: 3D unbounded NS step, fp32 (+72 B for the per-direction fused filter)."""
+    return (408 if with_forcing else 384) + (72 if with_filter else 0)
 
 
 # per-launch algorithmic bytes per cell (fp32) of the instrumented kernels: one read of every distinct input
@@ -79,6 +84,9 @@ KERNEL_BYTES_PER_CELL = {
     "poisson.y_inv": 72.0,
     "poisson.x_inv": 36.0,
     "update_vorticity_from_velocity_forcing": 36.0,  # read f(3) + w(3), write w(3)
+    "laplacian_filter.x": 8.0,       # per component launch: one read + one write of a scalar field
+    "laplacian_filter.y": 8.0,
+    "laplacian_filter.z": 8.0,
 }
 
 
@@ -166,6 +174,20 @@ def sphere_lag_grid(n_eq=96, diameter=0.2, centre=(0.25, 0.25, 0.25)):
     return np.concatenate(pts, axis=1)  # (3, N) float64
 
 
+def straight_rod(wl):
+    """The rod of flow_past_rod_case.py:44-48 at rest: 40 elements along -z from (0.2 X, 0.5 Y, 0.75 Z), length 1,
+    diameter Y / 5 (pyelastica attribute names; the elastic solve itself is outside the hot path)."""
+    from sopht_b200.simulator import CosseratRodState
+
+    nz, ny, nx = wl["grid"]
+    x_range = wl.get("x_range", X_RANGE)
+    y_range, z_range = ny / nx * x_range, nz / nx * x_range
+    return CosseratRodState.straight_rod(
+        n_elements=5 * nx // 16, start=np.array([0.2 * x_range, 0.5 * y_range, 0.75 * z_range]),
+        direction=np.array([0.0, 0.0, -1.0]), normal=np.array([0.0, 1.0, 0.0]), base_length=1.0,
+        base_radius=y_range / 10.0)
+
+
 class ClockSampler:
     """Samples SM clock and throttle reasons with NVML while the timed region runs."""
 
@@ -238,10 +260,13 @@ def build_cpu_case(wl, cores):
 
     grid = wl["grid"]
     forcing = wl["body"] is not None
+    x_range = wl.get("x_range", X_RANGE)
+    filt = wl.get("filter")
     sim = oflow.UnboundedNavierStokesFlowSimulator3D(
-        grid_size=grid, x_range=X_RANGE, kinematic_viscosity=NU, real_t=np.float32,
-        with_forcing=forcing, with_free_stream_flow=True, workers=cores)
-    sim.vorticity_field[...] = hill_vortex_vorticity(grid, X_RANGE)
+        grid_size=grid, x_range=x_range, kinematic_viscosity=NU, real_t=np.float32,
+        with_forcing=forcing, with_free_stream_flow=True, workers=cores, filter_vorticity=filt is not None,
+        **({"filter_setting_dict": filt} if filt else {}))
+    sim.vorticity_field[...] = hill_vortex_vorticity(grid, x_range)
     sim._poisson.vector_field_solve(sim.stream_func_field, sim.vorticity_field)
     from oracle import stencils as ost
 
@@ -250,9 +275,19 @@ def build_cpu_case(wl, cores):
     if forcing:
         from oracle import ib as oib
 
-        pos = sphere_lag_grid()
-        ds = np.pi * 0.2 / 96  # ~ lagrangian spacing
-        vb = (oib.VirtualBoundaryForcing(-1.5e5 * ds * ds, -87.5 * ds * ds, 3, sim.dx, pos.shape[1], np.float32),
+        if wl["body"] == "rod":
+            from oracle import forcing_grids as ofg
+
+            rod = straight_rod(wl)
+            points, ratio, angles = ofg.rod_surface_layout(rod, wl["grid"][2] // 8)
+            pos, _, _ = ofg.rod_surface_kinematics(rod, points, ratio, ofg.rod_surface_tables(points, angles)[2])
+            ds = max(np.amax(rod.lengths), np.amax(rod.radius) * 2 * np.pi / (wl["grid"][2] // 8))
+            k, c = -2e4, -1e2  # flow_past_rod_case.py:19-20
+        else:
+            pos = sphere_lag_grid()
+            ds = np.pi * 0.2 / 96  # ~ lagrangian spacing
+            k, c = -1.5e5, -87.5
+        vb = (oib.VirtualBoundaryForcing(k * ds * ds, c * ds * ds, 3, sim.dx, pos.shape[1], np.float32),
               pos, np.zeros_like(pos))
     return sim, vb
 
@@ -325,12 +360,17 @@ def run_ours(args, wl):
 
     grid = global_grid(wl, world)
     forcing = wl["body"] is not None
+    x_range = wl.get("x_range", X_RANGE)
+    filt = wl.get("filter")
+    if world > 1 and (filt or wl["body"] == "rod"):
+        raise SystemExit("workload c3 (rod + filter) is a single-GPU bench line; use c2 / u256 / u512 with --gpus N")
     dt_value = None
     if world == 1:
         sim = UnboundedNavierStokesFlowSimulator3D(
-            grid_size=grid, x_range=X_RANGE, kinematic_viscosity=NU, real_t=np.float32,
-            with_forcing=forcing, with_free_stream_flow=True, step_mode=args.step_mode)
-        sim.vorticity_field[...] = torch.from_numpy(hill_vortex_vorticity(grid, X_RANGE)).cuda()
+            grid_size=grid, x_range=x_range, kinematic_viscosity=NU, real_t=np.float32,
+            with_forcing=forcing, with_free_stream_flow=True, step_mode=args.step_mode,
+            filter_vorticity=filt is not None, **({"filter_setting_dict": filt} if filt else {}))
+        sim.vorticity_field[...] = torch.from_numpy(hill_vortex_vorticity(grid, x_range)).cuda()
         sim._unbounded_poisson_solver.vector_field_solve(
             solution_vector_field=sim.stream_func_field, rhs_vector_field=sim.vorticity_field)
         sim._curl(curl=sim.velocity_field, field=sim.stream_func_field, prefactor=np.float32(0.5 / sim.dx))
@@ -364,7 +404,21 @@ def run_ours(args, wl):
     cells = int(np.prod(grid))
 
     interactor = None
-    if forcing:
+    rod_interactor = None
+    if wl["body"] == "rod":
+        # the reference's own object graph: CosseratRodFlowInteraction owning a surface forcing grid on the device
+        from sopht_b200.simulator import CosseratRodFlowInteraction, CosseratRodSurfaceForcingGrid
+
+        rod = straight_rod(wl)
+        rod_interactor = CosseratRodFlowInteraction(
+            cosserat_rod=rod, eul_grid_forcing_field=sim.eul_grid_forcing_field,
+            eul_grid_velocity_field=sim.velocity_field, virtual_boundary_stiffness_coeff=-2e4,
+            virtual_boundary_damping_coeff=-1e2, dx=sim.dx, grid_dim=3, real_t=np.float32,
+            forcing_grid_cls=CosseratRodSurfaceForcingGrid,
+            surface_grid_density_for_largest_element=grid[2] // 8)
+        n_lag = rod_interactor.forcing_grid.num_lag_nodes
+        rod_state_bytes = rod_interactor.forcing_grid._state_host.numel() * 8
+    elif forcing:
         pos_h = torch.from_numpy(sphere_lag_grid()).pin_memory()
         vel_h = torch.zeros_like(pos_h).pin_memory()
         ds = np.pi * 0.2 / 96
@@ -382,6 +436,9 @@ def run_ours(args, wl):
         force_h = torch.zeros(3, pos_h.shape[1], dtype=torch.float32).pin_memory()
 
     def device_step():
+        if rod_interactor is not None:
+            rod_interactor.time_step(dt)
+            rod_interactor()  # rod state H2D (7 KB), grid kinematics, interpolate / force / spread
         if interactor is not None:
             interactor.time_step(dt)
             interactor.compute_interaction_force_on_eul_and_lag_grid(
@@ -395,6 +452,14 @@ def run_ours(args, wl):
         step_dt = sim.compute_stable_timestep(dt_prefac=0.5)  # device reduction + D2H scalar
         d2h_n = 4
         h2d_n = 0
+        if rod_interactor is not None:
+            # the coupled loop of flow_past_rod_case.py:236-251 with one rod sub-step per flow step: the rod's
+            # forcing hook reads the flow forces / torques back, then the flow interaction spreads the forcing
+            rod_interactor.compute_flow_forces_and_torques()
+            rod_interactor.time_step(step_dt)
+            rod_interactor()
+            h2d_n += 5 * rod_state_bytes  # every grid update / transfer uploads the packed rod state
+            d2h_n += rod_interactor.forcing_grid._out_host.numel() * 8
         if interactor is not None:
             p = pos_h.to("cuda", non_blocking=True)
             v = vel_h.to("cuda", non_blocking=True)
@@ -453,7 +518,7 @@ def run_ours(args, wl):
     _lib.profile_enable(False)
     roof, kernels = roofline_from_report(report, args.steps, cells_local, forcing, peak, peak_src, grid,
                                          side_stream=world == 1 and cells <= 2**25)
-    step_bpc = algorithmic_bytes_per_cell(forcing)
+    step_bpc = algorithmic_bytes_per_cell(forcing, filt is not None)
     whole = step_bpc * cells_local * args.steps / (ms * 1e-3) / 1e9  # per GPU
 
     if rank != 0:
@@ -472,7 +537,7 @@ def run_ours(args, wl):
         "config": {"workload": wl["desc"] + (f", weak-scaled to {world} z-slabs" if world > 1 else ""),
                    "grid": list(grid), "cells_per_gpu": cells_local,
                    "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
-                   "lagrangian_nodes": int(pos_h.shape[1]) if forcing else 0,
+                   "lagrangian_nodes": (n_lag if rod_interactor is not None else int(pos_h.shape[1])) if forcing else 0,
                    "step_mode": sim.step_mode, "poisson_path": sim._unbounded_poisson_solver.path,
                    "l2": "inputs larger than L2: per-GPU working set per step (fields + FFT workspace, "
                          f"{cells_local * 4 * 33 / 1e6:.0f} MB) exceeds the 126 MB L2"},

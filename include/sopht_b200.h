@@ -208,6 +208,16 @@ int sopht_advection_flux_eno3_3d(int dtype, const sopht_field_t *advection_flux,
 int sopht_laplacian_filter_flux_3d(int dtype, const sopht_field_t *filter_flux,
                                    const sopht_field_t *field, int axis, void *stream);
 
+/* The whole "convolution" Laplacian filter of a scalar (nz, ny, nx) or vector (3, nz, ny, nx) field in place: per
+ * component and per direction x, y, z:  f -= M_d^order f,  M_d g = 0.25 (-g[+1] - g[-1] + 2 g) on the ring-1 interior
+ * and 0 on the ring - what the reference's closure computes with 5 + 4 order passes per direction, here one read and
+ * one write per direction (shared-memory line kernels, csrc/filter3d.cu). scratch: one scalar field of the same grid
+ * (the factory's field_buffer), clobbered. Unit x-stride required (SOPHT_ERR_STRIDE otherwise: the caller falls back
+ * to the pass-by-pass composition). filter_order in [1, 64].
+ * ref: stencil_ops_3d/laplacian_filter_3d.py:129-163 (convolution closure), :58-80 (the 1-D stencils) */
+int sopht_laplacian_filter_convolution_3d(int dtype, const sopht_field_t *field, const sopht_field_t *scratch,
+                                          int filter_order, void *stream);
+
 /* sine-ramp penalisation of a `width`-cell ring, applied x then y then z.
  * ramp_{x,y,z}: HOST arrays of 2*width factors each (front ramp then back ramp), in the kernel dtype's
  * value range, precomputed by the caller from the grid coordinates exactly as the reference does.

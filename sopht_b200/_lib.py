@@ -64,6 +64,7 @@ _SIGNATURES: dict[str, list[Any]] = {
     "sopht_vorticity_stretching_flux_3d": [_F, _F, _F, _D],
     "sopht_advection_flux_eno3_3d": [_F, _F, _F, _D],
     "sopht_laplacian_filter_flux_3d": [_F, _F, _I],
+    "sopht_laplacian_filter_convolution_3d": [_F, _F, _I],
     "sopht_penalise_field_boundary_3d": [_F, _I, _PD, _PD, _PD],
     "sopht_penalise_field_boundary_3d_slab": [_F, _I, _PD, _PD, _PD, _I],
     "sopht_diffusion_flux_2d": [_F, _F, _D, _I],

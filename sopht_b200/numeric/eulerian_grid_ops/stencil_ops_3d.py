@@ -499,10 +499,28 @@ def gen_laplacian_filter_kernel_3d(
                 _filter_pass(flux, buf, axis)
             _lib.call("sopht_elementwise_saxpby", dt, f, f, flux, 1.0, -1.0)
 
+    def _fusable(f: torch.Tensor, buf: torch.Tensor) -> bool:
+        # order 0 subtracts whatever the flux buffer holds (reference behaviour): only the pass-by-pass path has it
+        return (1 <= filter_order <= 64 and f.stride(-1) == 1 and buf.stride(-1) == 1 and min(f.shape[-3:]) >= 3
+                and 3 * f.shape[-1] * f.element_size() <= 96 * 1024)  # a row and its two work copies in shared memory
+
+    def _convolution_fused_or_not(f: torch.Tensor, flux: torch.Tensor, buf: torch.Tensor) -> None:
+        """One line kernel per direction (csrc/filter3d.cu) instead of 5 + 4 order passes; f is a scalar field or
+        the whole vector field."""
+        if _fusable(f, buf):
+            _lib.call("sopht_laplacian_filter_convolution_3d", dt, f, buf, filter_order)
+        elif f.dim() == 4:
+            for c in range(3):
+                _convolution(f[c], flux, buf)
+        else:
+            _convolution(f, flux, buf)
+
+    fused_vector_impl = None
     if filter_type == "multiplicative":
         scalar_impl = _multiplicative
     elif filter_type == "convolution":
-        scalar_impl = _convolution
+        scalar_impl = _convolution_fused_or_not
+        fused_vector_impl = _convolution_fused_or_not
     else:
         msg = "Invalid filter type"
         raise ValueError(msg)
@@ -521,6 +539,9 @@ def gen_laplacian_filter_kernel_3d(
             with _lib.Staging() as s:
                 flux, buf = s.out(filter_flux_buffer), s.out(field_buffer)
                 v = s.out(vector_field)
+                if fused_vector_impl is not None:
+                    fused_vector_impl(v, flux, buf)
+                    return
                 for c in range(3):
                     scalar_impl(v[c], flux, buf)
 

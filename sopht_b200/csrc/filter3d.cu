@@ -22,36 +22,102 @@ __device__ __forceinline__ T filter_point(T minus, T centre, T plus) {
   return T(0.25) * (-plus - minus + T(2) * centre);
 }
 
-// ---- x: whole rows, one warp each -----------------------------------------------------------------------
+// ---- x: whole rows in shared memory, one warp per batch of rows --------------------------------------------
+// A warp keeps `rb` rows (about 512 cells) in flight so that short rows still put enough loads on the wire; rows are
+// independent, the batch is just a longer index space with the ring mask applied per row. All components of a vector
+// field go into one launch (in place: a batch is read completely before it is written).
 template <typename T>
 __global__ void __launch_bounds__(256)
-    filter_rows_x_kernel(T* f, int64_t sz, int64_t sy, int nz, int ny, int nx, int order) {
+    filter_rows_x_kernel(T* f, int64_t sc, int64_t sz, int64_t sy, int ncomp, int nz, int ny, int nx, int order,
+                         int rb) {
   extern __shared__ unsigned char filter_smem_raw[];
   T* smem = reinterpret_cast<T*>(filter_smem_raw);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, warps = blockDim.x >> 5;
-  T* orig = smem + (size_t)w * 3 * nx;
-  T* a = orig + nx;
-  T* b = a + nx;
-  const int64_t rows = (int64_t)(nz - 2) * (ny - 2);  // rows on the y / z ring keep their values
-  for (int64_t r = (int64_t)blockIdx.x * warps + w; r < rows; r += (int64_t)gridDim.x * warps) {
-    const int z = 1 + (int)(r / (ny - 2)), y = 1 + (int)(r % (ny - 2));
-    T* row = f + z * sz + y * sy;
-    for (int i = lane; i < nx; i += 32) {
-      const T v = row[i];
+  const int span = rb * nx;
+  T* orig = smem + (size_t)w * 3 * span;
+  T* a = orig + span;
+  T* b = a + span;
+  const int64_t rows_per_comp = (int64_t)(nz - 2) * (ny - 2);  // rows on the y / z ring keep their values
+  const int64_t rows = rows_per_comp * ncomp;
+  const int64_t batches = (rows + rb - 1) / rb;
+  for (int64_t bt = (int64_t)blockIdx.x * warps + w; bt < batches; bt += (int64_t)gridDim.x * warps) {
+    const int64_t r0 = bt * rb;
+    const int nrow = (int)(rows - r0 < rb ? rows - r0 : rb);
+    const int n = nrow * nx;
+    auto row_ptr = [&](int64_t r) -> T* {
+      const int64_t c = r / rows_per_comp, q = r - c * rows_per_comp;
+      return f + c * sc + (1 + q / (ny - 2)) * sz + (1 + q % (ny - 2)) * sy;
+    };
+    for (int i = lane; i < n; i += 32) {
+      const int rr = i / nx;
+      const T v = row_ptr(r0 + rr)[i - rr * nx];
       orig[i] = v;
       a[i] = v;
     }
     __syncwarp();
     for (int m = 0; m < order; ++m) {
-      for (int i = lane; i < nx; i += 32)
-        b[i] = (i >= 1 && i <= nx - 2) ? filter_point(a[i - 1], a[i], a[i + 1]) : T(0);
+      for (int i = lane; i < n; i += 32) {
+        const int col = i % nx;
+        b[i] = (col >= 1 && col <= nx - 2) ? filter_point(a[i - 1], a[i], a[i + 1]) : T(0);
+      }
       __syncwarp();
       T* t = a;
       a = b;
       b = t;
     }
-    for (int i = lane; i < nx; i += 32) row[i] = orig[i] - a[i];
+    for (int i = lane; i < n; i += 32) {
+      const int rr = i / nx;
+      row_ptr(r0 + rr)[i - rr * nx] = orig[i] - a[i];
+    }
     __syncwarp();
+  }
+}
+
+// ---- y / z, orders up to 8: register pipeline marching along the line -----------------------------------------
+// One thread per (x, line, segment): it walks its segment (plus an `K`-cell run-in and run-out) once, keeping the last
+// three values of every intermediate pass and the K + 1 pending originals in registers; pass m at position p - m is
+// formed as soon as pass m - 1 reaches p - m + 1. Loads and stores are coalesced across x; no shared memory, no
+// barriers. Out of place (a segment's run-in cells are another segment's outputs).
+template <typename T, int K>
+__global__ void __launch_bounds__(128)
+    filter_march_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t src_ls, int64_t src_os, int64_t dst_ls,
+                        int64_t dst_os, int line_len, int n_other, int nx, int seg_len) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, o = blockIdx.y;
+  if (x >= nx) return;
+  const int p_begin = blockIdx.z * seg_len;
+  const int p_end = p_begin + seg_len < line_len ? p_begin + seg_len : line_len;
+  const bool line_active = x >= 1 && x <= nx - 2 && o >= 1 && o <= n_other - 2;
+  const T* s = src + o * src_os + x;
+  T* d = dst + o * dst_os + x;
+  if (!line_active) {  // lines on the ring of the other two axes receive no flux
+    for (int p = p_begin; p < p_end; ++p) d[p * dst_ls] = s[p * src_ls];
+    return;
+  }
+  T g[K][3];       // g[m]: pass m at the three newest positions it has reached
+  T pending[K + 1];  // originals of the positions whose result is not out yet
+#pragma unroll
+  for (int m = 0; m < K; ++m) g[m][0] = g[m][1] = g[m][2] = T(0);
+#pragma unroll
+  for (int m = 0; m <= K; ++m) pending[m] = T(0);
+#pragma unroll 6
+  for (int p = p_begin - K; p < p_end + K; ++p) {
+    const T v = (p >= 0 && p < line_len) ? s[p * src_ls] : T(0);
+    g[0][0] = g[0][1], g[0][1] = g[0][2], g[0][2] = v;
+#pragma unroll
+    for (int m = 0; m < K; ++m) pending[m] = pending[m + 1];
+    pending[K] = v;
+    T out = T(0);
+#pragma unroll
+    for (int m = 1; m <= K; ++m) {
+      const int pos = p - m;
+      const T val = (pos >= 1 && pos <= line_len - 2) ? filter_point(g[m - 1][0], g[m - 1][1], g[m - 1][2]) : T(0);
+      if (m < K)
+        g[m][0] = g[m][1], g[m][1] = g[m][2], g[m][2] = val;
+      else
+        out = val;
+    }
+    const int q = p - K;
+    if (q >= p_begin && q < p_end) d[q * dst_ls] = pending[0] - out;
   }
 }
 
@@ -102,45 +168,82 @@ __global__ void __launch_bounds__(256)
 }
 
 template <typename T>
-int filter_component(T* f, int64_t sz, int64_t sy, T* scratch, int64_t tz, int64_t ty_, int nz, int ny, int nx,
-                     int order, cudaStream_t st) {
-  // x, in place
-  {
-    const size_t per_warp = sizeof(T) * 3 * (size_t)nx;
-    int warps = (int)((96 * 1024) / per_warp);
-    if (warps > 8) warps = 8;
-    if (warps < 1) SOPHT_FAIL(SOPHT_ERR_SHAPE, "laplacian filter (fused): rows of %d cells do not fit in shared memory", nx);
-    const size_t smem = per_warp * warps;
-    static bool attr_set = false;
-    if (!attr_set) {
-      SOPHT_CUDA(cudaFuncSetAttribute(filter_rows_x_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr_set = true;
-    }
-    const int64_t rows = (int64_t)(nz - 2) * (ny - 2);
-    int64_t blocks = (rows + warps - 1) / warps;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    SOPHT_PROF("laplacian_filter.x", st);
-    filter_rows_x_kernel<T><<<(int)blocks, 32 * warps, smem, st>>>(f, sz, sy, nz, ny, nx, order);
-    SOPHT_CHECK_LAUNCH();
-  }
-  const size_t smem = sizeof(T) * 3 * 32 * (size_t)(FILTER_SEG + 2 * order);
+int filter_rows_x(T* f, int64_t sc, int64_t sz, int64_t sy, int ncomp, int nz, int ny, int nx, int order,
+                  cudaStream_t st) {
+  int rb = 512 / nx;
+  if (rb < 1) rb = 1;
+  const size_t per_warp = sizeof(T) * 3 * (size_t)nx * rb;
+  int warps = (int)((96 * 1024) / per_warp);
+  if (warps > 8) warps = 8;
+  if (warps < 1) SOPHT_FAIL(SOPHT_ERR_SHAPE, "laplacian filter (fused): rows of %d cells do not fit in shared memory", nx);
+  const size_t smem = per_warp * warps;
   static bool attr_set = false;
   if (!attr_set) {
-    SOPHT_CUDA(cudaFuncSetAttribute(filter_lines_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SOPHT_CUDA(cudaFuncSetAttribute(filter_rows_x_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     attr_set = true;
   }
-  const dim3 block(32, 8);
-  {  // y: lines along y, one plane z per blockIdx.z; f -> scratch
-    const dim3 grid((nx + 31) / 32, (ny + FILTER_SEG - 1) / FILTER_SEG, nz);
-    SOPHT_PROF("laplacian_filter.y", st);
-    filter_lines_kernel<T><<<grid, block, smem, st>>>(f, scratch, sy, sz, ty_, tz, ny, nz, nx, order);
-    SOPHT_CHECK_LAUNCH();
+  const int64_t batches = ((int64_t)(nz - 2) * (ny - 2) * ncomp + rb - 1) / rb;
+  int64_t blocks = (batches + warps - 1) / warps;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  SOPHT_PROF("laplacian_filter.x", st);
+  filter_rows_x_kernel<T><<<(int)blocks, 32 * warps, smem, st>>>(f, sc, sz, sy, ncomp, nz, ny, nx, order, rb);
+  SOPHT_CHECK_LAUNCH();
+  return SOPHT_OK;
+}
+
+template <typename T, int K>
+void launch_march(const T* src, T* dst, int64_t src_ls, int64_t src_os, int64_t dst_ls, int64_t dst_os, int line_len,
+                  int n_other, int nx, cudaStream_t st) {
+  // segments short enough to give every SM a few thousand threads, long enough to amortise the 2 K run-in / run-out
+  int seg = 64;
+  while (seg > 4 * K && (int64_t)nx * n_other * ((line_len + seg - 1) / seg) < (int64_t)148 * 2048 * 2) seg /= 2;
+  const dim3 grid((nx + 127) / 128, n_other, (line_len + seg - 1) / seg);
+  filter_march_kernel<T, K><<<grid, 128, 0, st>>>(src, dst, src_ls, src_os, dst_ls, dst_os, line_len, n_other, nx, seg);
+}
+
+// lines along one strided axis, src -> dst
+template <typename T>
+int filter_lines(const T* src, T* dst, int64_t src_ls, int64_t src_os, int64_t dst_ls, int64_t dst_os, int line_len,
+                 int n_other, int nx, int order, cudaStream_t st) {
+#define MARCH(KK)                                                                                   \
+  case KK:                                                                                          \
+    launch_march<T, KK>(src, dst, src_ls, src_os, dst_ls, dst_os, line_len, n_other, nx, st);       \
+    break;
+  switch (order) {
+    MARCH(1) MARCH(2) MARCH(3) MARCH(4) MARCH(5) MARCH(6) MARCH(7) MARCH(8)
+    default: {  // long filters: shared-memory segments
+      const size_t smem = sizeof(T) * 3 * 32 * (size_t)(FILTER_SEG + 2 * order);
+      static bool attr_set = false;
+      if (!attr_set) {
+        SOPHT_CUDA(cudaFuncSetAttribute(filter_lines_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        160 * 1024));
+        attr_set = true;
+      }
+      const dim3 grid((nx + 31) / 32, (line_len + FILTER_SEG - 1) / FILTER_SEG, n_other);
+      filter_lines_kernel<T><<<grid, dim3(32, 8), smem, st>>>(src, dst, src_ls, src_os, dst_ls, dst_os, line_len,
+                                                             n_other, nx, order);
+    }
   }
-  {  // z: lines along z, one row y per blockIdx.z; scratch -> f
-    const dim3 grid((nx + 31) / 32, (nz + FILTER_SEG - 1) / FILTER_SEG, ny);
-    SOPHT_PROF("laplacian_filter.z", st);
-    filter_lines_kernel<T><<<grid, block, smem, st>>>(scratch, f, tz, ty_, sz, sy, nz, ny, nx, order);
-    SOPHT_CHECK_LAUNCH();
+#undef MARCH
+  SOPHT_CHECK_LAUNCH();
+  return SOPHT_OK;
+}
+
+template <typename T>
+int filter_field(T* f, int64_t sc, int64_t sz, int64_t sy, int ncomp, T* scratch, int64_t tz, int64_t ty_, int nz,
+                 int ny, int nx, int order, cudaStream_t st) {
+  int rc = filter_rows_x<T>(f, sc, sz, sy, ncomp, nz, ny, nx, order, st);  // x, in place, every component
+  if (rc) return rc;
+  for (int c = 0; c < ncomp; ++c) {
+    T* fc = f + c * sc;
+    {  // y: lines along y, the other axis is z; f -> scratch
+      SOPHT_PROF("laplacian_filter.y", st);
+      if ((rc = filter_lines<T>(fc, scratch, sy, sz, ty_, tz, ny, nz, nx, order, st))) return rc;
+    }
+    {  // z: lines along z, the other axis is y; scratch -> f
+      SOPHT_PROF("laplacian_filter.z", st);
+      if ((rc = filter_lines<T>(scratch, fc, tz, ty_, sz, sy, nz, ny, nx, order, st))) return rc;
+    }
   }
   return SOPHT_OK;
 }
@@ -169,17 +272,12 @@ extern "C" int sopht_laplacian_filter_convolution_3d(int dtype, const sopht_fiel
   const int nz = (int)field->shape[o], ny = (int)field->shape[o + 1], nx = (int)field->shape[o + 2];
   if (nz < 3 || ny < 3 || nx < 3) return SOPHT_OK;  // no interior: every flux is zero
   cudaStream_t st = as_stream(stream);
-  for (int c = 0; c < ncomp; ++c) {
-    int rc;
-    if (dtype == SOPHT_F32)
-      rc = filter_component<float>(reinterpret_cast<float*>(field->data) + (o ? c * field->stride[0] : 0),
-                                   field->stride[o], field->stride[o + 1], reinterpret_cast<float*>(scratch->data),
-                                   scratch->stride[0], scratch->stride[1], nz, ny, nx, filter_order, st);
-    else
-      rc = filter_component<double>(reinterpret_cast<double*>(field->data) + (o ? c * field->stride[0] : 0),
-                                    field->stride[o], field->stride[o + 1], reinterpret_cast<double*>(scratch->data),
-                                    scratch->stride[0], scratch->stride[1], nz, ny, nx, filter_order, st);
-    if (rc) return rc;
-  }
-  return SOPHT_OK;
+  const int64_t sc = o ? field->stride[0] : 0;
+  if (dtype == SOPHT_F32)
+    return filter_field<float>(reinterpret_cast<float*>(field->data), sc, field->stride[o], field->stride[o + 1],
+                               ncomp, reinterpret_cast<float*>(scratch->data), scratch->stride[0], scratch->stride[1],
+                               nz, ny, nx, filter_order, st);
+  return filter_field<double>(reinterpret_cast<double*>(field->data), sc, field->stride[o], field->stride[o + 1],
+                              ncomp, reinterpret_cast<double*>(scratch->data), scratch->stride[0], scratch->stride[1],
+                              nz, ny, nx, filter_order, st);
 }

@@ -16,7 +16,7 @@ def _rel_l2(a, b):
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
 @pytest.mark.parametrize("grid", [(17, 19, 23), (70, 9, 33), (5, 131, 64), (3, 3, 3), (66, 65, 40)])
-@pytest.mark.parametrize("order", [1, 2, 5])
+@pytest.mark.parametrize("order", [1, 2, 5, 8, 9])  # <= 8: register pipeline along y / z; 9: shared-memory segments
 def test_fused_convolution_filter_matches_oracle(dtype, grid, order):
     import torch
 

@@ -43,31 +43,33 @@ __global__ void __launch_bounds__(256)
   for (int64_t bt = (int64_t)blockIdx.x * warps + w; bt < batches; bt += (int64_t)gridDim.x * warps) {
     const int64_t r0 = bt * rb;
     const int nrow = (int)(rows - r0 < rb ? rows - r0 : rb);
-    const int n = nrow * nx;
     auto row_ptr = [&](int64_t r) -> T* {
       const int64_t c = r / rows_per_comp, q = r - c * rows_per_comp;
       return f + c * sc + (1 + q / (ny - 2)) * sz + (1 + q % (ny - 2)) * sy;
     };
-    for (int i = lane; i < n; i += 32) {
-      const int rr = i / nx;
-      const T v = row_ptr(r0 + rr)[i - rr * nx];
-      orig[i] = v;
-      a[i] = v;
+    for (int rr = 0; rr < nrow; ++rr) {  // all loads of the batch are issued before anything waits on them
+      const T* row = row_ptr(r0 + rr);
+      for (int i = lane; i < nx; i += 32) {
+        const T v = row[i];
+        orig[rr * nx + i] = v;
+        a[rr * nx + i] = v;
+      }
     }
     __syncwarp();
     for (int m = 0; m < order; ++m) {
-      for (int i = lane; i < n; i += 32) {
-        const int col = i % nx;
-        b[i] = (col >= 1 && col <= nx - 2) ? filter_point(a[i - 1], a[i], a[i + 1]) : T(0);
-      }
+      for (int rr = 0; rr < nrow; ++rr)
+        for (int i = lane; i < nx; i += 32) {
+          const int e = rr * nx + i;
+          b[e] = (i >= 1 && i <= nx - 2) ? filter_point(a[e - 1], a[e], a[e + 1]) : T(0);
+        }
       __syncwarp();
       T* t = a;
       a = b;
       b = t;
     }
-    for (int i = lane; i < n; i += 32) {
-      const int rr = i / nx;
-      row_ptr(r0 + rr)[i - rr * nx] = orig[i] - a[i];
+    for (int rr = 0; rr < nrow; ++rr) {
+      T* row = row_ptr(r0 + rr);
+      for (int i = lane; i < nx; i += 32) row[i] = orig[rr * nx + i] - a[rr * nx + i];
     }
     __syncwarp();
   }

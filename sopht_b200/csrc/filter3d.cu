@@ -22,6 +22,29 @@ __device__ __forceinline__ T filter_point(T minus, T centre, T plus) {
   return T(0.25) * (-plus - minus + T(2) * centre);
 }
 
+// Away from the two ends of a line the masks never act and `order` passes of the three-point stencil collapse into one
+// symmetric (2 order + 1)-tap filter: coefficients of (-1/4, 1/2, -1/4) convolved with itself `order` times, c[j] for
+// offsets +-j. Cells within `order` of a line end see the zeroed ring of the intermediate passes and keep the
+// pass-by-pass evaluation.
+constexpr int FIR_MAX_ORDER = 8;
+struct FirTaps {
+  double c[FIR_MAX_ORDER + 1];
+};
+inline FirTaps fir_taps(int order) {
+  double cur[2 * FIR_MAX_ORDER + 1] = {0.0}, nxt[2 * FIR_MAX_ORDER + 1];
+  cur[FIR_MAX_ORDER] = 1.0;
+  for (int m = 0; m < order; ++m) {
+    for (int j = 0; j <= 2 * FIR_MAX_ORDER; ++j) {
+      const double lo = j > 0 ? cur[j - 1] : 0.0, hi = j < 2 * FIR_MAX_ORDER ? cur[j + 1] : 0.0;
+      nxt[j] = 0.25 * (-hi - lo + 2.0 * cur[j]);
+    }
+    for (int j = 0; j <= 2 * FIR_MAX_ORDER; ++j) cur[j] = nxt[j];
+  }
+  FirTaps t;
+  for (int j = 0; j <= FIR_MAX_ORDER; ++j) t.c[j] = cur[FIR_MAX_ORDER + j];
+  return t;
+}
+
 // ---- x: whole rows in shared memory, one warp per batch of rows --------------------------------------------
 // A warp keeps `rb` rows (about 512 cells) in flight so that short rows still put enough loads on the wire; rows are
 // independent, the batch is just a longer index space with the ring mask applied per row. All components of a vector
@@ -29,7 +52,7 @@ __device__ __forceinline__ T filter_point(T minus, T centre, T plus) {
 template <typename T>
 __global__ void __launch_bounds__(256)
     filter_rows_x_kernel(T* f, int64_t sc, int64_t sz, int64_t sy, int ncomp, int nz, int ny, int nx, int order,
-                         int rb) {
+                         int rb, FirTaps taps) {
   extern __shared__ unsigned char filter_smem_raw[];
   T* smem = reinterpret_cast<T*>(filter_smem_raw);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, warps = blockDim.x >> 5;
@@ -56,12 +79,17 @@ __global__ void __launch_bounds__(256)
       }
     }
     __syncwarp();
+    // pass by pass only where the line ends are felt: the first and last 2 K columns (what is computed there is
+    // right for the outer K columns after K passes); everything else is one (2 K + 1)-tap filter of the originals
+    const bool fir = order <= FIR_MAX_ORDER && nx >= 4 * order;
+    const int wcols = fir ? 4 * order : nx;
     for (int m = 0; m < order; ++m) {
-      for (int rr = 0; rr < nrow; ++rr)
-        for (int i = lane; i < nx; i += 32) {
-          const int e = rr * nx + i;
-          b[e] = (i >= 1 && i <= nx - 2) ? filter_point(a[e - 1], a[e], a[e + 1]) : T(0);
-        }
+      for (int idx = lane; idx < nrow * wcols; idx += 32) {
+        const int rr = idx / wcols, wc = idx - rr * wcols;
+        const int i = (fir && wc >= 2 * order) ? nx - 4 * order + wc : wc;
+        const int e = rr * nx + i;
+        b[e] = (i >= 1 && i <= nx - 2) ? filter_point(a[e - 1], a[e], a[e + 1]) : T(0);
+      }
       __syncwarp();
       T* t = a;
       a = b;
@@ -69,7 +97,17 @@ __global__ void __launch_bounds__(256)
     }
     for (int rr = 0; rr < nrow; ++rr) {
       T* row = row_ptr(r0 + rr);
-      for (int i = lane; i < nx; i += 32) row[i] = orig[rr * nx + i] - a[rr * nx + i];
+      const T* o = orig + rr * nx;
+      for (int i = lane; i < nx; i += 32) {
+        T flux;
+        if (fir && i >= order && i <= nx - 1 - order) {
+          flux = T(taps.c[0]) * o[i];
+          for (int j = 1; j <= order; ++j) flux += T(taps.c[j]) * (o[i - j] + o[i + j]);
+        } else {
+          flux = a[rr * nx + i];
+        }
+        row[i] = o[i] - flux;
+      }
     }
     __syncwarp();
   }
@@ -83,7 +121,7 @@ __global__ void __launch_bounds__(256)
 template <typename T, int K>
 __global__ void __launch_bounds__(128)
     filter_march_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t src_ls, int64_t src_os, int64_t dst_ls,
-                        int64_t dst_os, int line_len, int n_other, int nx, int seg_len) {
+                        int64_t dst_os, int line_len, int n_other, int nx, int seg_len, FirTaps taps) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x, o = blockIdx.y;
   if (x >= nx) return;
   const int p_begin = blockIdx.z * seg_len;
@@ -93,6 +131,26 @@ __global__ void __launch_bounds__(128)
   T* d = dst + o * dst_os + x;
   if (!line_active) {  // lines on the ring of the other two axes receive no flux
     for (int p = p_begin; p < p_end; ++p) d[p * dst_ls] = s[p * src_ls];
+    return;
+  }
+  if (p_begin >= K && p_end <= line_len - K) {
+    // segment away from both line ends (uniform per CTA): sliding window of 2 K + 1 originals, one symmetric filter
+    T w[2 * K + 1];
+    T c[K + 1];
+#pragma unroll
+    for (int j = 0; j <= K; ++j) c[j] = T(taps.c[j]);
+#pragma unroll
+    for (int j = 0; j < 2 * K; ++j) w[j + 1] = s[(p_begin - K + j) * src_ls];
+#pragma unroll(2 * K + 1)
+    for (int q = p_begin; q < p_end; ++q) {
+#pragma unroll
+      for (int j = 0; j < 2 * K; ++j) w[j] = w[j + 1];
+      w[2 * K] = s[(q + K) * src_ls];
+      T flux = c[0] * w[K];
+#pragma unroll
+      for (int j = 1; j <= K; ++j) flux += c[j] * (w[K - j] + w[K + j]);
+      d[q * dst_ls] = w[K] - flux;
+    }
     return;
   }
   T g[K][3];       // g[m]: pass m at the three newest positions it has reached
@@ -188,7 +246,8 @@ int filter_rows_x(T* f, int64_t sc, int64_t sz, int64_t sy, int ncomp, int nz, i
   int64_t blocks = (batches + warps - 1) / warps;
   if (blocks > 148 * 16) blocks = 148 * 16;
   SOPHT_PROF("laplacian_filter.x", st);
-  filter_rows_x_kernel<T><<<(int)blocks, 32 * warps, smem, st>>>(f, sc, sz, sy, ncomp, nz, ny, nx, order, rb);
+  filter_rows_x_kernel<T><<<(int)blocks, 32 * warps, smem, st>>>(f, sc, sz, sy, ncomp, nz, ny, nx, order, rb,
+                                                                fir_taps(order <= FIR_MAX_ORDER ? order : 0));
   SOPHT_CHECK_LAUNCH();
   return SOPHT_OK;
 }
@@ -200,7 +259,8 @@ void launch_march(const T* src, T* dst, int64_t src_ls, int64_t src_os, int64_t 
   int seg = 64;
   while (seg > 4 * K && (int64_t)nx * n_other * ((line_len + seg - 1) / seg) < (int64_t)148 * 2048 * 2) seg /= 2;
   const dim3 grid((nx + 127) / 128, n_other, (line_len + seg - 1) / seg);
-  filter_march_kernel<T, K><<<grid, 128, 0, st>>>(src, dst, src_ls, src_os, dst_ls, dst_os, line_len, n_other, nx, seg);
+  filter_march_kernel<T, K><<<grid, 128, 0, st>>>(src, dst, src_ls, src_os, dst_ls, dst_os, line_len, n_other, nx, seg,
+                                                  fir_taps(K));
 }
 
 // lines along one strided axis, src -> dst

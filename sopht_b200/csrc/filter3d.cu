@@ -49,7 +49,7 @@ inline FirTaps fir_taps(int order) {
 // A warp keeps `rb` rows (about 512 cells) in flight so that short rows still put enough loads on the wire; rows are
 // independent, the batch is just a longer index space with the ring mask applied per row. All components of a vector
 // field go into one launch (in place: a batch is read completely before it is written).
-template <typename T>
+template <typename T, int K>  // K = the order when the one-pass filter applies (1..FIR_MAX_ORDER), 0 = pass by pass only
 __global__ void __launch_bounds__(256)
     filter_rows_x_kernel(T* f, int64_t sc, int64_t sz, int64_t sy, int ncomp, int nz, int ny, int nx, int order,
                          int rb, FirTaps taps) {
@@ -60,6 +60,9 @@ __global__ void __launch_bounds__(256)
   T* orig = smem + (size_t)w * 3 * span;
   T* a = orig + span;
   T* b = a + span;
+  T c[K + 1];
+#pragma unroll
+  for (int j = 0; j <= K; ++j) c[j] = T(taps.c[j]);
   const int64_t rows_per_comp = (int64_t)(nz - 2) * (ny - 2);  // rows on the y / z ring keep their values
   const int64_t rows = rows_per_comp * ncomp;
   const int64_t batches = (rows + rb - 1) / rb;
@@ -70,8 +73,10 @@ __global__ void __launch_bounds__(256)
       const int64_t c = r / rows_per_comp, q = r - c * rows_per_comp;
       return f + c * sc + (1 + q / (ny - 2)) * sz + (1 + q % (ny - 2)) * sy;
     };
+    // lane rr works out where row rr of the batch lives (64-bit divisions: once per row, not once per use)
+    const unsigned long long my_row = lane < nrow ? (unsigned long long)row_ptr(r0 + lane) : 0ull;
     for (int rr = 0; rr < nrow; ++rr) {  // all loads of the batch are issued before anything waits on them
-      const T* row = row_ptr(r0 + rr);
+      const T* row = reinterpret_cast<const T*>(__shfl_sync(0xffffffffu, my_row, rr));
       for (int i = lane; i < nx; i += 32) {
         const T v = row[i];
         orig[rr * nx + i] = v;
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(256)
     __syncwarp();
     // pass by pass only where the line ends are felt: the first and last 2 K columns (what is computed there is
     // right for the outer K columns after K passes); everything else is one (2 K + 1)-tap filter of the originals
-    const bool fir = order <= FIR_MAX_ORDER && nx >= 4 * order;
+    constexpr bool fir = K > 0;  // the host picks K > 0 only when nx >= 4 K
     const int wcols = fir ? 4 * order : nx;
     for (int m = 0; m < order; ++m) {
       for (int idx = lane; idx < nrow * wcols; idx += 32) {
@@ -96,13 +101,14 @@ __global__ void __launch_bounds__(256)
       b = t;
     }
     for (int rr = 0; rr < nrow; ++rr) {
-      T* row = row_ptr(r0 + rr);
+      T* row = reinterpret_cast<T*>(__shfl_sync(0xffffffffu, my_row, rr));
       const T* o = orig + rr * nx;
       for (int i = lane; i < nx; i += 32) {
         T flux;
-        if (fir && i >= order && i <= nx - 1 - order) {
-          flux = T(taps.c[0]) * o[i];
-          for (int j = 1; j <= order; ++j) flux += T(taps.c[j]) * (o[i - j] + o[i + j]);
+        if (fir && i >= K && i <= nx - 1 - K) {
+          flux = c[0] * o[i];
+#pragma unroll
+          for (int j = 1; j <= K; ++j) flux += c[j] * (o[i - j] + o[i + j]);
         } else {
           flux = a[rr * nx + i];
         }
@@ -232,22 +238,33 @@ int filter_rows_x(T* f, int64_t sc, int64_t sz, int64_t sy, int ncomp, int nz, i
                   cudaStream_t st) {
   int rb = 512 / nx;
   if (rb < 1) rb = 1;
+  if (rb > 32) rb = 32;  // one lane per row of the batch holds its address
   const size_t per_warp = sizeof(T) * 3 * (size_t)nx * rb;
   int warps = (int)((96 * 1024) / per_warp);
   if (warps > 8) warps = 8;
   if (warps < 1) SOPHT_FAIL(SOPHT_ERR_SHAPE, "laplacian filter (fused): rows of %d cells do not fit in shared memory", nx);
   const size_t smem = per_warp * warps;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SOPHT_CUDA(cudaFuncSetAttribute(filter_rows_x_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    attr_set = true;
-  }
   const int64_t batches = ((int64_t)(nz - 2) * (ny - 2) * ncomp + rb - 1) / rb;
   int64_t blocks = (batches + warps - 1) / warps;
   if (blocks > 148 * 16) blocks = 148 * 16;
+  const int k = (order <= FIR_MAX_ORDER && nx >= 4 * order) ? order : 0;
   SOPHT_PROF("laplacian_filter.x", st);
-  filter_rows_x_kernel<T><<<(int)blocks, 32 * warps, smem, st>>>(f, sc, sz, sy, ncomp, nz, ny, nx, order, rb,
-                                                                fir_taps(order <= FIR_MAX_ORDER ? order : 0));
+#define ROWS_X(KK)                                                                                              \
+  case KK: {                                                                                                    \
+    static bool attr_set = false;                                                                               \
+    if (!attr_set) {                                                                                            \
+      SOPHT_CUDA(cudaFuncSetAttribute(filter_rows_x_kernel<T, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      96 * 1024));                                                              \
+      attr_set = true;                                                                                          \
+    }                                                                                                           \
+    filter_rows_x_kernel<T, KK><<<(int)blocks, 32 * warps, smem, st>>>(f, sc, sz, sy, ncomp, nz, ny, nx, order, rb, \
+                                                                      fir_taps(KK));                            \
+    break;                                                                                                      \
+  }
+  switch (k) {
+    ROWS_X(0) ROWS_X(1) ROWS_X(2) ROWS_X(3) ROWS_X(4) ROWS_X(5) ROWS_X(6) ROWS_X(7) ROWS_X(8)
+  }
+#undef ROWS_X
   SOPHT_CHECK_LAUNCH();
   return SOPHT_OK;
 }

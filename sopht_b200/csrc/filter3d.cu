@@ -87,11 +87,11 @@ __global__ void __launch_bounds__(256)
     // pass by pass only where the line ends are felt: the first and last 2 K columns (what is computed there is
     // right for the outer K columns after K passes); everything else is one (2 K + 1)-tap filter of the originals
     constexpr bool fir = K > 0;  // the host picks K > 0 only when nx >= 4 K
-    const int wcols = fir ? 4 * order : nx;
+    const int wcols = fir ? 4 * K : nx;  // compile-time divisor on the filter path
     for (int m = 0; m < order; ++m) {
       for (int idx = lane; idx < nrow * wcols; idx += 32) {
         const int rr = idx / wcols, wc = idx - rr * wcols;
-        const int i = (fir && wc >= 2 * order) ? nx - 4 * order + wc : wc;
+        const int i = (fir && wc >= 2 * K) ? nx - 4 * K + wc : wc;
         const int e = rr * nx + i;
         b[e] = (i >= 1 && i <= nx - 2) ? filter_point(a[e - 1], a[e], a[e + 1]) : T(0);
       }

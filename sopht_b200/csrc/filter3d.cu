@@ -87,18 +87,45 @@ __global__ void __launch_bounds__(256)
     // pass by pass only where the line ends are felt: the first and last 2 K columns (what is computed there is
     // right for the outer K columns after K passes); everything else is one (2 K + 1)-tap filter of the originals
     constexpr bool fir = K > 0;  // the host picks K > 0 only when nx >= 4 K
-    const int wcols = fir ? 4 * K : nx;  // compile-time divisor on the filter path
-    for (int m = 0; m < order; ++m) {
-      for (int idx = lane; idx < nrow * wcols; idx += 32) {
-        const int rr = idx / wcols, wc = idx - rr * wcols;
-        const int i = (fir && wc >= 2 * K) ? nx - 4 * K + wc : wc;
-        const int e = rr * nx + i;
-        b[e] = (i >= 1 && i <= nx - 2) ? filter_point(a[e - 1], a[e], a[e + 1]) : T(0);
+    if constexpr (fir) {
+      // one lane per (row, line end): the 2 K cells next to the end live in registers, index 0 = the end cell (both
+      // ends are the same problem mirrored, the stencil is symmetric); no shared-memory traffic, no barriers
+      for (int job = lane; job < 2 * nrow; job += 32) {
+        const int rr = job >> 1;
+        const bool right = job & 1;
+        const T* o = orig + rr * nx;
+        T u[2 * K];
+#pragma unroll
+        for (int t = 0; t < 2 * K; ++t) u[t] = o[right ? nx - 1 - t : t];
+#pragma unroll
+        for (int m = 0; m < K; ++m) {
+          T prev = u[0];
+          u[0] = T(0);  // the end cell is on the ring: no flux, in every pass
+#pragma unroll
+          for (int t = 1; t < 2 * K; ++t) {
+            const T cur = u[t];
+            const T nxt = t + 1 < 2 * K ? u[t + 1] : T(0);  // beyond the window: only cells >= 2 K - m see it
+            u[t] = filter_point(prev, cur, nxt);
+            prev = cur;
+          }
+        }
+        T* fl = a + rr * nx;
+#pragma unroll
+        for (int t = 0; t < K; ++t) fl[right ? nx - 1 - t : t] = u[t];
       }
       __syncwarp();
-      T* t = a;
-      a = b;
-      b = t;
+    } else {
+      for (int m = 0; m < order; ++m) {
+        for (int rr = 0; rr < nrow; ++rr)
+          for (int i = lane; i < nx; i += 32) {
+            const int e = rr * nx + i;
+            b[e] = (i >= 1 && i <= nx - 2) ? filter_point(a[e - 1], a[e], a[e + 1]) : T(0);
+          }
+        __syncwarp();
+        T* t = a;
+        a = b;
+        b = t;
+      }
     }
     for (int rr = 0; rr < nrow; ++rr) {
       T* row = reinterpret_cast<T*>(__shfl_sync(0xffffffffu, my_row, rr));

@@ -43,22 +43,12 @@ class ImmersedBodyFlowInteraction(VirtualBoundaryForcing):
     """Base class for immersed body flow interaction (immersed_body_flow_interaction.py:15-141)."""
 
     def __init__(
-        self,
-        eul_grid_forcing_field: torch.Tensor,
-        eul_grid_velocity_field: torch.Tensor,
-        body_flow_forces: np.ndarray,
-        body_flow_torques: np.ndarray,
-        forcing_grid_cls: type[ImmersedBodyForcingGrid],
-        virtual_boundary_stiffness_coeff: float,
-        virtual_boundary_damping_coeff: float,
-        dx: float,
-        grid_dim: int,
-        real_t: type = np.float64,
-        eul_grid_coord_shift: float | None = None,
-        interp_kernel_width: float | None = None,
-        enable_eul_grid_forcing_reset: bool = False,
-        num_threads: int | bool = False,
-        start_time: float = 0.0,
+        self, eul_grid_forcing_field: torch.Tensor, eul_grid_velocity_field: torch.Tensor,
+        body_flow_forces: np.ndarray, body_flow_torques: np.ndarray,
+        forcing_grid_cls: type[ImmersedBodyForcingGrid], virtual_boundary_stiffness_coeff: float,
+        virtual_boundary_damping_coeff: float, dx: float, grid_dim: int, real_t: type = np.float64,
+        eul_grid_coord_shift: float | None = None, interp_kernel_width: float | None = None,
+        enable_eul_grid_forcing_reset: bool = False, num_threads: int | bool = False, start_time: float = 0.0,
         **forcing_grid_kwargs: Any,
     ) -> None:
         self.body_flow_forces = body_flow_forces
@@ -99,18 +89,9 @@ class ImmersedBodyFlowInteraction(VirtualBoundaryForcing):
         virtual_boundary_damping_coeff *= max_lag_grid_dx ** (grid_dim - 1)
 
         super().__init__(
-            virtual_boundary_stiffness_coeff,
-            virtual_boundary_damping_coeff,
-            grid_dim,
-            dx,
-            self.forcing_grid.num_lag_nodes,
-            real_t,
-            eul_grid_coord_shift,
-            interp_kernel_width,
-            enable_eul_grid_forcing_reset,
-            num_threads,
-            start_time,
-        )
+            virtual_boundary_stiffness_coeff, virtual_boundary_damping_coeff, grid_dim, dx,
+            self.forcing_grid.num_lag_nodes, real_t, eul_grid_coord_shift, interp_kernel_width,
+            enable_eul_grid_forcing_reset, num_threads, start_time)
 
     def compute_interaction_on_lag_grid(self) -> None:
         """Compute interaction forces on the Lagrangian forcing grid (:105-113)."""
@@ -154,19 +135,11 @@ class RigidBodyFlowInteraction(ImmersedBodyFlowInteraction):
     def __init__(
         self,
         rigid_body: Any,
-        eul_grid_forcing_field: torch.Tensor,
-        eul_grid_velocity_field: torch.Tensor,
-        virtual_boundary_stiffness_coeff: float,
-        virtual_boundary_damping_coeff: float,
-        dx: float,
-        grid_dim: int,
-        forcing_grid_cls: type[ImmersedBodyForcingGrid],
-        real_t: type = np.float64,
-        eul_grid_coord_shift: float | None = None,
-        interp_kernel_width: float | None = None,
-        enable_eul_grid_forcing_reset: bool = False,
-        num_threads: int | bool = False,
-        start_time: float = 0.0,
+        eul_grid_forcing_field: torch.Tensor, eul_grid_velocity_field: torch.Tensor,
+        virtual_boundary_stiffness_coeff: float, virtual_boundary_damping_coeff: float, dx: float, grid_dim: int,
+        forcing_grid_cls: type[ImmersedBodyForcingGrid], real_t: type = np.float64,
+        eul_grid_coord_shift: float | None = None, interp_kernel_width: float | None = None,
+        enable_eul_grid_forcing_reset: bool = False, num_threads: int | bool = False, start_time: float = 0.0,
         **forcing_grid_kwargs: Any,
     ) -> None:
         forcing_grid_kwargs["rigid_body"] = rigid_body
@@ -183,19 +156,11 @@ class CosseratRodFlowInteraction(ImmersedBodyFlowInteraction):
     def __init__(
         self,
         cosserat_rod: Any,
-        eul_grid_forcing_field: torch.Tensor,
-        eul_grid_velocity_field: torch.Tensor,
-        virtual_boundary_stiffness_coeff: float,
-        virtual_boundary_damping_coeff: float,
-        dx: float,
-        grid_dim: int,
-        forcing_grid_cls: type[ImmersedBodyForcingGrid],
-        real_t: type = np.float64,
-        eul_grid_coord_shift: float | None = None,
-        interp_kernel_width: float | None = None,
-        enable_eul_grid_forcing_reset: bool = False,
-        num_threads: int | bool = False,
-        start_time: float = 0.0,
+        eul_grid_forcing_field: torch.Tensor, eul_grid_velocity_field: torch.Tensor,
+        virtual_boundary_stiffness_coeff: float, virtual_boundary_damping_coeff: float, dx: float, grid_dim: int,
+        forcing_grid_cls: type[ImmersedBodyForcingGrid], real_t: type = np.float64,
+        eul_grid_coord_shift: float | None = None, interp_kernel_width: float | None = None,
+        enable_eul_grid_forcing_reset: bool = False, num_threads: int | bool = False, start_time: float = 0.0,
         **forcing_grid_kwargs: Any,
     ) -> None:
         forcing_grid_kwargs["cosserat_rod"] = cosserat_rod

@@ -108,3 +108,59 @@ def test_fused_convolution_filter_at_rod_case_size():
     inner = const[1:-1, 1:-1, 1:-1]
     # away from the walls a constant has no flux; next to a wall the masked stencil sees the zeroed ring of the flux
     assert float((inner[5:-5, 5:-5, 5:-5] - 3.0).abs().max()) == 0.0
+
+
+def _one_pass_filter_emulation(f, order):
+    """numpy emulation of what csrc/filter3d.cu evaluates per direction: away from the line ends one symmetric
+    (2 order + 1)-tap filter of the originals, within `order` cells of an end the pass-by-pass values of a
+    2 order-cell window; lines on the ring of the other two axes untouched."""
+    taps = np.zeros(2 * order + 1)
+    taps[order] = 1.0
+    for _ in range(order):
+        padded = np.pad(taps, 1)
+        taps = (0.25 * (-padded[2:] - padded[:-2] + 2 * padded[1:-1]))
+    out = f.astype(np.float64).copy()
+    for axis in (2, 1, 0):
+        src = np.moveaxis(out, axis, -1).copy()
+        n = src.shape[-1]
+        flux = np.zeros_like(src)
+        if n >= 4 * order:
+            for j in range(-order, order + 1):
+                flux[..., order : n - order] += taps[order + j] * src[..., order + j : n - order + j]
+            for window, flip in ((src[..., : 2 * order], False), (src[..., ::-1][..., : 2 * order], True)):
+                u = window.copy()
+                for _ in range(order):
+                    nxt = np.zeros_like(u)
+                    nxt[..., 1:-1] = 0.25 * (-u[..., 2:] - u[..., :-2] + 2 * u[..., 1:-1])
+                    nxt[..., -1] = 0.25 * (-u[..., -2] + 2 * u[..., -1])  # beyond the window: treated as 0
+                    u = nxt
+                if flip:
+                    flux[..., n - order :] = u[..., :order][..., ::-1]
+                else:
+                    flux[..., :order] = u[..., :order]
+        else:  # short lines: pass by pass over the whole line
+            u = src.copy()
+            for _ in range(order):
+                nxt = np.zeros_like(u)
+                nxt[..., 1:-1] = 0.25 * (-u[..., 2:] - u[..., :-2] + 2 * u[..., 1:-1])
+                u = nxt
+            flux = u
+        # no flux on lines that lie on the ring of the other two axes
+        flux[0], flux[-1] = 0.0, 0.0
+        flux[:, 0], flux[:, -1] = 0.0, 0.0
+        out = np.moveaxis(src - flux, -1, axis)
+    return out
+
+
+@pytest.mark.parametrize("grid", [(17, 19, 23), (9, 30, 12), (24, 8, 21)])
+@pytest.mark.parametrize("order", [1, 2, 5])
+def test_one_pass_filter_algorithm_matches_oracle(grid, order):
+    """CPU: the single-filter-plus-end-windows formulation of the CUDA kernels equals the reference's pass-by-pass
+    closure (oracle restatement of laplacian_filter_3d.py:129-163)."""
+    from oracle import stencils as ost
+
+    rng = np.random.default_rng(21)
+    f = rng.standard_normal(grid)
+    ref = f.copy()
+    ost.laplacian_filter_3d(ref, np.zeros(grid), np.zeros(grid), order, "convolution")
+    np.testing.assert_allclose(_one_pass_filter_emulation(f, order), ref, rtol=0, atol=1e-13)

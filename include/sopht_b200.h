@@ -299,6 +299,14 @@ int sopht_poisson_create(sopht_poisson_t *handle, int dtype, int dim, int nz, in
 int sopht_poisson_neumann_create(sopht_poisson_t *handle, int dtype, int dim, int nz, int ny, int nx, double dx,
                                  void *stream);
 
+/* Handle for -laplacian(solution) = rhs with PERIODIC boundaries in every direction, mean mode of the solution zero
+ * (BASELINE config 4; an extension - the reference has no periodic solver, so there is no reference interface to
+ * cite: parity is against analytic Fourier modes). three_point_symbol = 0: spectral symbol (2 pi m / L)^2;
+ * != 0: the symbol of the 7-point Laplacian with wrap-around neighbours (its exact inverse). Used with
+ * sopht_poisson_solve / sopht_poisson_path / sopht_poisson_destroy. */
+int sopht_poisson_periodic_create(sopht_poisson_t *handle, int dtype, int dim, int nz, int ny, int nx, double dx,
+                                  int three_point_symbol, void *stream);
+
 /* -laplacian(solution) = rhs on the unbounded domain. Fields: scalar grid fields, or vector fields
  * with a leading component axis (each component solved independently).
  * ref: UnboundedPoissonSolverPYFFTW3D.py:111-172 (solve, vector_field_solve),

@@ -126,3 +126,27 @@ class FastDiagPoissonSolver:
     def vector_field_solve(self, solution_vector_field, rhs_vector_field):
         for c in range(len(self.grid_size)):
             self.solve(solution_vector_field[c], rhs_vector_field[c])
+
+
+class PeriodicPoissonSolver:
+    """numpy restatement of the periodic Poisson solve (-del^2 psi = rhs, zero-mean solution) - an EXTENSION for
+    BASELINE config 4. **Parity unpinned**: the reference has no periodic solver and no test of one (SURVEY.md fact
+    2); this class is pinned on analytic Fourier modes only (tests/test_periodic_poisson.py)."""
+
+    def __init__(self, grid_size, dx, symbol="spectral"):
+        self.grid_size = tuple(grid_size)
+        dim = len(self.grid_size)
+        lam = np.zeros(self.grid_size)
+        for axis, n in enumerate(self.grid_size):
+            k = np.arange(n)
+            if symbol == "spectral":
+                m = np.where(k <= n // 2, k, k - n)
+                sym = (2.0 * np.pi * m / (n * dx)) ** 2
+            else:
+                sym = 4.0 * np.sin(np.pi * k / n) ** 2 / (dx * dx)
+            lam = lam + sym.reshape([-1 if a == axis else 1 for a in range(dim)])
+        lam[(0,) * dim] = np.inf
+        self.inv_symbol = 1.0 / lam
+
+    def solve(self, solution_field, rhs_field):
+        solution_field[...] = np.fft.ifftn(np.fft.fftn(rhs_field.astype(np.float64)) * self.inv_symbol).real

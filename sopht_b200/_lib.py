@@ -135,6 +135,8 @@ _HANDLE_SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     ),
     "sopht_poisson_neumann_create": (
         ctypes.c_int, [ctypes.POINTER(_P), _I, _I, _I, _I, _I, ctypes.c_double, _P]),
+    "sopht_poisson_periodic_create": (
+        ctypes.c_int, [ctypes.POINTER(_P), _I, _I, _I, _I, _I, ctypes.c_double, _I, _P]),
     "sopht_poisson_solve": (ctypes.c_int, [_P, _F, _F, _P]),
     "sopht_poisson_green_hat": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
     "sopht_poisson_path": (ctypes.c_char_p, [_P]),

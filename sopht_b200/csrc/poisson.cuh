@@ -36,5 +36,8 @@ PoissonImpl* make_pow2_poisson(int nz, int ny, int nx, double dx, const double* 
 // Homogeneous Neumann walls on the cell-centred grid (the reference's FastDiagPoissonSolver{2,3}D): mirror
 // extension + periodic three-point symbol (poisson_neumann.cu)
 PoissonImpl* make_neumann_poisson(int dtype, int dim, int nz, int ny, int nx, double dx, cudaStream_t st, int* rc);
+// Periodic in every direction (an extension, BASELINE config 4): same pipeline without the mirror step
+PoissonImpl* make_periodic_poisson(int dtype, int three_point_symbol, int dim, int nz, int ny, int nx, double dx,
+                                   cudaStream_t st, int* rc);
 
 }  // namespace sopht

@@ -73,6 +73,21 @@ int sopht_poisson_neumann_create(sopht_poisson_t* handle, int dtype, int dim, in
   return SOPHT_OK;
 }
 
+int sopht_poisson_periodic_create(sopht_poisson_t* handle, int dtype, int dim, int nz, int ny, int nx, double dx,
+                                  int three_point_symbol, void* stream) {
+  SOPHT_CHECK_DTYPE(dtype);
+  if (!handle) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: null handle pointer", __func__);
+  if (dim != 2 && dim != 3) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: dim must be 2 or 3", __func__);
+  if (ny <= 0 || nx <= 0 || (dim == 3 && nz <= 0))
+    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid sizes must be positive", __func__);
+  if (!(dx > 0)) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: dx must be positive", __func__);
+  int rc = SOPHT_OK;
+  PoissonImpl* impl = make_periodic_poisson(dtype, three_point_symbol, dim, nz, ny, nx, dx, as_stream(stream), &rc);
+  if (!impl) return rc;
+  *handle = new sopht_poisson{dtype, dim, dim == 3 ? nz : 1, ny, nx, impl};
+  return SOPHT_OK;
+}
+
 int sopht_poisson_solve(sopht_poisson_t h, const sopht_field_t* solution_field,
                         const sopht_field_t* rhs_field, void* stream) {
   if (!h || !h->impl) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle", __func__);

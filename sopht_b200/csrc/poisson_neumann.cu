@@ -13,6 +13,9 @@
 //   symbol : spectrum *= 1 / (lz[kz] + ly[ky] + lx[kx]) / (8 nz ny nx), 0 for the mean mode; the symbol is rebuilt
 //            from three 1-D tables, never stored on the grid
 //   ifft   : C2C inverse along z, batched 2-D C2R over the first nz planes, crop the low corner
+// The same pipeline without the mirror step is the PERIODIC solve (BASELINE config 4, an extension: the reference has
+// nothing periodic): transform sizes n instead of 2 n, symbol either spectral ((2 pi m / L)^2, the
+// default) or the three-point one (exact inverse of the 7-point Laplacian with wrap-around neighbours).
 // ref: sopht/numeric/eulerian_grid_ops/poisson_solver_3d/FastDiagPoissonSolver3D.py:15-208,
 //      poisson_solver_2d/FastDiagPoissonSolver2D.py:13-119
 #include <cufft.h>
@@ -56,12 +59,13 @@ struct Fft<double> {
 // planes (np, 2ny, 2nx) <- rhs (np, ny, nx) mirrored about the y and x walls; x fastest, one thread per cell
 template <typename T>
 __global__ void __launch_bounds__(256)
-    mirror_planes_kernel(T* __restrict__ dst, View3<const T> src, int np, int ny, int nx) {
+    mirror_planes_kernel(T* __restrict__ dst, View3<const T> src, int np, int ny, int nx, int my, int mx) {
+  // my = 2 ny, mx = 2 nx: even extension; my = ny, mx = nx (periodic solve): a plain gather into contiguous planes
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
-  if (i >= 2 * nx || j >= 2 * ny) return;
+  if (i >= mx || j >= my) return;
   const int si = i < nx ? i : 2 * nx - 1 - i, sj = j < ny ? j : 2 * ny - 1 - j;
-  for (int k = blockIdx.z; k < np; k += gridDim.z) dst[((int64_t)k * 2 * ny + j) * 2 * nx + i] = src(k, sj, si);
+  for (int k = blockIdx.z; k < np; k += gridDim.z) dst[((int64_t)k * my + j) * mx + i] = src(k, sj, si);
 }
 
 // spectrum plane 2nz-1-z <- plane z (the 2-D transform of the mirror image in z is the transform of the plane)
@@ -98,17 +102,19 @@ __global__ void __launch_bounds__(256)
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-    crop_corner_kernel(View3<T> dst, const T* __restrict__ src, int np, int ny, int nx) {
+    crop_corner_kernel(View3<T> dst, const T* __restrict__ src, int np, int ny, int nx, int my, int mx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int j = blockIdx.y * blockDim.y + threadIdx.y;
   if (i >= nx || j >= ny) return;
-  for (int k = blockIdx.z; k < np; k += gridDim.z) dst(k, j, i) = src[((int64_t)k * 2 * ny + j) * 2 * nx + i];
+  for (int k = blockIdx.z; k < np; k += gridDim.z) dst(k, j, i) = src[((int64_t)k * my + j) * mx + i];
 }
 
 template <typename T>
 struct NeumannPoisson : PoissonImpl {
   using C = typename Fft<T>::C;
   int dim = 3, nz = 1, ny = 0, nx = 0;
+  int kind = 0;  // 0: Neumann walls (mirror), 1: periodic + spectral symbol, 2: periodic + three-point symbol
+  int tz = 1, ty = 0, tx = 0;  // transform sizes: 2 n (mirror) or n (periodic)
   T *lz = nullptr, *ly = nullptr, *lx = nullptr;  // three-point symbol per axis on the mirrored period
   T* planes = nullptr;                            // (nz, 2ny, 2nx)
   C* spec = nullptr;                              // (n2z, 2ny, nx+1)
@@ -125,15 +131,24 @@ struct NeumannPoisson : PoissonImpl {
     if (p_c2r) cufftDestroy(p_c2r);
     if (p_z) cufftDestroy(p_z);
   }
-  const char* path_name() const override { return "neumann_mirror_fft"; }
+  const char* path_name() const override {
+    return kind == 0 ? "neumann_mirror_fft" : kind == 1 ? "periodic_fft_spectral" : "periodic_fft_three_point";
+  }
 
-  int upload_symbol(T** dst, int n, int count, double dx, cudaStream_t st) {
-    // (2 - 2 cos(2 pi k / (2 n))) / dx^2 = 4 sin^2(pi k / (2 n)) / dx^2, evaluated in double
+  int upload_symbol(T** dst, int period, int count, double dx, cudaStream_t st) {
+    // three-point symbol on a period of `period` cells: (2 - 2 cos(2 pi k / period)) / dx^2 = 4 sin^2(pi k / period) / dx^2
+    // spectral symbol: (2 pi m / (period dx))^2, m the signed wavenumber; both evaluated in double
     const double pi = 3.14159265358979323846;
     std::vector<T> h(count);
     for (int k = 0; k < count; ++k) {
-      const double s = sin(pi * k / (2.0 * n));
-      h[k] = (T)(4.0 * s * s / (dx * dx));
+      if (kind == 1) {
+        const int m = k <= period / 2 ? k : k - period;
+        const double w = 2.0 * pi * m / (period * dx);
+        h[k] = (T)(w * w);
+      } else {
+        const double s = sin(pi * k / period);
+        h[k] = (T)(4.0 * s * s / (dx * dx));
+      }
     }
     SOPHT_CUDA(cudaMalloc(dst, sizeof(T) * count));
     SOPHT_CUDA(cudaMemcpyAsync(*dst, h.data(), sizeof(T) * count, cudaMemcpyHostToDevice, st));
@@ -141,18 +156,21 @@ struct NeumannPoisson : PoissonImpl {
     return SOPHT_OK;
   }
 
-  int init(int dim_, int nz_, int ny_, int nx_, double dx, cudaStream_t st) {
+  int init(int kind_, int dim_, int nz_, int ny_, int nx_, double dx, cudaStream_t st) {
+    kind = kind_;
     dim = dim_;
     nz = dim == 3 ? nz_ : 1;
     ny = ny_;
     nx = nx_;
-    const int n2z = dim == 3 ? 2 * nz : 1, n2y = 2 * ny, n2x = 2 * nx, nkx = nx + 1;
+    const int f = kind == 0 ? 2 : 1;
+    tz = dim == 3 ? f * nz : 1, ty = f * ny, tx = f * nx;
+    const int n2z = tz, n2y = ty, n2x = tx, nkx = tx / 2 + 1;
     if ((int64_t)n2z * n2y * n2x > 0x7fffffffLL)
-      SOPHT_FAIL(SOPHT_ERR_SHAPE, "poisson(neumann): mirrored grid exceeds 2^31 cells");
+      SOPHT_FAIL(SOPHT_ERR_SHAPE, "poisson(neumann / periodic): transform grid exceeds 2^31 cells");
     int rc;
-    if ((rc = upload_symbol(&lz, nz, n2z, dx, st))) return rc;  // dim 2: one entry, k = 0 -> 0
-    if ((rc = upload_symbol(&ly, ny, n2y, dx, st))) return rc;
-    if ((rc = upload_symbol(&lx, nx, nkx, dx, st))) return rc;
+    if ((rc = upload_symbol(&lz, tz, n2z, dx, st))) return rc;  // dim 2: one entry, k = 0 -> 0
+    if ((rc = upload_symbol(&ly, ty, n2y, dx, st))) return rc;
+    if ((rc = upload_symbol(&lx, tx, nkx, dx, st))) return rc;
     norm = (T)(1.0 / ((double)n2z * n2y * n2x));  // cuFFT's inverse is unnormalised
     SOPHT_CUDA(cudaMalloc(&planes, sizeof(T) * (size_t)nz * n2y * n2x));
     SOPHT_CUDA(cudaMalloc(&spec, sizeof(C) * (size_t)n2z * n2y * nkx));
@@ -169,21 +187,23 @@ struct NeumannPoisson : PoissonImpl {
   }
 
   int solve_scalar(View3<T> sol, View3<const T> rhs, cudaStream_t st) {
-    const int n2z = dim == 3 ? 2 * nz : 1, n2y = 2 * ny, n2x = 2 * nx, nkx = nx + 1;
+    const int n2z = tz, n2y = ty, n2x = tx, nkx = tx / 2 + 1;
     const int64_t plane_spec = (int64_t)n2y * nkx;
     {
       Grid3 g = cell_grid(nz, n2y, n2x);
       if (g.grid.z > 4096) g.grid.z = 4096;
       SOPHT_PROF("poisson_neumann.mirror", st);
-      mirror_planes_kernel<T><<<g.grid, g.block, 0, st>>>(planes, rhs, nz, ny, nx);
+      mirror_planes_kernel<T><<<g.grid, g.block, 0, st>>>(planes, rhs, nz, ny, nx, n2y, n2x);
       SOPHT_CHECK_LAUNCH();
     }
     NEUMANN_CUFFT(cufftSetStream(p_r2c, st));
     NEUMANN_CUFFT(Fft<T>::r2c(p_r2c, planes, spec));
     g_launch_count++;
     if (dim == 3) {
-      mirror_z_spectrum_kernel<C><<<148 * 8, 256, 0, st>>>(spec, nz, plane_spec);
-      SOPHT_CHECK_LAUNCH();
+      if (kind == 0) {
+        mirror_z_spectrum_kernel<C><<<148 * 8, 256, 0, st>>>(spec, nz, plane_spec);
+        SOPHT_CHECK_LAUNCH();
+      }
       NEUMANN_CUFFT(cufftSetStream(p_z, st));
       NEUMANN_CUFFT(Fft<T>::c2c(p_z, spec, spec, CUFFT_FORWARD));
       g_launch_count++;
@@ -206,7 +226,7 @@ struct NeumannPoisson : PoissonImpl {
       Grid3 g = cell_grid(nz, ny, nx);
       if (g.grid.z > 4096) g.grid.z = 4096;
       SOPHT_PROF("poisson_neumann.crop", st);
-      crop_corner_kernel<T><<<g.grid, g.block, 0, st>>>(sol, planes, nz, ny, nx);
+      crop_corner_kernel<T><<<g.grid, g.block, 0, st>>>(sol, planes, nz, ny, nx, n2y, n2x);
       SOPHT_CHECK_LAUNCH();
     }
     return SOPHT_OK;
@@ -236,9 +256,9 @@ struct NeumannPoisson : PoissonImpl {
 };
 
 template <typename T>
-PoissonImpl* make_neumann(int dim, int nz, int ny, int nx, double dx, cudaStream_t st, int* rc) {
+PoissonImpl* make_neumann(int kind, int dim, int nz, int ny, int nx, double dx, cudaStream_t st, int* rc) {
   auto* p = new NeumannPoisson<T>();
-  *rc = p->init(dim, nz, ny, nx, dx, st);
+  *rc = p->init(kind, dim, nz, ny, nx, dx, st);
   if (*rc) {
     delete p;
     return nullptr;
@@ -249,8 +269,15 @@ PoissonImpl* make_neumann(int dim, int nz, int ny, int nx, double dx, cudaStream
 }  // namespace
 
 PoissonImpl* make_neumann_poisson(int dtype, int dim, int nz, int ny, int nx, double dx, cudaStream_t st, int* rc) {
-  return dtype == SOPHT_F32 ? make_neumann<float>(dim, nz, ny, nx, dx, st, rc)
-                            : make_neumann<double>(dim, nz, ny, nx, dx, st, rc);
+  return dtype == SOPHT_F32 ? make_neumann<float>(0, dim, nz, ny, nx, dx, st, rc)
+                            : make_neumann<double>(0, dim, nz, ny, nx, dx, st, rc);
+}
+
+PoissonImpl* make_periodic_poisson(int dtype, int three_point_symbol, int dim, int nz, int ny, int nx, double dx,
+                                   cudaStream_t st, int* rc) {
+  const int kind = three_point_symbol ? 2 : 1;
+  return dtype == SOPHT_F32 ? make_neumann<float>(kind, dim, nz, ny, nx, dx, st, rc)
+                            : make_neumann<double>(kind, dim, nz, ny, nx, dx, st, rc);
 }
 
 }  // namespace sopht

@@ -1,0 +1,101 @@
+"""Periodic Poisson solver (extension for BASELINE config 4: periodic Taylor-Green vortex). The reference has nothing
+periodic: parity is UNPINNED by the reference and rests on analytic answers - single Fourier modes,
+the Taylor-Green stream function, and the exact-inverse property of the three-point symbol."""
+
+import numpy as np
+import pytest
+
+TOL = {"float32": 1e-5, "float64": 1e-12}
+
+
+def _rel_l2(a, b):
+    return float(np.linalg.norm((np.asarray(a, dtype=np.float64) - b).ravel()) / np.linalg.norm(np.ravel(b)))
+
+
+def _taylor_green(grid, x_range):
+    """A Taylor-Green-type single mode cos cos cos on the periodic box (the vorticity of u = (sin x cos y cos z,
+    -cos x sin y cos z, 0) has this shape; wavenumber
+    2 pi / L per axis) and the psi_z with -lap psi_z = omega_z: psi = omega / |k|^2."""
+    nz, ny, nx = grid
+    dx = x_range / nx
+    z, y, x = np.meshgrid((np.arange(nz) + 0.5) * dx, (np.arange(ny) + 0.5) * dx, (np.arange(nx) + 0.5) * dx,
+                          indexing="ij")
+    kx, ky, kz = 2 * np.pi / x_range, 2 * np.pi / (ny * dx), 2 * np.pi / (nz * dx)
+    omega = -(kx + ky) * np.cos(kx * x) * np.cos(ky * y) * np.cos(kz * z)
+    return omega, omega / (kx * kx + ky * ky + kz * kz)
+
+
+def test_oracle_periodic_analytic():
+    from oracle.poisson import PeriodicPoissonSolver
+
+    grid, x_range = (12, 16, 20), 2.0
+    omega, psi = _taylor_green(grid, x_range)
+    sol = np.zeros(grid)
+    PeriodicPoissonSolver(grid, x_range / grid[2], "spectral").solve(sol, omega + 3.0)  # the mean is dropped
+    assert _rel_l2(sol, psi) < 1e-13
+    rng = np.random.default_rng(2)
+    rhs = rng.standard_normal(grid)
+    rhs -= rhs.mean()
+    dx = x_range / grid[2]
+    PeriodicPoissonSolver(grid, dx, "three_point").solve(sol, rhs)
+    lap = sum(np.roll(sol, 1, a) + np.roll(sol, -1, a) for a in range(3)) - 6 * sol
+    assert _rel_l2(-lap / dx**2, rhs) < 1e-12 and abs(sol.mean()) < 1e-14
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+@pytest.mark.parametrize("grid", [(12, 16, 20), (17, 19, 23), (32, 32, 64)])
+def test_cuda_periodic_poisson_3d(dtype, grid):
+    import torch
+
+    import sopht_b200.numeric.eulerian_grid_ops as spne
+    from oracle.poisson import PeriodicPoissonSolver
+
+    real_t = np.float32 if dtype == "float32" else np.float64
+    x_range = 2.0
+    omega, psi = _taylor_green(grid, x_range)
+    solver = spne.PeriodicPoissonSolver3D(*grid, x_range=x_range, real_t=real_t)
+    assert solver.path == "periodic_fft_spectral"
+    rhs = torch.from_numpy((omega + 3.0).astype(real_t)).cuda()
+    sol = torch.zeros_like(rhs)
+    solver.solve(solution_field=sol, rhs_field=rhs)
+    assert _rel_l2(sol.cpu().numpy(), psi) < TOL[dtype]
+    # random vector rhs against the numpy restatement, both symbols; three_point inverts the wrap-around Laplacian
+    rng = np.random.default_rng(4)
+    v = rng.standard_normal((3, *grid)).astype(real_t)
+    dx = x_range / grid[2]
+    for symbol in ("spectral", "three_point"):
+        s = spne.PeriodicPoissonSolver3D(*grid, x_range=x_range, real_t=real_t, symbol=symbol)
+        out = torch.zeros((3, *grid), dtype=rhs.dtype, device="cuda")
+        s.vector_field_solve(solution_vector_field=out, rhs_vector_field=torch.from_numpy(v).cuda())
+        ref = np.zeros(grid)
+        oracle = PeriodicPoissonSolver(grid, dx, symbol)
+        for c in range(3):
+            oracle.solve(ref, v[c])
+            assert _rel_l2(out[c].cpu().numpy(), ref) < TOL[dtype]
+    if dtype == "float64":
+        o = out[0]
+        lap = sum(torch.roll(o, 1, a) + torch.roll(o, -1, a) for a in range(3)) - 6 * o
+        want = torch.from_numpy(v[0] - v[0].mean()).cuda()
+        assert float(torch.linalg.vector_norm(-lap / dx**2 - want) / torch.linalg.vector_norm(want)) < 1e-11
+    with pytest.raises(ValueError, match="symbol"):
+        spne.PeriodicPoissonSolver3D(*grid, symbol="chebyshev")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_cuda_periodic_poisson_2d(dtype):
+    import torch
+
+    import sopht_b200.numeric.eulerian_grid_ops as spne
+
+    real_t = np.float32 if dtype == "float32" else np.float64
+    ny, nx, x_range = 24, 40, 1.0
+    dx = x_range / nx
+    y, x = np.meshgrid((np.arange(ny) + 0.5) * dx, (np.arange(nx) + 0.5) * dx, indexing="ij")
+    kx, ky = 2 * np.pi * 2 / x_range, 2 * np.pi * 3 / (ny * dx)
+    rhs = np.sin(kx * x) * np.cos(ky * y)
+    solver = spne.PeriodicPoissonSolver2D(ny, nx, x_range=x_range, real_t=real_t)
+    sol = torch.zeros((ny, nx), dtype=getattr(torch, dtype), device="cuda")
+    solver.solve(solution_field=sol, rhs_field=torch.from_numpy(rhs.astype(real_t)).cuda())
+    assert _rel_l2(sol.cpu().numpy(), rhs / (kx * kx + ky * ky)) < TOL[dtype]

@@ -6,6 +6,7 @@ from .navier_stokes_flow_simulators import (
     UnboundedNavierStokesFlowSimulator3D,
     compute_advection_diffusion_stable_timestep,
 )
+from .periodic_flow_simulators import PeriodicNavierStokesFlowSimulator3D
 from .passive_transport_flow_simulators import (
     PassiveTransportFlowSimulator,
     create_unbounded_flow_simulator_2d,
@@ -15,6 +16,7 @@ from .passive_transport_flow_simulators import (
 __all__ = [
     "FlowSimulator",
     "PassiveTransportFlowSimulator",
+    "PeriodicNavierStokesFlowSimulator3D",
     "UnboundedNavierStokesFlowSimulator2D",
     "UnboundedNavierStokesFlowSimulator3D",
     "compute_advection_diffusion_stable_timestep",

@@ -99,3 +99,71 @@ def test_cuda_periodic_poisson_2d(dtype):
     sol = torch.zeros((ny, nx), dtype=getattr(torch, dtype), device="cuda")
     solver.solve(solution_field=sol, rhs_field=torch.from_numpy(rhs.astype(real_t)).cuda())
     assert _rel_l2(sol.cpu().numpy(), rhs / (kx * kx + ky * ky)) < TOL[dtype]
+
+
+def _taylor_green_2d_vorticity(sim_position_field, x_range):
+    """omega_z = 2 k sin(k x) sin(k y), k = 2 pi / L, of u = (sin kx cos ky, -cos kx sin ky, 0): an exact solution of
+    the Navier-Stokes equations whose amplitude decays as exp(-2 nu k^2 t) (the nonlinear term vanishes)."""
+    k = 2 * np.pi / x_range
+    x, y = sim_position_field[0], sim_position_field[1]
+    return 2 * k * np.sin(k * x) * np.sin(k * y), k
+
+
+def test_oracle_periodic_flow_step_taylor_green_decay():
+    """CPU: the halo-wrapped composition of the reference's sub-steps reproduces the analytic Taylor-Green decay."""
+    from oracle import flow as oflow
+
+    x_range, nu = 1.0, 5e-3
+    sim = oflow.PeriodicNavierStokesFlowSimulator3D((8, 32, 32), x_range, nu, real_t=np.float64)
+    w0, k = _taylor_green_2d_vorticity(sim.position_field, x_range)
+    sim.vorticity_field[2] = w0
+    sim.compute_velocity_from_vorticity()
+    # u_x = sin(kx) cos(ky) up to the second-order error of the centred curl
+    u_exact = np.sin(k * sim.position_field[0]) * np.cos(k * sim.position_field[1])
+    assert _rel_l2(sim.velocity_field[0], u_exact) < 2e-2
+    steps, dt = 40, 2e-3
+    for _ in range(steps):
+        sim.time_step(dt)
+    decay = np.exp(-2 * nu * k * k * steps * dt)
+    assert _rel_l2(sim.vorticity_field[2], decay * w0) < 5e-3
+    assert np.abs(sim.vorticity_field[:2]).max() < 1e-10 * np.abs(w0).max()  # the flow stays two-dimensional
+    assert 0 < sim.compute_stable_timestep() < 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_cuda_periodic_flow_step_matches_oracle(dtype):
+    """The CUDA simulator against the numpy restatement on a random periodic field (identical step counts), and the
+    Taylor-Green decay on the device."""
+    import torch
+
+    from oracle import flow as oflow
+    from sopht_b200.simulator import PeriodicNavierStokesFlowSimulator3D
+
+    real_t = np.float32 if dtype == "float32" else np.float64
+    grid, x_range, nu = (12, 20, 24), 1.0, 1e-2
+    sim = PeriodicNavierStokesFlowSimulator3D(grid, x_range, nu, real_t=real_t)
+    ref = oflow.PeriodicNavierStokesFlowSimulator3D(grid, x_range, nu, real_t=np.float64)
+    rng = np.random.default_rng(8)
+    w0 = rng.standard_normal((3, *grid)).astype(real_t)
+    sim.vorticity_field[...] = torch.from_numpy(w0).cuda()
+    ref.vorticity_field[...] = w0
+    sim.compute_velocity_from_vorticity()
+    ref.compute_velocity_from_vorticity()
+    tol = 2e-5 if dtype == "float32" else 1e-11
+    assert _rel_l2(sim.velocity_field.cpu().numpy(), ref.velocity_field) < tol
+    for _ in range(3):
+        sim.time_step(1e-4)
+        ref.time_step(1e-4)
+    assert _rel_l2(sim.vorticity_field.cpu().numpy(), ref.vorticity_field) < tol
+    assert _rel_l2(sim.velocity_field.cpu().numpy(), ref.velocity_field) < tol
+    assert sim.compute_stable_timestep() == pytest.approx(ref.compute_stable_timestep(), rel=1e-4)
+
+    tg = PeriodicNavierStokesFlowSimulator3D((8, 32, 32), x_range, 5e-3, real_t=real_t)
+    w, k = _taylor_green_2d_vorticity(tg.position_field.cpu().numpy().astype(np.float64), x_range)
+    tg.vorticity_field[2] = torch.from_numpy(w.astype(real_t)).cuda()
+    tg.compute_velocity_from_vorticity()
+    for _ in range(40):
+        tg.time_step(2e-3)
+    decay = np.exp(-2 * 5e-3 * k * k * 40 * 2e-3)
+    assert _rel_l2(tg.vorticity_field[2].cpu().numpy(), decay * w) < 5e-3

@@ -1,5 +1,5 @@
-"""Periodic Taylor-Green step (BASELINE config 4) on one GPU - NOT part of bench.py's contract and not measured in
-round 1 (written after the round's GPU budget was spent; the simulator itself is covered by tests/test_periodic_poisson.py).
+"""Periodic Taylor-Green step (BASELINE config 4) on one GPU - NOT part of bench.py's contract (round 1 has one
+256^3 line from it, profiles/r01_bench_periodic_256.json; the simulator is covered by tests/test_periodic_poisson.py).
 
     python tools/bench_periodic.py [--n 512] [--steps 10] [--warmup 3]
 

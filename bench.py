@@ -4,9 +4,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
 Workloads (grid tuples are (nz, ny, nx) like the reference):
-  c2      3D flow past rigid sphere, unbounded Poisson, 128x128x256 fp32, IB forcing (BASELINE configs[1])  [default]
+  u512    3D unbounded flow step 512^3 fp32 (no body): the north-star single-GPU size; weak-scaled with the rank
+          count, so --gpus 8 runs 1024^3 (BASELINE configs[4])                                             [default]
+  c2      3D flow past rigid sphere, unbounded Poisson, 128x128x256 fp32, IB forcing (BASELINE configs[1])
+  c3      3D Cosserat rod in cross-flow, 256x128x128 fp32, order-5 filter (BASELINE configs[2])
   u256    3D unbounded flow step 256^3 fp32 (no body)
-  u512    3D unbounded flow step 512^3 fp32 (no body; the north-star single-GPU target size)
 A "step" is one pass of the hot path: [IB gather + forcing + spread] -> vorticity update (rotational
 advection + diffusion + boundary penalisation) -> unbounded FFT Poisson solve -> velocity = curl(psi) + U_inf.
 
@@ -63,6 +65,7 @@ def global_grid(wl, world):
 
 
 NU = 1e-3
+CPU_KIND_DESC = "numpy stencils + scipy.fft oracle (port of the reference dataflow)"
 X_RANGE = 1.0
 U_INF = (1.0, 0.0, 0.0)
 
@@ -301,6 +304,15 @@ def cpu_step(sim, vb, dt):
     sim.time_step(dt, free_stream_velocity=U_INF)
 
 
+def cpu_sample_grid(grid, max_cells=2**24):
+    """Bounded CPU sample of a workload: the same flow on a grid halved (largest axis first) until it has at most
+    `max_cells` cells. Per-cell work is identical, so the throughput unit (Gcell/s) carries over."""
+    g = list(grid)
+    while int(np.prod(g)) > max_cells:
+        g[int(np.argmax(g))] //= 2
+    return tuple(g)
+
+
 def time_cpu(wl, steps, warmup):
     cores = len(os.sched_getaffinity(0))
     sim, vb = build_cpu_case(wl, cores)
@@ -315,24 +327,46 @@ def time_cpu(wl, steps, warmup):
     return cells * steps / el / 1e9, el / steps * 1e3, cores
 
 
+def workload_config(wl, grid, world, n_lag):
+    """The `config` object of the JSON line: names the workload only, identical for both arms."""
+    cells_local = int(np.prod(grid)) // world
+    return {"workload": wl["desc"] + (f", weak-scaled to {world} z-slabs" if world > 1 else ""),
+            "grid": list(grid), "cells_per_gpu": cells_local,
+            "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
+            "lagrangian_nodes": n_lag,
+            "l2": "inputs larger than L2: per-GPU working set per step (fields + FFT workspace, "
+                  f"{cells_local * 4 * 33 / 1e6:.0f} MB) exceeds the 126 MB L2"}
+
+
+def workload_lag_nodes(wl):
+    if wl["body"] == "sphere":
+        return int(sphere_lag_grid().shape[1])
+    if wl["body"] == "rod":
+        n_elem = 5 * wl["grid"][2] // 16
+        return n_elem * (wl["grid"][2] // 8)
+    return 0
+
+
 def run_reference_arm(args, wl):
+    """CPU arm: the oracle's restatement of the reference step on the host cores, same metric / config / steps /
+    warm-up as the GPU arm; every step is one pass over a bounded sample of the workload (cpu_sample_grid)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))
-    warm = 1 if args.warmup > 0 else 0
-    # same (weak-scaled) global grid as the GPU arm at this rank count; bound the sample: big grids run fewer steps
-    wl = dict(wl, grid=global_grid(wl, max(args.gpus, 1)))
-    cells = int(np.prod(wl["grid"]))
-    if cells > 2**24:
-        steps = min(steps, 2)
-    val, ms, cores = time_cpu(wl, steps, warm)
-    sample = f"{steps} full steps of {wl['desc']} (numpy/scipy.fft oracle, scipy workers={cores})"
+    world = max(args.gpus, 1)
+    grid = global_grid(wl, world)
+    sample_grid = cpu_sample_grid(grid)
+    steps, warm = args.steps, args.warmup
+    val, ms, cores = time_cpu(dict(wl, grid=sample_grid), steps, warm)
+    sample = (f"{steps} steps (+{warm} warm-up) of the same flow step on a {sample_grid[0]}x{sample_grid[1]}x"
+              f"{sample_grid[2]} grid" + ("" if sample_grid == tuple(grid) else " (bounded sample of the workload grid)")
+              + f"; {CPU_KIND_DESC}, {cores} threads, {ms:.0f} ms/step")
     line = {
         "impl": "reference", "metric": "3D flow step Gcell-updates/s", "value": val, "unit": "Gcell/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["desc"], "grid": list(wl["grid"]), "timing": "host perf_counter (CPU arm)"},
+        "config": workload_config(wl, grid, world, workload_lag_nodes(wl)),
+        "timing": "host perf_counter (CPU arm)",
         "cpu_baseline": {"value": val, "unit": "Gcell/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "Gcell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -343,6 +377,99 @@ def run_reference_arm(args, wl):
 # ---------------------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------------------
+def parity_single_gpu():
+    """N = 1: two coupled steps at BASELINE configs[1] size (128x128x256, forcing + free stream) from a seeded random
+    state through the same fused CUDA step the timed loop uses, against the CPU oracle; worst relative L2 error."""
+    import torch
+
+    from oracle import flow as oflow
+    from sopht_b200.simulator import UnboundedNavierStokesFlowSimulator3D
+
+    grid = (128, 128, 256)
+    kw = dict(grid_size=grid, x_range=1.0, kinematic_viscosity=NU, real_t=np.float32, with_forcing=True,
+              with_free_stream_flow=True)
+    sim = UnboundedNavierStokesFlowSimulator3D(**kw)
+    ref = oflow.UnboundedNavierStokesFlowSimulator3D(workers=len(os.sched_getaffinity(0)), **kw)
+    rng = np.random.default_rng(2024)
+    for name in ("vorticity_field", "velocity_field", "eul_grid_forcing_field"):
+        a = rng.standard_normal((3, *grid)).astype(np.float32)
+        getattr(ref, name)[...] = a
+        getattr(sim, name)[...] = torch.from_numpy(a).cuda()
+    dt = float(ref.compute_stable_timestep(dt_prefac=0.5))
+    worst = abs(float(sim.compute_stable_timestep(dt_prefac=0.5)) - dt) / dt
+    for _ in range(2):
+        sim.time_step(dt=dt, free_stream_velocity=U_INF)
+        ref.time_step(dt, free_stream_velocity=U_INF)
+    errs = {}
+    for name in ("vorticity_field", "velocity_field", "stream_func_field"):
+        a = getattr(sim, name).cpu().numpy().astype(np.float64)
+        b = getattr(ref, name).astype(np.float64)
+        errs[name] = float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    worst = max(worst, *errs.values())
+    del sim
+    torch.cuda.empty_cache()
+    return {"value": worst, "metric": "max rel-L2 (vorticity, velocity, stream function, dt)", "tolerance": 1e-5,
+            "ok": bool(worst < 1e-5), "against": "CPU oracle (oracle/flow.py), 2 coupled steps, 128x128x256 fp32, "
+            "seeded random state, forcing + free stream", "fields": errs}
+
+
+def parity_slab(world):
+    """N > 1: the z-slab decomposed step (peer-memory halos, NVLink transposes) against the single-GPU step of the
+    same library on the whole grid, every rank on its own planes; worst relative L2 error over the ranks."""
+    import torch
+    import torch.distributed as dist
+
+    from sopht_b200.parallel import SlabUnboundedNavierStokesFlowSimulator3D
+    from sopht_b200.simulator import UnboundedNavierStokesFlowSimulator3D
+
+    grid = (128, 64, 128)
+    kw = dict(grid_size=grid, x_range=1.0, kinematic_viscosity=NU, real_t=np.float32, with_forcing=True,
+              with_free_stream_flow=True)
+    slab = SlabUnboundedNavierStokesFlowSimulator3D(**kw)
+    full = UnboundedNavierStokesFlowSimulator3D(**kw)
+    rng = np.random.default_rng(2025)
+    for name in ("vorticity_field", "velocity_field", "eul_grid_forcing_field"):
+        a = rng.standard_normal((3, *grid)).astype(np.float32)
+        getattr(full, name)[...] = torch.from_numpy(a).cuda()
+        slab.set_owned(getattr(slab, name), a)
+    dt = float(full.compute_stable_timestep(dt_prefac=0.5))
+    worst = abs(float(slab.compute_stable_timestep(dt_prefac=0.5)) - dt) / dt
+    for _ in range(2):
+        full.time_step(dt=dt, free_stream_velocity=U_INF)
+        slab.time_step(dt=dt, free_stream_velocity=U_INF)
+    errs = {}
+    for name in ("vorticity_field", "velocity_field", "stream_func_field"):
+        a = slab.owned(getattr(slab, name)).double()
+        b = getattr(full, name)[:, slab.z_slice].double()
+        num = (a - b).pow(2).sum()
+        dist.all_reduce(num)
+        errs[name] = float((num / getattr(full, name).double().pow(2).sum()).sqrt())
+    worst = max(worst, *errs.values())
+    torch.cuda.synchronize()
+    del slab, full
+    torch.cuda.empty_cache()
+    return {"value": worst, "metric": "max rel-L2 (vorticity, velocity, stream function, dt)", "tolerance": 1e-5,
+            "ok": bool(worst < 1e-5), "against": f"single-GPU step of the same library on the whole 128x64x128 grid "
+            f"(itself pinned to the CPU oracle at N = 1), {world} z-slabs, 2 steps, seeded random state",
+            "fields": errs}
+
+
+def guarded(fn, *a, limit_s=240.0):
+    """Run a parity check; a hang (a peer that never answers) must not take the bench line with it."""
+    box = {}
+
+    def work():
+        try:
+            box["r"] = fn(*a)
+        except Exception as e:  # noqa: BLE001
+            box["r"] = {"value": None, "ok": False, "error": f"{type(e).__name__}: {e}"[:300]}
+
+    th = threading.Thread(target=work, daemon=True)
+    th.start()
+    th.join(limit_s)
+    return box.get("r", {"value": None, "ok": False, "error": f"parity check did not finish in {limit_s:.0f} s"})
+
+
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
@@ -362,6 +489,9 @@ def run_ours(args, wl):
     forcing = wl["body"] is not None
     x_range = wl.get("x_range", X_RANGE)
     filt = wl.get("filter")
+    parity = None
+    if not args.no_parity:
+        parity = guarded(parity_single_gpu) if world == 1 else guarded(parity_slab, world)
     if world > 1 and (filt or wl["body"] == "rod"):
         raise SystemExit("workload c3 (rod + filter) is a single-GPU bench line; use c2 / u256 / u512 with --gpus N")
     dt_value = None
@@ -525,24 +655,28 @@ def run_ours(args, wl):
         return
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        csteps = 8 if cells <= 2**23 else 2
-        cval, cms, cores = time_cpu(wl, csteps, 1)
+        sample_grid = cpu_sample_grid(grid)
+        csteps = 8 if int(np.prod(sample_grid)) <= 2**23 else 4
+        cval, cms, cores = time_cpu(dict(wl, grid=sample_grid), csteps, 1)
         cpu = {"value": cval, "unit": "Gcell/s", "cores": cores, "kind": "port",
-               "sample": f"{csteps} full steps of the same workload, numpy/scipy.fft oracle, {cms:.0f} ms/step"}
+               "sample": f"{csteps} steps (+1 warm-up) of the same flow step on a {sample_grid[0]}x{sample_grid[1]}x"
+                         f"{sample_grid[2]} grid" + ("" if sample_grid == tuple(grid) else
+                                                     " (bounded sample of the workload grid)")
+                         + f"; {CPU_KIND_DESC}, {cores} threads, {cms:.0f} ms/step"}
     line = {
         "metric": "3D flow step Gcell-updates/s", "value": value, "unit": "Gcell/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": wl["desc"] + (f", weak-scaled to {world} z-slabs" if world > 1 else ""),
-                   "grid": list(grid), "cells_per_gpu": cells_local,
-                   "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
-                   "lagrangian_nodes": (n_lag if rod_interactor is not None else int(pos_h.shape[1])) if forcing else 0,
-                   "step_mode": sim.step_mode, "poisson_path": sim._unbounded_poisson_solver.path,
-                   "l2": "inputs larger than L2: per-GPU working set per step (fields + FFT workspace, "
-                         f"{cells_local * 4 * 33 / 1e6:.0f} MB) exceeds the 126 MB L2"},
+        "config": workload_config(
+            wl, grid, world, (n_lag if rod_interactor is not None else int(pos_h.shape[1])) if forcing else 0),
+        "path": {"step_mode": sim.step_mode, "poisson_path": sim._unbounded_poisson_solver.path},
+        "parity": parity,
         "e2e": {"value": e2e_val, "unit": "Gcell/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "note": "public-API loop of the reference's examples: stable-dt read-back every step (device reduction "
+                        "+ D2H scalar), then the coupled step; body workloads also upload the Lagrangian positions / "
+                        "velocities from pinned host memory and read the Lagrangian forces back"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": roof,
@@ -562,9 +696,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="u512", choices=sorted(WORKLOADS))
     ap.add_argument("--step-mode", default="auto", choices=["auto", "fused", "unfused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -9,6 +9,8 @@ Workloads (grid tuples are (nz, ny, nx) like the reference):
   c2      3D flow past rigid sphere, unbounded Poisson, 128x128x256 fp32, IB forcing (BASELINE configs[1])
   c3      3D Cosserat rod in cross-flow, 256x128x128 fp32, order-5 filter (BASELINE configs[2])
   u256    3D unbounded flow step 256^3 fp32 (no body)
+  tg512 / tg256  3D periodic Taylor-Green vortex, 512^3 / 256^3 fp32 (BASELINE configs[3]; an extension: the reference
+          has no periodic case, parity is against the numpy restatement + the analytic decay - "unpinned")
 A "step" is one pass of the hot path: [IB gather + forcing + spread] -> vorticity update (rotational
 advection + diffusion + boundary penalisation) -> unbounded FFT Poisson solve -> velocity = curl(psi) + U_inf.
 
@@ -19,8 +21,10 @@ advection + diffusion + boundary penalisation) -> unbounded FFT Poisson solve ->
               the public simulator API, and reads the step's results (stable dt, Lagrangian forces) back.
 `roofline`    dominant kernel, algorithmic bytes / CUDA-event time (a second K-step region with the
               library's per-phase event timers switched on), against MEASURED_PEAKS.json.
-`cpu_baseline` the CPU oracle (numpy + scipy.fft restatement of the reference's dataflow) on the
-              box's host cores, bounded sample, rank 0 at N=1 only.
+`cpu_baseline` the CPU oracle in its C / OpenMP form (one loop nest per reference kernel, unfused passes, + scipy.fft
+              standing in for pyFFTW: the reference's dataflow) on the box's host cores, bounded sample, rank 0 at N=1.
+`parity`      computed in this process: N=1 two coupled steps at 128x128x256 against the CPU oracle, N>1 the slab
+              step against the single-GPU step on every rank's own planes (max rel-L2, tolerance 1e-5).
 """
 
 from __future__ import annotations
@@ -47,6 +51,10 @@ WORKLOADS = {
                     "order-5 convolution filter"),
     "u256": dict(grid=(256, 256, 256), body=None, desc="3D unbounded flow step 256^3 fp32"),
     "u512": dict(grid=(512, 512, 512), body=None, desc="3D unbounded flow step 512^3 fp32"),
+    "tg512": dict(grid=(512, 512, 512), body=None, periodic=True,
+                  desc="3D periodic Taylor-Green vortex 512^3 fp32"),
+    "tg256": dict(grid=(256, 256, 256), body=None, periodic=True,
+                  desc="3D periodic Taylor-Green vortex 256^3 fp32"),
 }
 def global_grid(wl, world):
     """Weak scaling: the per-GPU cell count is fixed, the global grid grows with the number of ranks
@@ -65,7 +73,8 @@ def global_grid(wl, world):
 
 
 NU = 1e-3
-CPU_KIND_DESC = "numpy stencils + scipy.fft oracle (port of the reference dataflow)"
+CPU_KIND_DESC = ("C/OpenMP loop nest per reference kernel (oracle/c/ref_kernels.c, unfused passes like pystencils) + "
+                 "scipy.fft in place of pyFFTW")
 X_RANGE = 1.0
 U_INF = (1.0, 0.0, 0.0)
 
@@ -259,14 +268,17 @@ def measured_peak_hbm():
 # CPU arm: the oracle's restatement of the reference step (numpy stencils + scipy.fft + IB loops)
 # ---------------------------------------------------------------------------------------------------------
 def build_cpu_case(wl, cores):
+    from oracle import cstencils
     from oracle import flow as oflow
 
+    cstencils.load()
+    cstencils.set_num_threads(cores)
     grid = wl["grid"]
     forcing = wl["body"] is not None
     x_range = wl.get("x_range", X_RANGE)
     filt = wl.get("filter")
     sim = oflow.UnboundedNavierStokesFlowSimulator3D(
-        grid_size=grid, x_range=x_range, kinematic_viscosity=NU, real_t=np.float32,
+        grid_size=grid, x_range=x_range, kinematic_viscosity=NU, real_t=np.float32, kernels=cstencils,
         with_forcing=forcing, with_free_stream_flow=True, workers=cores, filter_vorticity=filt is not None,
         **({"filter_setting_dict": filt} if filt else {}))
     sim.vorticity_field[...] = hill_vortex_vorticity(grid, x_range)
@@ -690,6 +702,168 @@ def run_ours(args, wl):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------------
+# periodic Taylor-Green workload (BASELINE configs[3]); single GPU
+# ---------------------------------------------------------------------------------------------------------
+PERIODIC_BYTES_PER_CELL = 180  # stencils 60 + periodic Poisson 3 x 40
+PERIODIC_KERNEL_BYTES = {"ns3d.advect": 36.0, "ns3d.diffuse": 24.0, "ns3d.velocity": 24.0}
+
+
+def taylor_green_vorticity(grid, real_t=np.float32):
+    """Vorticity of u = (sin x cos y cos z, -cos x sin y cos z, 0) on [0, 2 pi)^3 mapped onto the unit box."""
+    nz, ny, nx = grid
+    k = 2 * np.pi
+    z = (np.arange(nz) + 0.5) / nx * k
+    y = (np.arange(ny) + 0.5) / nx * k
+    x = (np.arange(nx) + 0.5) / nx * k
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    w = np.empty((3, nz, ny, nx), dtype=real_t)
+    w[0] = -k * np.cos(X) * np.sin(Y) * np.sin(Z)
+    w[1] = -k * np.sin(X) * np.cos(Y) * np.sin(Z)
+    w[2] = 2 * k * np.sin(X) * np.sin(Y) * np.cos(Z)
+    return w
+
+
+def parity_periodic():
+    """Fused periodic step against the numpy restatement (oracle/flow.py, itself checked against the analytic
+    Taylor-Green decay; no reference code exists for this case: unpinned), 3 steps at 32x64x128."""
+    import torch
+
+    from oracle import flow as oflow
+    from sopht_b200.simulator import PeriodicNavierStokesFlowSimulator3D
+
+    grid = (32, 64, 128)
+    sim = PeriodicNavierStokesFlowSimulator3D(grid, 1.0, NU, real_t=np.float32)
+    ref = oflow.PeriodicNavierStokesFlowSimulator3D(grid, 1.0, NU, real_t=np.float32)
+    w0 = np.random.default_rng(7).standard_normal((3, *grid)).astype(np.float32)
+    sim.vorticity_field[...] = torch.from_numpy(w0).cuda()
+    ref.vorticity_field[...] = w0
+    sim.compute_velocity_from_vorticity()
+    ref.compute_velocity_from_vorticity()
+    dt = float(ref.compute_stable_timestep(0.5))
+    for _ in range(3):
+        sim.time_step(dt)
+        ref.time_step(dt)
+    errs = {}
+    for name in ("vorticity_field", "velocity_field"):
+        a = getattr(sim, name).cpu().numpy().astype(np.float64)
+        b = np.asarray(getattr(ref, name), dtype=np.float64)
+        errs[name] = float(np.linalg.norm(a - b) / np.linalg.norm(b))
+    worst = max(errs.values())
+    return {"value": worst, "metric": "max rel-L2 (vorticity, velocity)", "tolerance": 1e-5, "ok": bool(worst < 1e-5),
+            "against": "numpy restatement of the periodic step (oracle/flow.py), 3 steps, 32x64x128 fp32, seeded "
+                       "random state; UNPINNED: the reference has no periodic code", "fields": errs}
+
+
+def run_periodic(args, wl):
+    import torch
+
+    from sopht_b200 import _lib
+    from sopht_b200.simulator import PeriodicNavierStokesFlowSimulator3D
+
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        raise SystemExit("the periodic workloads are single-GPU bench lines in this round")
+    torch.cuda.set_device(0)
+    _lib.load()
+    grid = wl["grid"]
+    cells = int(np.prod(grid))
+    parity = None if args.no_parity else guarded(parity_periodic)
+    sim = PeriodicNavierStokesFlowSimulator3D(grid, X_RANGE, NU, real_t=np.float32, step_mode=(
+        "auto" if args.step_mode == "auto" else args.step_mode))
+    sim.vorticity_field[...] = torch.from_numpy(taylor_green_vorticity(grid)).cuda()
+    sim.compute_velocity_from_vorticity()
+    dt = float(0.1 * sim.dx)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    def device_step():
+        sim.time_step(dt)
+
+    def e2e_step():
+        sim.time_step(sim.compute_stable_timestep(dt_prefac=0.5))  # device reduction + D2H scalar every step
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    n0 = _lib.launch_count()
+    with ClockSampler(0) as clk:
+        ms = timed(device_step, args.steps)
+    launches = _lib.launch_count() - n0
+    value = cells * args.steps / (ms * 1e-3) / 1e9
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    peak, peak_src = measured_peak_hbm()
+    _lib.profile_enable(True)
+    torch.cuda.synchronize()
+    for _ in range(args.steps):
+        device_step()
+    torch.cuda.synchronize()
+    report = _lib.profile_report()
+    _lib.profile_enable(False)
+    kernels = {}
+    total = sum(v["ms"] for v in report.values()) or 1.0
+    for label, v in report.items():
+        e = {"launches_per_step": v["launches"] / args.steps, "ms_per_step": v["ms"] / args.steps,
+             "share": v["ms"] / total}
+        bpc = PERIODIC_KERNEL_BYTES.get(label)
+        if bpc:
+            e["algorithmic_bytes_per_cell"] = bpc
+            e["achieved_gbs"] = bpc * cells * v["launches"] / (v["ms"] * 1e-3) / 1e9
+            e["frac"] = e["achieved_gbs"] / peak
+        kernels[label] = e
+    # the Poisson solve as one entry (cuFFT passes + the symbol kernel): 120 B / cell algorithmic
+    pois_ms = sum(v["ms"] for k, v in report.items() if k.startswith("poisson"))
+    pois = {"ms_per_step": pois_ms / args.steps, "algorithmic_bytes_per_cell": 120.0,
+            "achieved_gbs": 120.0 * cells * args.steps / (pois_ms * 1e-3) / 1e9 if pois_ms else None}
+    if pois["achieved_gbs"]:
+        pois["frac"] = pois["achieved_gbs"] / peak
+    whole = PERIODIC_BYTES_PER_CELL * cells * args.steps / (ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": pois["achieved_gbs"], "peak": peak, "unit": "GB/s",
+            "frac": pois.get("frac"), "traffic": None, "kernel": "periodic Poisson solve (all passes)",
+            "algorithmic_bytes_per_launch": 120.0 * cells, "avg_launch_ms": pois["ms_per_step"],
+            "share_of_step": pois_ms / total, "peak_source": peak_src}
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import flow as oflow
+
+        g = cpu_sample_grid(grid, 2**22)
+        ref = oflow.PeriodicNavierStokesFlowSimulator3D(g, X_RANGE, NU, real_t=np.float32)
+        ref.vorticity_field[...] = taylor_green_vorticity(g)
+        ref.compute_velocity_from_vorticity()
+        ref.time_step(dt)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ref.time_step(dt)
+        el = (time.perf_counter() - t0) / 3
+        cpu = {"value": int(np.prod(g)) / el / 1e9, "unit": "Gcell/s", "cores": 1, "kind": "port",
+               "sample": f"3 steps (+1 warm-up) of the numpy restatement of the periodic step on a {g[0]}x{g[1]}x{g[2]} "
+                         f"grid (bounded sample), {el * 1e3:.0f} ms/step"}
+    line = {
+        "metric": "3D flow step Gcell-updates/s", "value": value, "unit": "Gcell/s", "n_gpus": 1,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl, grid, 1, 0),
+        "path": {"step_mode": sim.step_mode, "poisson_path": "periodic: cuFFT transforms + symbol kernel"},
+        "parity": parity,
+        "e2e": {"value": cells * args.steps / (ms_e2e * 1e-3) / 1e9, "unit": "Gcell/s",
+                "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
+                "note": "stable-dt read-back every step, then the step"},
+        "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof,
+        "step_roofline": {"algorithmic_bytes_per_cell": PERIODIC_BYTES_PER_CELL, "achieved": whole, "unit": "GB/s",
+                          "frac": whole / peak},
+        "kernels": kernels, "poisson": pois, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -702,7 +876,11 @@ def main():
     ap.add_argument("--no-parity", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
+    if wl.get("periodic"):
+        if args.impl == "reference":
+            raise SystemExit("the periodic workloads have no reference arm (the reference has no periodic case)")
+        run_periodic(args, wl)
+    elif args.impl == "reference":
         run_reference_arm(args, wl)
     else:
         run_ours(args, wl)

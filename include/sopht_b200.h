@@ -406,6 +406,11 @@ int sopht_peer_halo_exchange(sopht_peer_arena_t handle, int nfields, const int64
                              int64_t plane_bytes, void *stream);
 /* all-ranks barrier in stream order (everything enqueued before it on every rank is complete and visible) */
 int sopht_peer_barrier(sopht_peer_arena_t handle, void *stream);
+/* The device-side polls of the two calls above are bounded (SOPHT_PEER_TIMEOUT_S, default 30 s): a rank that died or
+ * issued another sequence of exchanges no longer hangs its neighbours' GPUs; the kernel gives up and records the rank
+ * it was waiting for. status() synchronises, returns 0 when healthy or a CUDA error code with the stalled rank in
+ * *stalled_rank_out (-1 when healthy). */
+int sopht_peer_arena_status(sopht_peer_arena_t handle, int *stalled_rank_out);
 int sopht_peer_arena_destroy(sopht_peer_arena_t handle);
 
 /* ------------------------------------------------------------------------ */
@@ -538,6 +543,24 @@ int sopht_ns3d_velocity_from_stream_function(int dtype, const sopht_field_t *vel
                                              const sopht_field_t *stream_func_field, double prefactor,
                                              const double *free_stream_velocity, void *max_abs_sum_out,
                                              void *stream);
+
+/* The same three passes for a PERIODIC box (BASELINE config 4; an extension - the reference has no periodic case,
+ * nearest reference step: navier_stokes_flow_simulators.py:449-485 without the penalisation). x and y neighbours wrap
+ * around inside the kernels and every row / cell of a plane is updated; z keeps the ghost-ring rule, i.e. the arrays are
+ * (3, nz + 2, ny, nx) with one halo plane per z side that the caller fills before the call: sopht_wrap_z_halos on one
+ * GPU, the neighbour rank's planes (sopht_peer_halo_exchange, periodic ring) in a slab decomposition. Rows must be
+ * 16-byte multiples (no fallback kernel: anything else is refused). */
+int sopht_ns3d_advect_rotational_periodic_xy(int dtype, const sopht_field_t *out_vorticity_field,
+                                             const sopht_field_t *vorticity_field,
+                                             const sopht_field_t *velocity_field, double prefactor, void *stream);
+int sopht_ns3d_diffuse_periodic_xy(int dtype, const sopht_field_t *out_field, const sopht_field_t *field,
+                                   double nu_dt_by_dx2, const sopht_field_t *zero_field, void *stream);
+int sopht_ns3d_velocity_from_stream_function_periodic_xy(int dtype, const sopht_field_t *velocity_field,
+                                                         const sopht_field_t *stream_func_field, double prefactor,
+                                                         const double *free_stream_velocity, void *max_abs_sum_out,
+                                                         void *stream);
+/* field (C, nz + 2, ny, nx) or (nz + 2, ny, nx): plane 0 <- plane nz, plane nz + 1 <- plane 1 (one launch) */
+int sopht_wrap_z_halos(int dtype, const sopht_field_t *field, void *stream);
 
 #ifdef __cplusplus
 }

@@ -12,13 +12,18 @@ from . import stencils as ost
 
 
 def compute_advection_diffusion_stable_timestep(
-    velocity_field, velocity_magnitude_field, grid_dim, dx, cfl, kinematic_viscosity, real_t=np.float32
+    velocity_field, velocity_magnitude_field, grid_dim, dx, cfl, kinematic_viscosity, real_t=np.float32,
+    kernels=None,
 ):
     """passive_transport_flow_simulators.py:139-155 (writes velocity_magnitude_field)."""
     tol = 10 * np.finfo(real_t).eps
-    velocity_magnitude_field[...] = np.sum(np.fabs(velocity_field), axis=0)
+    if kernels is not None and hasattr(kernels, "abs_sum_max"):
+        vmax = kernels.abs_sum_max(velocity_magnitude_field, velocity_field)
+    else:
+        velocity_magnitude_field[...] = np.sum(np.fabs(velocity_field), axis=0)
+        vmax = np.amax(velocity_magnitude_field)
     return min(
-        cfl * dx / (np.amax(velocity_magnitude_field) + tol),
+        cfl * dx / (vmax + tol),
         0.9 * dx**2 / (2 * grid_dim) / kinematic_viscosity + tol,
     )
 
@@ -40,7 +45,8 @@ class UnboundedNavierStokesFlowSimulator3D:
 
     def __init__(self, grid_size, x_range, kinematic_viscosity, cfl=0.1, real_t=np.float32, time=0.0,
                  with_forcing=False, with_free_stream_flow=False, filter_vorticity=False,
-                 flow_density=1.0, workers=1, **kwargs):
+                 flow_density=1.0, workers=1, kernels=None, **kwargs):
+        self._k = kernels if kernels is not None else ost  # kernel vocabulary: numpy (default) or oracle.cstencils
         self.grid_dim = 3
         self.grid_size = tuple(grid_size)
         self.x_range = x_range
@@ -66,33 +72,34 @@ class UnboundedNavierStokesFlowSimulator3D:
         if with_forcing:
             self.eul_grid_forcing_field = np.zeros_like(self.velocity_field)
         nz, ny, nx = self.grid_size
-        self._poisson = opoisson.UnboundedPoissonSolver3D(nz, ny, nx, x_range=x_range, real_t=real_t, workers=workers)
+        self._poisson = opoisson.UnboundedPoissonSolver3D(
+            nz, ny, nx, x_range=x_range, real_t=real_t, workers=workers, kernels=kernels)
 
     def _navier_stokes_time_step(self, dt, free_stream_velocity=(0.0, 0.0, 0.0)):
         """navier_stokes_flow_simulators.py:449-485."""
         t = self.real_t
-        ost.elementwise_cross_product(self.buffer_vector_field, self.velocity_field, self.vorticity_field)
-        ost.update_vorticity_from_velocity_forcing_3d(
+        self._k.elementwise_cross_product(self.buffer_vector_field, self.velocity_field, self.vorticity_field)
+        self._k.update_vorticity_from_velocity_forcing_3d(
             self.vorticity_field, self.buffer_vector_field, t(dt / (2 * self.dx)))
-        ost.diffusion_timestep_euler_forward_vector(
+        self._k.diffusion_timestep_euler_forward_vector(
             self.vorticity_field, self.buffer_scalar_field, t(self.kinematic_viscosity * dt / self.dx / self.dx))
         if self.filter_vorticity:
-            ost.laplacian_filter_3d_vector(
+            self._k.laplacian_filter_3d_vector(
                 self.vorticity_field, self.buffer_vector_field[0], self.buffer_vector_field[1],
                 self.filter_setting_dict["order"], self.filter_setting_dict["type"])
-        ost.penalise_field_boundary_vector(self.vorticity_field, self.penalty_zone_width, self.dx, self.coords)
+        self._k.penalise_field_boundary_vector(self.vorticity_field, self.penalty_zone_width, self.dx, self.coords)
         self._poisson.vector_field_solve(self.stream_func_field, self.vorticity_field)
-        ost.curl_3d(self.velocity_field, self.stream_func_field, t(0.5 / self.dx))
+        self._k.curl_3d(self.velocity_field, self.stream_func_field, t(0.5 / self.dx))
         if self.with_free_stream_flow:
-            ost.add_fixed_val_vector(self.velocity_field, self.velocity_field, free_stream_velocity)
+            self._k.add_fixed_val_vector(self.velocity_field, self.velocity_field, free_stream_velocity)
 
     def _navier_stokes_with_forcing_time_step(self, dt, free_stream_velocity=(0.0, 0.0, 0.0)):
         """navier_stokes_flow_simulators.py:487-498."""
-        ost.update_vorticity_from_velocity_forcing_3d(
+        self._k.update_vorticity_from_velocity_forcing_3d(
             self.vorticity_field, self.eul_grid_forcing_field,
             self.real_t(dt / (2 * self.dx * self.flow_density)))
         self._navier_stokes_time_step(dt, free_stream_velocity)
-        ost.set_fixed_val_vector(self.eul_grid_forcing_field, [0.0] * 3)
+        self._k.set_fixed_val_vector(self.eul_grid_forcing_field, [0.0] * 3)
 
     def time_step(self, dt, free_stream_velocity=(0.0, 0.0, 0.0)):
         if self.with_forcing:
@@ -104,14 +111,15 @@ class UnboundedNavierStokesFlowSimulator3D:
     def compute_stable_timestep(self, dt_prefac=1.0):
         return dt_prefac * compute_advection_diffusion_stable_timestep(
             self.velocity_field, self.buffer_scalar_field, 3, self.dx, self.cfl,
-            self.kinematic_viscosity, self.real_t)
+            self.kinematic_viscosity, self.real_t, kernels=self._k)
 
 
 class UnboundedNavierStokesFlowSimulator2D:
     """navier_stokes_flow_simulators.py:24-209."""
 
     def __init__(self, grid_size, x_range, kinematic_viscosity, cfl=0.1, real_t=np.float32, time=0.0,
-                 with_forcing=False, with_free_stream_flow=False, flow_density=1.0, workers=1, **kwargs):
+                 with_forcing=False, with_free_stream_flow=False, flow_density=1.0, workers=1, kernels=None, **kwargs):
+        self._k = kernels if kernels is not None else ost
         self.grid_dim = 2
         self.grid_size = tuple(grid_size)
         self.x_range = x_range
@@ -133,28 +141,29 @@ class UnboundedNavierStokesFlowSimulator2D:
         if with_forcing:
             self.eul_grid_forcing_field = np.zeros_like(self.velocity_field)
         ny, nx = self.grid_size
-        self._poisson = opoisson.UnboundedPoissonSolver2D(ny, nx, x_range=x_range, real_t=real_t, workers=workers)
+        self._poisson = opoisson.UnboundedPoissonSolver2D(
+            ny, nx, x_range=x_range, real_t=real_t, workers=workers, kernels=kernels)
 
     def _navier_stokes_time_step(self, dt, free_stream_velocity=(0.0, 0.0)):
         """navier_stokes_flow_simulators.py:171-195."""
         t = self.real_t
-        ost.advection_timestep_euler_forward_conservative_eno3(
+        self._k.advection_timestep_euler_forward_conservative_eno3(
             self.vorticity_field, self.buffer_scalar_field, self.velocity_field, t(dt / self.dx))
-        ost.diffusion_timestep_euler_forward(
+        self._k.diffusion_timestep_euler_forward(
             self.vorticity_field, self.buffer_scalar_field, t(self.kinematic_viscosity * dt / self.dx / self.dx))
-        ost.penalise_field_boundary(self.vorticity_field, self.penalty_zone_width, self.dx, self.coords)
+        self._k.penalise_field_boundary(self.vorticity_field, self.penalty_zone_width, self.dx, self.coords)
         self._poisson.solve(self.stream_func_field, self.vorticity_field)
-        ost.outplane_field_curl_2d(self.velocity_field, self.stream_func_field, t(0.5 / self.dx))
+        self._k.outplane_field_curl_2d(self.velocity_field, self.stream_func_field, t(0.5 / self.dx))
         if self.with_free_stream_flow:
-            ost.add_fixed_val_vector(self.velocity_field, self.velocity_field, free_stream_velocity)
+            self._k.add_fixed_val_vector(self.velocity_field, self.velocity_field, free_stream_velocity)
 
     def _navier_stokes_with_forcing_time_step(self, dt, free_stream_velocity=(0.0, 0.0)):
         """navier_stokes_flow_simulators.py:197-209."""
-        ost.update_vorticity_from_velocity_forcing_2d(
+        self._k.update_vorticity_from_velocity_forcing_2d(
             self.vorticity_field, self.eul_grid_forcing_field,
             self.real_t(dt / (2 * self.dx * self.flow_density)))
         self._navier_stokes_time_step(dt, free_stream_velocity)
-        ost.set_fixed_val_vector(self.eul_grid_forcing_field, [0.0] * 2)
+        self._k.set_fixed_val_vector(self.eul_grid_forcing_field, [0.0] * 2)
 
     def time_step(self, dt, free_stream_velocity=(0.0, 0.0)):
         if self.with_forcing:
@@ -166,7 +175,7 @@ class UnboundedNavierStokesFlowSimulator2D:
     def compute_stable_timestep(self, dt_prefac=1.0):
         return dt_prefac * compute_advection_diffusion_stable_timestep(
             self.velocity_field, self.buffer_scalar_field, 2, self.dx, self.cfl,
-            self.kinematic_viscosity, self.real_t)
+            self.kinematic_viscosity, self.real_t, kernels=self._k)
 
 
 def wrap_halos(field):

@@ -13,7 +13,9 @@ from scipy.fft import irfftn, rfftn
 
 
 class UnboundedPoissonSolver3D:
-    def __init__(self, grid_size_z, grid_size_y, grid_size_x, x_range=1.0, real_t=np.float64, workers=1):
+    def __init__(self, grid_size_z, grid_size_y, grid_size_x, x_range=1.0, real_t=np.float64, workers=1,
+                 kernels=None):
+        self._k = kernels  # None: numpy slice arithmetic; oracle.cstencils: the reference's elementwise kernel passes
         self.nz, self.ny, self.nx = grid_size_z, grid_size_y, grid_size_x
         self.real_t = real_t
         self.workers = workers
@@ -42,11 +44,21 @@ class UnboundedPoissonSolver3D:
 
     def solve(self, solution_field, rhs_field):  # :111-149
         buf = self.domain_doubled_buffer
+        corner = (slice(None, self.nz), slice(None, self.ny), slice(None, self.nx))
+        if self._k is not None:  # the reference's own passes: set_fixed_val, copy, rfft, complex product, irfft, copy
+            k = self._k
+            k.set_fixed_val(buf, 0)
+            k.elementwise_copy(buf[corner], rhs_field)
+            spec = rfftn(buf, workers=self.workers)
+            k.elementwise_complex_product(spec, spec, self.fourier_greens_function_times_dx_cubed)
+            back = irfftn(spec, s=buf.shape, workers=self.workers, overwrite_x=True)
+            k.elementwise_copy(solution_field, back[corner])
+            return
         buf[...] = 0
-        buf[: self.nz, : self.ny, : self.nx] = rhs_field
+        buf[corner] = rhs_field
         spec = rfftn(buf, workers=self.workers)
         spec = spec * self.fourier_greens_function_times_dx_cubed
-        solution_field[...] = irfftn(spec, s=buf.shape, workers=self.workers)[: self.nz, : self.ny, : self.nx]
+        solution_field[...] = irfftn(spec, s=buf.shape, workers=self.workers)[corner]
 
     def vector_field_solve(self, solution_vector_field, rhs_vector_field):  # :151-172
         for c in range(3):
@@ -54,7 +66,8 @@ class UnboundedPoissonSolver3D:
 
 
 class UnboundedPoissonSolver2D:
-    def __init__(self, grid_size_y, grid_size_x, x_range=1.0, real_t=np.float64, workers=1):
+    def __init__(self, grid_size_y, grid_size_x, x_range=1.0, real_t=np.float64, workers=1, kernels=None):
+        self._k = kernels
         self.ny, self.nx = grid_size_y, grid_size_x
         self.real_t = real_t
         self.workers = workers
@@ -79,11 +92,21 @@ class UnboundedPoissonSolver2D:
 
     def solve(self, solution_field, rhs_field):  # :95-129
         buf = self.domain_doubled_buffer
+        corner = (slice(None, self.ny), slice(None, self.nx))
+        if self._k is not None:
+            k = self._k
+            k.set_fixed_val(buf, 0)
+            k.elementwise_copy(buf[corner], rhs_field)
+            spec = rfftn(buf, workers=self.workers)
+            k.elementwise_complex_product(spec, spec, self.fourier_greens_function_times_dx_squared)
+            back = irfftn(spec, s=buf.shape, workers=self.workers, overwrite_x=True)
+            k.elementwise_copy(solution_field, back[corner])
+            return
         buf[...] = 0
-        buf[: self.ny, : self.nx] = rhs_field
+        buf[corner] = rhs_field
         spec = rfftn(buf, workers=self.workers)
         spec = spec * self.fourier_greens_function_times_dx_squared
-        solution_field[...] = irfftn(spec, s=buf.shape, workers=self.workers)[: self.ny, : self.nx]
+        solution_field[...] = irfftn(spec, s=buf.shape, workers=self.workers)[corner]
 
 
 class FastDiagPoissonSolver:

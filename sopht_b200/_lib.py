@@ -56,6 +56,7 @@ _SIGNATURES: dict[str, list[Any]] = {
     "sopht_brinkmann_penalise_vs_fixed_val": [_F, _F, _F, _D, _D],
     "sopht_char_func_from_level_set": [_F, _F, _D],
     "sopht_abs_sum_max": [_F, _F, _P],
+    "sopht_wrap_z_halos": [_F],
     "sopht_diffusion_flux_3d": [_F, _F, _D, _I],
     "sopht_curl_3d": [_F, _F, _D, _I],
     "sopht_divergence_3d": [_F, _F, _D, _I],
@@ -173,11 +174,15 @@ _HANDLE_SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
          ctypes.c_int64, _P],
     ),
     "sopht_peer_barrier": (ctypes.c_int, [_P, _P]),
+    "sopht_peer_arena_status": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int)]),
     "sopht_peer_arena_destroy": (ctypes.c_int, [_P]),
     # fused 3-D Navier-Stokes passes
     "sopht_ns3d_advect_rotational": (ctypes.c_int, [_I, _F, _F, _F, _D, _P]),
     "sopht_ns3d_diffuse": (ctypes.c_int, [_I, _F, _F, _D, _F, _P]),
     "sopht_ns3d_velocity_from_stream_function": (ctypes.c_int, [_I, _F, _F, _D, _PD, _P, _P]),
+    "sopht_ns3d_advect_rotational_periodic_xy": (ctypes.c_int, [_I, _F, _F, _F, _D, _P]),
+    "sopht_ns3d_diffuse_periodic_xy": (ctypes.c_int, [_I, _F, _F, _D, _F, _P]),
+    "sopht_ns3d_velocity_from_stream_function_periodic_xy": (ctypes.c_int, [_I, _F, _F, _D, _PD, _P, _P]),
     # immersed boundary (int dtype, int dim, ...)
     "sopht_ib_local_support": (ctypes.c_int, [_I, _I, _F, _F, _F, _I, _D, _D, _P]),
     "sopht_ib_interpolation_weights": (ctypes.c_int, [_I, _I, _I, _F, _F, _D, _D, _P]),
@@ -402,6 +407,7 @@ class Staging:
 
     def __init__(self) -> None:
         self._map: dict[tuple, torch.Tensor] = {}
+        self._arrays: list[tuple[tuple, np.ndarray, bool]] = []  # (key, array, is_output) of every staged view
         self._writeback: list[tuple[np.ndarray, torch.Tensor]] = []
 
     def __enter__(self) -> "Staging":
@@ -412,13 +418,26 @@ class Staging:
             for arr, t in self._writeback:
                 arr[...] = t.cpu().numpy()
         self._map.clear()
+        self._arrays.clear()
         self._writeback.clear()
+
+    def _check_overlap(self, key: tuple, a: np.ndarray, out: bool) -> None:
+        """Two DIFFERENT views of one host buffer (a field and its slice, a vector field and one component) become
+        independent device copies, and the later write-back would silently clobber the earlier one - the reference's
+        in-place numpy semantics cannot be kept, so refuse instead of returning wrong data."""
+        for k2, b, out2 in self._arrays:
+            if k2 != key and (out or out2) and np.shares_memory(a, b):
+                msg = ("numpy arguments that partially overlap (different views of one buffer, one of them an output) "
+                       "cannot be staged through the device; pass CUDA tensors (views alias there) or disjoint arrays")
+                raise ValueError(msg)
+        self._arrays.append((key, a, out))
 
     def _get(self, a: Any, out: bool) -> torch.Tensor:
         if isinstance(a, torch.Tensor):
             return a
         if isinstance(a, np.ndarray):
             key = (a.__array_interface__["data"][0], a.shape, a.strides, a.dtype.str)
+            self._check_overlap(key, a, out)
             t = self._map.get(key)
             if t is None:
                 if not torch.cuda.is_available():

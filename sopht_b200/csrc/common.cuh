@@ -56,6 +56,15 @@ struct ProfScope {
 bool ns3d_try_forcing_curl_vec(int dtype, const sopht_field_t* vorticity_field,
                                const sopht_field_t* velocity_forcing_field, double prefactor, cudaStream_t st);
 
+// max that keeps a NaN once it has seen one (numpy's amax does; `a > m ? a : m` drops it): a diverged velocity field must
+// show up as dt = NaN in compute_stable_timestep like in the reference (passive_transport_flow_simulators.py:150-155).
+// A NaN is returned with the sign bit clear so that the integer atomicMax of AtomicMaxNonNeg ranks it above every float.
+template <typename T>
+__host__ __device__ __forceinline__ T nanmax(T a, T m) {
+  if (a != a) return fabs(a);
+  return (a > m) ? a : m;  // m NaN: comparison false, m kept
+}
+
 // ---- device-side views ----------------------------------------------------------------------
 // 3-D scalar view (z, y, x); strides in elements.
 template <typename T>

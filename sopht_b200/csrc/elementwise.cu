@@ -350,12 +350,12 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
       for (int c = 0; c < DIM; ++c) s += fabs(vel[c * vc + o]);
       mag[k * ms0 + j * ms1 + i * ms2] = s;
-      m = s > m ? s : m;
+      m = nanmax(s, m);
     }
   }
   for (int off = 16; off > 0; off >>= 1) {
     const T o = __shfl_xor_sync(0xffffffffu, m, off);
-    m = o > m ? o : m;
+    m = nanmax(o, m);
   }
   __shared__ T wm[8];
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(256)
     m = tid < nw ? wm[tid] : T(0);
     for (int off = 4; off > 0; off >>= 1) {
       const T o = __shfl_xor_sync(0xffffffffu, m, off);
-      m = o > m ? o : m;
+      m = nanmax(o, m);
     }
     if (tid == 0) MaxBits<T>::atomic_max(max_out, m);
   }

@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(FTHREADS, 2)
       out.p[1][o] = uy;
       out.p[2][o] = uz;
       const T a = fabs(ux) + fabs(uy) + fabs(uz);
-      m = a > m ? a : m;
+      m = nanmax(a, m);
     }
     pprev_x = pcur_x, pprev_y = pcur_y;
     pcur_x = pnext_x, pcur_y = pnext_y;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(FTHREADS, 2)
   if (max_out) {
     for (int off = 16; off > 0; off >>= 1) {
       const T o = __shfl_xor_sync(0xffffffffu, m, off);
-      m = o > m ? o : m;
+      m = nanmax(o, m);
     }
     const int tid = ty * FTX + tx;
     if ((tid & 31) == 0) wmax[tid >> 5] = m;
@@ -280,7 +280,7 @@ __global__ void __launch_bounds__(FTHREADS, 2)
       m = tid < FTHREADS / 32 ? wmax[tid] : T(0);
       for (int off = 16; off > 0; off >>= 1) {
         const T o = __shfl_xor_sync(0xffffffffu, m, off);
-        m = o > m ? o : m;
+        m = nanmax(o, m);
       }
       if (tid == 0) AtomicMaxNonNeg<T>::apply(max_out, m);
     }
@@ -319,7 +319,7 @@ __device__ __forceinline__ Vec<T> cross_z(const Vec<T>* u, const Vec<T>* w) {
 }
 
 // out = w + p * curl_c(u x w). 24 B read + 12 B written per cell (fp32).
-template <typename T>
+template <typename T, bool PXY>
 __global__ void __launch_bounds__(32 * VBY, 2)
     advect_vec_kernel(Vec3Out<T> out, Vec3View<T> w, Vec3View<T> u, T p, int nz, int ny, int nx, int kchunk) {
   constexpr int W = Vec<T>::W;
@@ -329,9 +329,8 @@ __global__ void __launch_bounds__(32 * VBY, 2)
   if (j >= ny) return;  // warp-uniform
   const int k0 = blockIdx.z * kchunk, k1 = min(k0 + kchunk, nz);
   const bool act = i0 < nx;
-  const bool jin = j >= 1 && j < ny - 1;
-  const bool has_l = lane == 0 && act && i0 > 0;
-  const bool has_r = lane == 31 && act && i0 + W < nx;
+  const sv::Nbr<PXY> nb(act, lane, i0, W, j, ny, nx, w.sy);
+  const bool jin = nb.jin, has_l = nb.has_l, has_r = nb.has_r;
   const int64_t col = (int64_t)j * w.sy + i0;  // u shares sz / sy with w (checked on the host)
   const int64_t ocol = (int64_t)j * out.sy + i0;
 
@@ -359,19 +358,19 @@ __global__ void __launch_bounds__(32 * VBY, 2)
     // issue every load of this iteration first: next plane (centre), rows j+1 / j-1 and the two x edges
     Vec<T> un[3], wn[3], uu[3], wu[3], ud[3], wd[3];
     T ul[3], wl[3], ur[3], wr[3];
-    const bool kn = act && k + 1 < nz, up = act && j + 1 < ny, dn = act && j >= 1;
+    const bool kn = act && k + 1 < nz, up = nb.has_up, dn = nb.has_dn;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       un[c] = sv::vload_if(kn, u.p[c] + pl + w.sz);
       wn[c] = sv::vload_if(kn, w.p[c] + pl + w.sz);
-      uu[c] = sv::vload_if(up, u.p[c] + pl + w.sy);
-      wu[c] = sv::vload_if(up, w.p[c] + pl + w.sy);
-      ud[c] = sv::vload_if(dn, u.p[c] + pl - w.sy);
-      wd[c] = sv::vload_if(dn, w.p[c] + pl - w.sy);
-      ul[c] = sv::sload_if(has_l, u.p[c] + pl - 1);
-      wl[c] = sv::sload_if(has_l, w.p[c] + pl - 1);
-      ur[c] = sv::sload_if(has_r, u.p[c] + pl + W);
-      wr[c] = sv::sload_if(has_r, w.p[c] + pl + W);
+      uu[c] = sv::vload_if(up, u.p[c] + pl + nb.up);
+      wu[c] = sv::vload_if(up, w.p[c] + pl + nb.up);
+      ud[c] = sv::vload_if(dn, u.p[c] + pl + nb.dn);
+      wd[c] = sv::vload_if(dn, w.p[c] + pl + nb.dn);
+      ul[c] = sv::sload_if(has_l, u.p[c] + pl + nb.left);
+      wl[c] = sv::sload_if(has_l, w.p[c] + pl + nb.left);
+      ur[c] = sv::sload_if(has_r, u.p[c] + pl + nb.right);
+      wr[c] = sv::sload_if(has_r, w.p[c] + pl + nb.right);
     }
     const Vec<T> bnext_x = cross_x(un, wn), bnext_y = cross_y(un, wn), bnext_z = cross_z(un, wn);
     const Vec<T> bz_jp = cross_z(uu, wu), bx_jp = cross_x(uu, wu);
@@ -379,15 +378,15 @@ __global__ void __launch_bounds__(32 * VBY, 2)
     const T ebz_l = ul[0] * wl[1] - wl[0] * ul[1], eby_l = ul[2] * wl[0] - wl[2] * ul[0];
     const T ebz_r = ur[0] * wr[1] - wr[0] * ur[1], eby_r = ur[2] * wr[0] - wr[2] * ur[0];
     Vec<T> bz_im, bz_ip, by_im, by_ip;
-    sv::x_neighbours(bcur_z, ebz_l, ebz_r, lane, bz_im, bz_ip);
-    sv::x_neighbours(bcur_y, eby_l, eby_r, lane, by_im, by_ip);
+    sv::x_neighbours(bcur_z, ebz_l, ebz_r, nb.use_l(lane), nb.use_r(lane), bz_im, bz_ip);
+    sv::x_neighbours(bcur_y, eby_l, eby_r, nb.use_l(lane), nb.use_r(lane), by_im, by_ip);
     if (act) {
       Vec<T> ox = wc[0], oy = wc[1], oz = wc[2];
       if (jin && k >= 1 && k < nz - 1) {
 #pragma unroll
         for (int m = 0; m < W; ++m) {
           const int i = i0 + m;
-          if (i >= 1 && i < nx - 1) {
+          if (nb.iin(i, nx)) {
             const T ccx = bz_jp.v[m] - bz_jm.v[m] - bnext_y.v[m] + bprev_y.v[m];
             const T ccy = bnext_x.v[m] - bprev_x.v[m] - bz_ip.v[m] + bz_im.v[m];
             const T ccz = by_ip.v[m] - by_im.v[m] - bx_jp.v[m] + bx_jm.v[m];
@@ -410,7 +409,7 @@ __global__ void __launch_bounds__(32 * VBY, 2)
 }
 
 // out = f + q * Lap_7pt(f) [, zero <- 0]; blockIdx.z = chunk * ncomp + comp. 4 + 4 (+4) B per cell (fp32).
-template <typename T>
+template <typename T, bool PXY>
 __global__ void __launch_bounds__(32 * VBY)
     diffuse_vec_kernel(Vec3Out<T> out, Vec3View<T> in, Vec3Out<T> zero, int has_zero, int ncomp, T q, int nz,
                        int ny, int nx, int kchunk) {
@@ -425,10 +424,8 @@ __global__ void __launch_bounds__(32 * VBY)
   T* o_p = comp == 0 ? out.p[0] : (comp == 1 ? out.p[1] : out.p[2]);
   T* z_p = comp == 0 ? zero.p[0] : (comp == 1 ? zero.p[1] : zero.p[2]);
   const bool act = i0 < nx;
-  const bool jin = j >= 1 && j < ny - 1;
-  const bool has_l = lane == 0 && act && i0 > 0;
-  const bool has_r = lane == 31 && act && i0 + W < nx;
-  const bool up = act && j + 1 < ny, dn = act && j >= 1;
+  const sv::Nbr<PXY> nb(act, lane, i0, W, j, ny, nx, in.sy);
+  const bool jin = nb.jin, has_l = nb.has_l, has_r = nb.has_r, up = nb.has_up, dn = nb.has_dn;
   f += (int64_t)j * in.sy + i0;
   o_p += (int64_t)j * out.sy + i0;
   z_p += (int64_t)j * zero.sy + i0;
@@ -439,18 +436,18 @@ __global__ void __launch_bounds__(32 * VBY)
   for (int k = k0; k < k1; ++k) {
     const T* pk = f + (int64_t)k * in.sz;
     const Vec<T> fnext = sv::vload_if(act && k + 1 < nz, pk + in.sz);
-    const Vec<T> fup = sv::vload_if(up, pk + in.sy);
-    const Vec<T> fdn = sv::vload_if(dn, pk - in.sy);
-    const T el = sv::sload_if(has_l, pk - 1), er = sv::sload_if(has_r, pk + W);
+    const Vec<T> fup = sv::vload_if(up, pk + nb.up);
+    const Vec<T> fdn = sv::vload_if(dn, pk + nb.dn);
+    const T el = sv::sload_if(has_l, pk + nb.left), er = sv::sload_if(has_r, pk + nb.right);
     Vec<T> xl, xr;
-    sv::x_neighbours(fcur, el, er, lane, xl, xr);
+    sv::x_neighbours(fcur, el, er, nb.use_l(lane), nb.use_r(lane), xl, xr);
     if (act) {
       Vec<T> v = fcur;
       if (jin && k >= 1 && k < nz - 1) {
 #pragma unroll
         for (int m = 0; m < W; ++m) {
           const int i = i0 + m;
-          if (i >= 1 && i < nx - 1) {
+          if (nb.iin(i, nx)) {
             const T flux =
                 q * (fnext.v[m] + fprev.v[m] + fup.v[m] + fdn.v[m] + xr.v[m] + xl.v[m] - T(6) * fcur.v[m]);
             v.v[m] = fcur.v[m] + flux;
@@ -469,7 +466,7 @@ __global__ void __launch_bounds__(32 * VBY)
 //                cell (fp32).
 // ACCUM = true : out += p * curl_c(psi) on the interior, ring cells untouched (the forcing update
 //                w += p curl(f), update_vorticity_from_velocity_forcing_3d.py:12-132). 24 B read + 12 B written.
-template <typename T, bool ACCUM>
+template <typename T, bool ACCUM, bool PXY = false>
 __global__ void __launch_bounds__(32 * VBY)
     velocity_vec_kernel(Vec3Out<T> out, Vec3View<T> psi, T p, T fx, T fy, T fz, T* max_out, int nz, int ny,
                         int nx, int kchunk) {
@@ -481,10 +478,8 @@ __global__ void __launch_bounds__(32 * VBY)
   const int k0 = blockIdx.z * kchunk, k1 = min(k0 + kchunk, nz);
   const bool row = j < ny;
   const bool act = row && i0 < nx;
-  const bool jin = j >= 1 && j < ny - 1;
-  const bool has_l = lane == 0 && act && i0 > 0;
-  const bool has_r = lane == 31 && act && i0 + W < nx;
-  const bool up = act && j + 1 < ny, dn = act && j >= 1;
+  const sv::Nbr<PXY> nb(act, lane, i0, W, j, ny, nx, psi.sy);
+  const bool jin = nb.jin, has_l = nb.has_l, has_r = nb.has_r, up = nb.has_up, dn = nb.has_dn;
   const int64_t col = (int64_t)j * psi.sy + i0;
   const int64_t ocol = (int64_t)j * out.sy + i0;
   T m_acc = T(0);
@@ -501,15 +496,15 @@ __global__ void __launch_bounds__(32 * VBY)
     const Vec<T> pxn = sv::vload_if(kn, psi.p[0] + pl + psi.sz);
     const Vec<T> pyn = sv::vload_if(kn, psi.p[1] + pl + psi.sz);
     const Vec<T> pzc = sv::vload_if(act, psi.p[2] + pl);
-    const Vec<T> pz_jp = sv::vload_if(up, psi.p[2] + pl + psi.sy);
-    const Vec<T> pz_jm = sv::vload_if(dn, psi.p[2] + pl - psi.sy);
-    const Vec<T> px_jp = sv::vload_if(up, psi.p[0] + pl + psi.sy);
-    const Vec<T> px_jm = sv::vload_if(dn, psi.p[0] + pl - psi.sy);
-    const T ezl = sv::sload_if(has_l, psi.p[2] + pl - 1), ezr = sv::sload_if(has_r, psi.p[2] + pl + W);
-    const T eyl = sv::sload_if(has_l, psi.p[1] + pl - 1), eyr = sv::sload_if(has_r, psi.p[1] + pl + W);
+    const Vec<T> pz_jp = sv::vload_if(up, psi.p[2] + pl + nb.up);
+    const Vec<T> pz_jm = sv::vload_if(dn, psi.p[2] + pl + nb.dn);
+    const Vec<T> px_jp = sv::vload_if(up, psi.p[0] + pl + nb.up);
+    const Vec<T> px_jm = sv::vload_if(dn, psi.p[0] + pl + nb.dn);
+    const T ezl = sv::sload_if(has_l, psi.p[2] + pl + nb.left), ezr = sv::sload_if(has_r, psi.p[2] + pl + nb.right);
+    const T eyl = sv::sload_if(has_l, psi.p[1] + pl + nb.left), eyr = sv::sload_if(has_r, psi.p[1] + pl + nb.right);
     Vec<T> pz_im, pz_ip, py_im, py_ip;
-    sv::x_neighbours(pzc, ezl, ezr, lane, pz_im, pz_ip);
-    sv::x_neighbours(pyc, eyl, eyr, lane, py_im, py_ip);
+    sv::x_neighbours(pzc, ezl, ezr, nb.use_l(lane), nb.use_r(lane), pz_im, pz_ip);
+    sv::x_neighbours(pyc, eyl, eyr, nb.use_l(lane), nb.use_r(lane), py_im, py_ip);
     const bool kin = jin && k >= 1 && k < nz - 1;
     if (act && (!ACCUM || kin)) {  // accumulate mode: a ring plane / ring row keeps its values (warp-uniform)
       Vec<T> ux, uy, uz;
@@ -519,7 +514,7 @@ __global__ void __launch_bounds__(32 * VBY)
       for (int m = 0; m < W; ++m) {
         const int i = i0 + m;
         if (ACCUM) {
-          if (i >= 1 && i < nx - 1) {
+          if (nb.iin(i, nx)) {
             ux.v[m] += p * (pz_jp.v[m] - pz_jm.v[m] - pyn.v[m] + pym.v[m]);
             uy.v[m] += p * (pxn.v[m] - pxm.v[m] - pz_ip.v[m] + pz_im.v[m]);
             uz.v[m] += p * (py_ip.v[m] - py_im.v[m] - px_jp.v[m] + px_jm.v[m]);
@@ -527,7 +522,7 @@ __global__ void __launch_bounds__(32 * VBY)
           continue;
         }
         T vx = T(0), vy = T(0), vz = T(0);
-        if (kin && i >= 1 && i < nx - 1) {
+        if (kin && nb.iin(i, nx)) {
           const T ccx = pz_jp.v[m] - pz_jm.v[m] - pyn.v[m] + pym.v[m];
           const T ccy = pxn.v[m] - pxm.v[m] - pz_ip.v[m] + pz_im.v[m];
           const T ccz = py_ip.v[m] - py_im.v[m] - px_jp.v[m] + px_jm.v[m];
@@ -540,7 +535,7 @@ __global__ void __launch_bounds__(32 * VBY)
         vz = vz + fz;
         ux.v[m] = vx, uy.v[m] = vy, uz.v[m] = vz;
         const T a = fabs(vx) + fabs(vy) + fabs(vz);
-        m_acc = a > m_acc ? a : m_acc;
+        m_acc = nanmax(a, m_acc);
       }
       sv::vstore(out.p[0] + o, ux);
       sv::vstore(out.p[1] + o, uy);
@@ -552,14 +547,14 @@ __global__ void __launch_bounds__(32 * VBY)
   if (!ACCUM && max_out) {
     for (int off = 16; off > 0; off >>= 1) {
       const T o = __shfl_xor_sync(0xffffffffu, m_acc, off);
-      m_acc = o > m_acc ? o : m_acc;
+      m_acc = nanmax(o, m_acc);
     }
     if (lane == 0) wmax[threadIdx.y] = m_acc;
     __syncthreads();
     if (threadIdx.y == 0 && lane == 0) {
       T m = wmax[0];
 #pragma unroll
-      for (int r = 1; r < VBY; ++r) m = wmax[r] > m ? wmax[r] : m;
+      for (int r = 1; r < VBY; ++r) m = nanmax(wmax[r], m);
       AtomicMaxNonNeg<T>::apply(max_out, m);
     }
   }
@@ -703,23 +698,21 @@ using namespace sopht;
     if (rc__) return rc__; \
   } while (0)
 
-extern "C" {
-
-int sopht_ns3d_advect_rotational(int dtype, const sopht_field_t* out_vorticity_field,
-                                 const sopht_field_t* vorticity_field,
-                                 const sopht_field_t* velocity_field, double prefactor, void* stream) {
+static int ns3d_advect(const char* fn, bool pxy, int dtype, const sopht_field_t* out_vorticity_field,
+                       const sopht_field_t* vorticity_field, const sopht_field_t* velocity_field,
+                       double prefactor, void* stream) {
   SOPHT_CHECK_DTYPE(dtype);
-  RETURN_IF(check_vec3(__func__, out_vorticity_field));
-  RETURN_IF(check_vec3(__func__, vorticity_field));
-  RETURN_IF(check_vec3(__func__, velocity_field));
+  RETURN_IF(check_vec3(fn, out_vorticity_field));
+  RETURN_IF(check_vec3(fn, vorticity_field));
+  RETURN_IF(check_vec3(fn, velocity_field));
   if (!same_shape(out_vorticity_field, vorticity_field) || !same_shape(out_vorticity_field, velocity_field))
-    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: field shapes differ", __func__);
+    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: field shapes differ", fn);
   if (vorticity_field->stride[1] != velocity_field->stride[1] ||
       vorticity_field->stride[2] != velocity_field->stride[2])
-    SOPHT_FAIL(SOPHT_ERR_STRIDE, "%s: vorticity and velocity must share their plane/row strides", __func__);
+    SOPHT_FAIL(SOPHT_ERR_STRIDE, "%s: vorticity and velocity must share their plane/row strides", fn);
   const size_t elem = dtype == SOPHT_F32 ? 4 : 8;
   if (overlaps(out_vorticity_field, vorticity_field, elem) || overlaps(out_vorticity_field, velocity_field, elem))
-    SOPHT_FAIL(SOPHT_ERR_ARG, "%s: the output must not alias an input (neighbours are read)", __func__);
+    SOPHT_FAIL(SOPHT_ERR_ARG, "%s: the output must not alias an input (neighbours are read)", fn);
   const int nz = (int)vorticity_field->shape[1], ny = (int)vorticity_field->shape[2],
             nx = (int)vorticity_field->shape[3];
   if ((int64_t)nz * ny * nx == 0) return SOPHT_OK;
@@ -727,26 +720,28 @@ int sopht_ns3d_advect_rotational(int dtype, const sopht_field_t* out_vorticity_f
   SOPHT_PROF("ns3d.advect", st);
   if (vec_ok(out_vorticity_field, dtype) && vec_ok(vorticity_field, dtype) && vec_ok(velocity_field, dtype)) {
     const int w = dtype == SOPHT_F32 ? 4 : 2;
-    static const int slots32 = resident_ctas(advect_vec_kernel<float>, 32 * VBY);
-    static const int slots64 = resident_ctas(advect_vec_kernel<double>, 32 * VBY);
+    static const int slots32 = resident_ctas(advect_vec_kernel<float, false>, 32 * VBY);
+    static const int slots64 = resident_ctas(advect_vec_kernel<double, false>, 32 * VBY);
     const int kchunk = pick_vec_kchunk(nz, ny, nx, 1, w, dtype == SOPHT_F32 ? slots32 : slots64);
     dim3 grid((nx + 32 * w - 1) / (32 * w), (ny + VBY - 1) / VBY, (nz + kchunk - 1) / kchunk), block(32, VBY, 1);
-    if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
-    if (dtype == SOPHT_F32)
-      advect_vec_kernel<float><<<grid, block, 0, st>>>(
-          out_view<float>(out_vorticity_field), in_view<float>(vorticity_field),
-          in_view<float>(velocity_field), (float)prefactor, nz, ny, nx, kchunk);
-    else
-      advect_vec_kernel<double><<<grid, block, 0, st>>>(
-          out_view<double>(out_vorticity_field), in_view<double>(vorticity_field),
-          in_view<double>(velocity_field), prefactor, nz, ny, nx, kchunk);
+    if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", fn);
+#define SOPHT_LAUNCH_ADVECT(T, P)                                                                          \
+  advect_vec_kernel<T, P><<<grid, block, 0, st>>>(out_view<T>(out_vorticity_field), in_view<T>(vorticity_field), \
+                                                  in_view<T>(velocity_field), (T)prefactor, nz, ny, nx, kchunk)
+    if (dtype == SOPHT_F32) {
+      if (pxy) SOPHT_LAUNCH_ADVECT(float, true); else SOPHT_LAUNCH_ADVECT(float, false);
+    } else {
+      if (pxy) SOPHT_LAUNCH_ADVECT(double, true); else SOPHT_LAUNCH_ADVECT(double, false);
+    }
+#undef SOPHT_LAUNCH_ADVECT
     SOPHT_CHECK_LAUNCH();
     return SOPHT_OK;
   }
+  if (pxy) SOPHT_FAIL(SOPHT_ERR_STRIDE, "%s: the periodic kernels need 16-byte aligned, unit-stride rows", fn);
   const int tx = dtype == SOPHT_F32 ? Tile<float>::TX : Tile<double>::TX, ty = Tile<float>::TY;
   const int kchunk = pick_kchunk(nz, ny, nx, 1, tx, ty);
   dim3 grid((nx + tx - 1) / tx, (ny + ty - 1) / ty, (nz + kchunk - 1) / kchunk), block(tx, ty, 1);
-  if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
+  if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", fn);
   if (dtype == SOPHT_F32)
     advect_rotational_kernel<float><<<grid, block, 0, st>>>(
         out_view<float>(out_vorticity_field), in_view<float>(vorticity_field), in_view<float>(velocity_field),
@@ -759,20 +754,21 @@ int sopht_ns3d_advect_rotational(int dtype, const sopht_field_t* out_vorticity_f
   return SOPHT_OK;
 }
 
-int sopht_ns3d_diffuse(int dtype, const sopht_field_t* out_field, const sopht_field_t* field,
-                       double nu_dt_by_dx2, const sopht_field_t* zero_field, void* stream) {
+static int ns3d_diffuse(const char* fn, bool pxy, int dtype, const sopht_field_t* out_field,
+                        const sopht_field_t* field, double nu_dt_by_dx2, const sopht_field_t* zero_field,
+                        void* stream) {
   SOPHT_CHECK_DTYPE(dtype);
-  RETURN_IF(check_vec3(__func__, out_field));
-  RETURN_IF(check_vec3(__func__, field));
-  if (!same_shape(out_field, field)) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: field shapes differ", __func__);
+  RETURN_IF(check_vec3(fn, out_field));
+  RETURN_IF(check_vec3(fn, field));
+  if (!same_shape(out_field, field)) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: field shapes differ", fn);
   const size_t elem = dtype == SOPHT_F32 ? 4 : 8;
   if (overlaps(out_field, field, elem))
-    SOPHT_FAIL(SOPHT_ERR_ARG, "%s: the output must not alias the input (neighbours are read)", __func__);
+    SOPHT_FAIL(SOPHT_ERR_ARG, "%s: the output must not alias the input (neighbours are read)", fn);
   if (zero_field) {
-    RETURN_IF(check_vec3(__func__, zero_field));
-    if (!same_shape(zero_field, field)) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: field shapes differ", __func__);
+    RETURN_IF(check_vec3(fn, zero_field));
+    if (!same_shape(zero_field, field)) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: field shapes differ", fn);
     if (overlaps(zero_field, field, elem) || overlaps(zero_field, out_field, elem))
-      SOPHT_FAIL(SOPHT_ERR_ARG, "%s: the field to zero must not alias input or output", __func__);
+      SOPHT_FAIL(SOPHT_ERR_ARG, "%s: the field to zero must not alias input or output", fn);
   }
   const int nz = (int)field->shape[1], ny = (int)field->shape[2], nx = (int)field->shape[3];
   if ((int64_t)nz * ny * nx == 0) return SOPHT_OK;
@@ -780,30 +776,31 @@ int sopht_ns3d_diffuse(int dtype, const sopht_field_t* out_field, const sopht_fi
   SOPHT_PROF("ns3d.diffuse", st);
   if (vec_ok(out_field, dtype) && vec_ok(field, dtype) && (!zero_field || vec_ok(zero_field, dtype))) {
     const int w = dtype == SOPHT_F32 ? 4 : 2;
-    static const int slots32 = resident_ctas(diffuse_vec_kernel<float>, 32 * VBY);
-    static const int slots64 = resident_ctas(diffuse_vec_kernel<double>, 32 * VBY);
+    static const int slots32 = resident_ctas(diffuse_vec_kernel<float, false>, 32 * VBY);
+    static const int slots64 = resident_ctas(diffuse_vec_kernel<double, false>, 32 * VBY);
     const int kchunk = pick_vec_kchunk(nz, ny, nx, 3, w, dtype == SOPHT_F32 ? slots32 : slots64);
     const int nchunk = (nz + kchunk - 1) / kchunk;
     dim3 grid((nx + 32 * w - 1) / (32 * w), (ny + VBY - 1) / VBY, nchunk * 3), block(32, VBY, 1);
-    if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
-    if (dtype == SOPHT_F32)
-      diffuse_vec_kernel<float><<<grid, block, 0, st>>>(
-          out_view<float>(out_field), in_view<float>(field),
-          zero_field ? out_view<float>(zero_field) : out_view<float>(out_field), zero_field != nullptr, 3,
-          (float)nu_dt_by_dx2, nz, ny, nx, kchunk);
-    else
-      diffuse_vec_kernel<double><<<grid, block, 0, st>>>(
-          out_view<double>(out_field), in_view<double>(field),
-          zero_field ? out_view<double>(zero_field) : out_view<double>(out_field), zero_field != nullptr, 3,
-          nu_dt_by_dx2, nz, ny, nx, kchunk);
+    if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", fn);
+#define SOPHT_LAUNCH_DIFFUSE(T, P)                                                                       \
+  diffuse_vec_kernel<T, P><<<grid, block, 0, st>>>(                                                     \
+      out_view<T>(out_field), in_view<T>(field), zero_field ? out_view<T>(zero_field) : out_view<T>(out_field), \
+      zero_field != nullptr, 3, (T)nu_dt_by_dx2, nz, ny, nx, kchunk)
+    if (dtype == SOPHT_F32) {
+      if (pxy) SOPHT_LAUNCH_DIFFUSE(float, true); else SOPHT_LAUNCH_DIFFUSE(float, false);
+    } else {
+      if (pxy) SOPHT_LAUNCH_DIFFUSE(double, true); else SOPHT_LAUNCH_DIFFUSE(double, false);
+    }
+#undef SOPHT_LAUNCH_DIFFUSE
     SOPHT_CHECK_LAUNCH();
     return SOPHT_OK;
   }
+  if (pxy) SOPHT_FAIL(SOPHT_ERR_STRIDE, "%s: the periodic kernels need 16-byte aligned, unit-stride rows", fn);
   const int tx = dtype == SOPHT_F32 ? Tile<float>::TX : Tile<double>::TX, ty = Tile<float>::TY;
   const int kchunk = pick_kchunk(nz, ny, nx, 3, tx, ty);
   const int nchunk = (nz + kchunk - 1) / kchunk;
   dim3 grid((nx + tx - 1) / tx, (ny + ty - 1) / ty, nchunk * 3), block(tx, ty, 1);
-  if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
+  if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", fn);
   if (dtype == SOPHT_F32)
     diffuse_kernel<float><<<grid, block, 0, st>>>(
         out_view<float>(out_field), in_view<float>(field),
@@ -818,18 +815,17 @@ int sopht_ns3d_diffuse(int dtype, const sopht_field_t* out_field, const sopht_fi
   return SOPHT_OK;
 }
 
-int sopht_ns3d_velocity_from_stream_function(int dtype, const sopht_field_t* velocity_field,
-                                             const sopht_field_t* stream_func_field, double prefactor,
-                                             const double* free_stream_velocity, void* max_abs_sum_out,
-                                             void* stream) {
+static int ns3d_velocity(const char* fn, bool pxy, int dtype, const sopht_field_t* velocity_field,
+                         const sopht_field_t* stream_func_field, double prefactor,
+                         const double* free_stream_velocity, void* max_abs_sum_out, void* stream) {
   SOPHT_CHECK_DTYPE(dtype);
-  RETURN_IF(check_vec3(__func__, velocity_field));
-  RETURN_IF(check_vec3(__func__, stream_func_field));
+  RETURN_IF(check_vec3(fn, velocity_field));
+  RETURN_IF(check_vec3(fn, stream_func_field));
   if (!same_shape(velocity_field, stream_func_field))
-    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: field shapes differ", __func__);
+    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: field shapes differ", fn);
   const size_t elem = dtype == SOPHT_F32 ? 4 : 8;
   if (overlaps(velocity_field, stream_func_field, elem))
-    SOPHT_FAIL(SOPHT_ERR_ARG, "%s: the output must not alias the input (neighbours are read)", __func__);
+    SOPHT_FAIL(SOPHT_ERR_ARG, "%s: the output must not alias the input (neighbours are read)", fn);
   const int nz = (int)velocity_field->shape[1], ny = (int)velocity_field->shape[2],
             nx = (int)velocity_field->shape[3];
   if ((int64_t)nz * ny * nx == 0) return SOPHT_OK;
@@ -845,22 +841,25 @@ int sopht_ns3d_velocity_from_stream_function(int dtype, const sopht_field_t* vel
     static const int slots64 = resident_ctas(velocity_vec_kernel<double, false>, 32 * VBY);
     const int kchunk = pick_vec_kchunk(nz, ny, nx, 1, w, dtype == SOPHT_F32 ? slots32 : slots64);
     dim3 grid((nx + 32 * w - 1) / (32 * w), (ny + VBY - 1) / VBY, (nz + kchunk - 1) / kchunk), block(32, VBY, 1);
-    if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
-    if (dtype == SOPHT_F32)
-      velocity_vec_kernel<float, false><<<grid, block, 0, st>>>(
-          out_view<float>(velocity_field), in_view<float>(stream_func_field), (float)prefactor, (float)f0,
-          (float)f1, (float)f2, reinterpret_cast<float*>(max_abs_sum_out), nz, ny, nx, kchunk);
-    else
-      velocity_vec_kernel<double, false><<<grid, block, 0, st>>>(
-          out_view<double>(velocity_field), in_view<double>(stream_func_field), prefactor, f0, f1, f2,
-          reinterpret_cast<double*>(max_abs_sum_out), nz, ny, nx, kchunk);
+    if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", fn);
+#define SOPHT_LAUNCH_VELOCITY(T, P)                                                                      \
+  velocity_vec_kernel<T, false, P><<<grid, block, 0, st>>>(out_view<T>(velocity_field), in_view<T>(stream_func_field), \
+                                                           (T)prefactor, (T)f0, (T)f1, (T)f2,           \
+                                                           reinterpret_cast<T*>(max_abs_sum_out), nz, ny, nx, kchunk)
+    if (dtype == SOPHT_F32) {
+      if (pxy) SOPHT_LAUNCH_VELOCITY(float, true); else SOPHT_LAUNCH_VELOCITY(float, false);
+    } else {
+      if (pxy) SOPHT_LAUNCH_VELOCITY(double, true); else SOPHT_LAUNCH_VELOCITY(double, false);
+    }
+#undef SOPHT_LAUNCH_VELOCITY
     SOPHT_CHECK_LAUNCH();
     return SOPHT_OK;
   }
+  if (pxy) SOPHT_FAIL(SOPHT_ERR_STRIDE, "%s: the periodic kernels need 16-byte aligned, unit-stride rows", fn);
   const int tx = dtype == SOPHT_F32 ? Tile<float>::TX : Tile<double>::TX, ty = Tile<float>::TY;
   const int kchunk = pick_kchunk(nz, ny, nx, 1, tx, ty);
   dim3 grid((nx + tx - 1) / tx, (ny + ty - 1) / ty, (nz + kchunk - 1) / kchunk), block(tx, ty, 1);
-  if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", __func__);
+  if (grid.y > 65535 || grid.z > 65535) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid too large", fn);
   if (dtype == SOPHT_F32)
     velocity_from_psi_kernel<float><<<grid, block, 0, st>>>(
         out_view<float>(velocity_field), in_view<float>(stream_func_field), (float)prefactor, (float)f0,
@@ -871,6 +870,94 @@ int sopht_ns3d_velocity_from_stream_function(int dtype, const sopht_field_t* vel
         reinterpret_cast<double*>(max_abs_sum_out), nz, ny, nx, kchunk);
   SOPHT_CHECK_LAUNCH();
   return SOPHT_OK;
+}
+
+
+namespace sopht {
+// plane 0 <- plane nz, plane nz + 1 <- plane 1 of every component; 16-byte vectors when rows allow it
+template <typename V>
+static __global__ void __launch_bounds__(256)
+    wrap_z_kernel(char* base, int64_t comp_stride_b, int64_t plane_stride_b, int64_t row_stride_b, int ncomp,
+                  int nzp, int ny, int row_vecs) {
+  const int64_t per = (int64_t)ny * row_vecs, total = per * ncomp * 2;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(q % row_vecs);
+    const int j = (int)((q / row_vecs) % ny);
+    const int side = (int)((q / per) & 1), c = (int)(q / per / 2);
+    char* comp = base + c * comp_stride_b + j * row_stride_b + (int64_t)v * sizeof(V);
+    const int src = side ? 1 : nzp - 2, dst = side ? nzp - 1 : 0;
+    *reinterpret_cast<V*>(comp + dst * plane_stride_b) = *reinterpret_cast<const V*>(comp + src * plane_stride_b);
+  }
+}
+}  // namespace sopht
+
+extern "C" {
+
+int sopht_ns3d_advect_rotational(int dtype, const sopht_field_t* out_vorticity_field,
+                                 const sopht_field_t* vorticity_field, const sopht_field_t* velocity_field,
+                                 double prefactor, void* stream) {
+  return ns3d_advect(__func__, false, dtype, out_vorticity_field, vorticity_field, velocity_field, prefactor, stream);
+}
+int sopht_ns3d_diffuse(int dtype, const sopht_field_t* out_field, const sopht_field_t* field, double nu_dt_by_dx2,
+                       const sopht_field_t* zero_field, void* stream) {
+  return ns3d_diffuse(__func__, false, dtype, out_field, field, nu_dt_by_dx2, zero_field, stream);
+}
+int sopht_ns3d_velocity_from_stream_function(int dtype, const sopht_field_t* velocity_field,
+                                             const sopht_field_t* stream_func_field, double prefactor,
+                                             const double* free_stream_velocity, void* max_abs_sum_out,
+                                             void* stream) {
+  return ns3d_velocity(__func__, false, dtype, velocity_field, stream_func_field, prefactor, free_stream_velocity,
+                       max_abs_sum_out, stream);
+}
+
+
+int sopht_wrap_z_halos(int dtype, const sopht_field_t* field, void* stream) {
+  SOPHT_CHECK_DTYPE(dtype);
+  if (!valid_field(field, 3, 4)) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: expected a (C, nz + 2, ny, nx) or (nz + 2, ny, nx) field", __func__);
+  const int o = field->ndim == 4 ? 1 : 0;
+  const int ncomp = o ? (int)field->shape[0] : 1;
+  const int nzp = (int)field->shape[o], ny = (int)field->shape[o + 1], nx = (int)field->shape[o + 2];
+  if (nzp < 3) SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: at least one owned plane between the two halo planes", __func__);
+  if (field->stride[o + 2] != 1 && nx > 1) SOPHT_FAIL(SOPHT_ERR_STRIDE, "%s: unit x stride required", __func__);
+  if ((int64_t)ny * nx == 0) return SOPHT_OK;
+  const int64_t elem = dtype == SOPHT_F32 ? 4 : 8;
+  const int64_t cs = (o ? field->stride[0] : 0) * elem, ps = field->stride[o] * elem, rs = field->stride[o + 1] * elem;
+  const bool vec = ((nx * elem) % 16 == 0) && (cs % 16 == 0) && (ps % 16 == 0) && (rs % 16 == 0) &&
+                   (reinterpret_cast<uintptr_t>(field->data) % 16 == 0);
+  const int row_vecs = vec ? (int)(nx * elem / 16) : nx;
+  const int64_t total = (int64_t)ny * row_vecs * ncomp * 2;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cudaStream_t st = as_stream(stream);
+  SOPHT_PROF("ns3d.wrap_z", st);
+  char* base = reinterpret_cast<char*>(field->data);
+  if (vec)
+    wrap_z_kernel<uint4><<<blocks, 256, 0, st>>>(base, cs, ps, rs, ncomp, nzp, ny, row_vecs);
+  else if (elem == 4)
+    wrap_z_kernel<float><<<blocks, 256, 0, st>>>(base, cs, ps, rs, ncomp, nzp, ny, row_vecs);
+  else
+    wrap_z_kernel<double><<<blocks, 256, 0, st>>>(base, cs, ps, rs, ncomp, nzp, ny, row_vecs);
+  SOPHT_CHECK_LAUNCH();
+  return SOPHT_OK;
+}
+
+/* periodic box: x and y wrap around inside the kernels; z keeps the ghost-ring rule, so the arrays carry one halo plane
+ * per z side that the caller fills (wrap copy on one GPU, neighbour planes in a slab decomposition) */
+int sopht_ns3d_advect_rotational_periodic_xy(int dtype, const sopht_field_t* out_vorticity_field,
+                                             const sopht_field_t* vorticity_field,
+                                             const sopht_field_t* velocity_field, double prefactor, void* stream) {
+  return ns3d_advect(__func__, true, dtype, out_vorticity_field, vorticity_field, velocity_field, prefactor, stream);
+}
+int sopht_ns3d_diffuse_periodic_xy(int dtype, const sopht_field_t* out_field, const sopht_field_t* field,
+                                   double nu_dt_by_dx2, const sopht_field_t* zero_field, void* stream) {
+  return ns3d_diffuse(__func__, true, dtype, out_field, field, nu_dt_by_dx2, zero_field, stream);
+}
+int sopht_ns3d_velocity_from_stream_function_periodic_xy(int dtype, const sopht_field_t* velocity_field,
+                                                         const sopht_field_t* stream_func_field, double prefactor,
+                                                         const double* free_stream_velocity, void* max_abs_sum_out,
+                                                         void* stream) {
+  return ns3d_velocity(__func__, true, dtype, velocity_field, stream_func_field, prefactor, free_stream_velocity,
+                       max_abs_sum_out, stream);
 }
 
 }  // extern "C"

@@ -17,7 +17,9 @@
 //      its own flags[neighbour][DONE] >= e - when the kernel retires, this rank's halo planes are complete.
 // ref: the reference has no distributed path; what is exchanged is the ghost ring its stencil kernels read
 // (SURVEY.md 8e).
+#include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -33,17 +35,39 @@ constexpr size_t HEADER = 4096;
 struct Header {
   uint32_t flags[MAX_RANKS][SLOTS];
   uint32_t counter;
+  uint32_t error;  // 0, or 1 + the rank a poll gave up on (sticky; read by sopht_peer_arena_status)
 };
 static_assert(sizeof(Header) <= HEADER, "arena header");
 
 __device__ __forceinline__ void signal(uint32_t* remote, uint32_t epoch) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
 }
-__device__ __forceinline__ void wait_for(const uint32_t* local, uint32_t epoch) {
+// Poll a local flag until the peer has stored `epoch` into it. The spin is bounded (budget_ns of %globaltimer): a rank
+// that died, or that issued its exchanges in a different order, must not hang every neighbour's GPU for good - the
+// kernel gives up, records which peer it was waiting for in the header and lets the stream drain; the host layer
+// turns the sticky error word into an exception (sopht_peer_arena_status).
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void wait_for(const uint32_t* local, uint32_t epoch, Header* mine, int peer_rank,
+                                         uint64_t budget_ns) {
   uint32_t v;
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
   do {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(local) : "memory");
-  } while ((int32_t)(v - epoch) < 0);  // wrap-safe
+    if ((int32_t)(v - epoch) >= 0) return;  // wrap-safe
+    if ((++spins & 1023u) == 0) {
+      const uint64_t now = global_ns();
+      if (!t0) t0 = now;
+      if (now - t0 > budget_ns) {
+        atomicCAS(&mine->error, 0u, 1u + (uint32_t)peer_rank);
+        return;
+      }
+    }
+  } while (true);
 }
 
 struct HaloField {
@@ -61,6 +85,7 @@ struct HaloArgs {
   char* hi;
   int rank, rank_lo, rank_hi;
   uint32_t epoch;
+  uint64_t budget_ns;
 };
 
 __global__ void __launch_bounds__(256) halo_push_kernel(HaloArgs a) {
@@ -72,8 +97,8 @@ __global__ void __launch_bounds__(256) halo_push_kernel(HaloArgs a) {
       if (hlo) signal(&hlo->flags[a.rank][SLOT_READY], a.epoch);
       if (hhi) signal(&hhi->flags[a.rank][SLOT_READY], a.epoch);
     }
-    if (hlo) wait_for(&mine->flags[a.rank_lo][SLOT_READY], a.epoch);
-    if (hhi) wait_for(&mine->flags[a.rank_hi][SLOT_READY], a.epoch);
+    if (hlo) wait_for(&mine->flags[a.rank_lo][SLOT_READY], a.epoch, mine, a.rank_lo, a.budget_ns);
+    if (hhi) wait_for(&mine->flags[a.rank_hi][SLOT_READY], a.epoch, mine, a.rank_hi, a.budget_ns);
   }
   __syncthreads();
   // my first owned planes [h, 2h) -> low neighbour's planes [n + h, n + 2h); my last owned planes [n, n + h) ->
@@ -106,8 +131,8 @@ __global__ void __launch_bounds__(256) halo_push_kernel(HaloArgs a) {
       mine->counter = 0;  // next launch (stream-ordered) starts from zero
       if (hlo) signal(&hlo->flags[a.rank][SLOT_DONE], a.epoch);
       if (hhi) signal(&hhi->flags[a.rank][SLOT_DONE], a.epoch);
-      if (hlo) wait_for(&mine->flags[a.rank_lo][SLOT_DONE], a.epoch);
-      if (hhi) wait_for(&mine->flags[a.rank_hi][SLOT_DONE], a.epoch);
+      if (hlo) wait_for(&mine->flags[a.rank_lo][SLOT_DONE], a.epoch, mine, a.rank_lo, a.budget_ns);
+      if (hhi) wait_for(&mine->flags[a.rank_hi][SLOT_DONE], a.epoch, mine, a.rank_hi, a.budget_ns);
     }
   }
 }
@@ -116,6 +141,7 @@ struct BarrierArgs {
   char* peer[MAX_RANKS];
   int nranks, rank;
   uint32_t epoch;
+  uint64_t budget_ns;
 };
 // all-ranks barrier in stream order: everything every rank enqueued before it (including its stores into
 // other ranks' memory) is complete and visible when it retires
@@ -124,7 +150,8 @@ __global__ void peer_barrier_kernel(BarrierArgs a) {
   __threadfence_system();
   if (q < a.nranks && q != a.rank) {
     signal(&reinterpret_cast<Header*>(a.peer[q])->flags[a.rank][SLOT_BARRIER], a.epoch);
-    wait_for(&reinterpret_cast<Header*>(a.peer[a.rank])->flags[q][SLOT_BARRIER], a.epoch);
+    Header* mine = reinterpret_cast<Header*>(a.peer[a.rank]);
+    wait_for(&mine->flags[q][SLOT_BARRIER], a.epoch, mine, q, a.budget_ns);
   }
 }
 
@@ -140,6 +167,7 @@ struct sopht_peer_arena {
   char* peer[MAX_RANKS] = {};
   bool opened = false;
   uint32_t halo_epoch = 0, barrier_epoch = 0;
+  uint64_t budget_ns = 30ull * 1000000000ull;  // SOPHT_PEER_TIMEOUT_S
 };
 
 extern "C" {
@@ -150,6 +178,8 @@ int sopht_peer_arena_create(sopht_peer_arena_t* handle, size_t payload_bytes, in
   if (nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks)
     SOPHT_FAIL(SOPHT_ERR_ARG, "%s: 1 <= nranks <= %d and 0 <= rank < nranks", __func__, MAX_RANKS);
   auto* h = new sopht_peer_arena();
+  if (const char* v = getenv("SOPHT_PEER_TIMEOUT_S"))
+    if (atof(v) > 0) h->budget_ns = (uint64_t)(atof(v) * 1e9);
   h->bytes = HEADER + ((payload_bytes + 255) / 256) * 256;
   h->nranks = nranks, h->rank = rank;
   if (cudaMalloc(&h->base, h->bytes) != cudaSuccess) {
@@ -187,10 +217,30 @@ int sopht_peer_arena_open(sopht_peer_arena_t h, const unsigned char* all_ipc_han
     cudaIpcMemHandle_t ipc;
     memcpy(&ipc, all_ipc_handles + (size_t)q * 64, 64);
     void* p = nullptr;
-    SOPHT_CUDA(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+    const cudaError_t e = cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {  // leave the arena as it was before the call: no half-open peer table
+      for (int r = 0; r < h->nranks; ++r)
+        if (r != h->rank && h->peer[r]) {
+          cudaIpcCloseMemHandle(h->peer[r]);
+          h->peer[r] = nullptr;
+        }
+      SOPHT_FAIL(SOPHT_ERR_CUDA, "%s: cudaIpcOpenMemHandle(rank %d) failed: %s", __func__, q, cudaGetErrorString(e));
+    }
     h->peer[q] = reinterpret_cast<char*>(p);
   }
   h->opened = true;
+  return SOPHT_OK;
+}
+
+/* 0 = healthy; otherwise a device-side poll of this arena timed out (SOPHT_PEER_TIMEOUT_S, default 30 s) waiting for
+ * rank (return value - 1): that rank died or issued a different sequence of exchanges / barriers. Synchronises the
+ * device (reads one word back). */
+int sopht_peer_arena_status(sopht_peer_arena_t h, int* stalled_rank_out) {
+  if (!h) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle", __func__);
+  uint32_t err = 0;
+  SOPHT_CUDA(cudaMemcpy(&err, h->base + offsetof(Header, error), sizeof(err), cudaMemcpyDeviceToHost));
+  if (stalled_rank_out) *stalled_rank_out = err ? (int)err - 1 : -1;
+  if (err) SOPHT_FAIL(SOPHT_ERR_CUDA, "%s: a peer exchange timed out waiting for rank %d", __func__, (int)err - 1);
   return SOPHT_OK;
 }
 
@@ -223,6 +273,7 @@ int sopht_peer_halo_exchange(sopht_peer_arena_t h, int nfields, const int64_t* p
   a.lo = h->rank > 0 ? h->peer[h->rank - 1] : nullptr;
   a.hi = h->rank + 1 < h->nranks ? h->peer[h->rank + 1] : nullptr;
   a.epoch = ++h->halo_epoch;
+  a.budget_ns = h->budget_ns;
   const int64_t vecs = (int64_t)halo * plane_bytes / 16 * total_comp * 2;
   int blocks = (int)((vecs + 256 * 8 - 1) / (256 * 8));
   if (blocks > 64) blocks = 64;  // far below one CTA per SM: every CTA is resident, the polls cannot starve
@@ -241,6 +292,7 @@ int sopht_peer_barrier(sopht_peer_arena_t h, void* stream) {
   for (int q = 0; q < h->nranks; ++q) a.peer[q] = h->peer[q];
   a.nranks = h->nranks, a.rank = h->rank;
   a.epoch = ++h->barrier_epoch;
+  a.budget_ns = h->budget_ns;
   cudaStream_t st = as_stream(stream);
   SOPHT_PROF("comm.peer_barrier", st);
   peer_barrier_kernel<<<1, 32, 0, st>>>(a);

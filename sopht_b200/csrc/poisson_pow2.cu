@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "poisson.cuh"
 #include "poisson_pow2_phases.cuh"
+#include "poisson_zrow.cuh"
 
 namespace sopht {
 
@@ -267,6 +268,87 @@ __global__ void __launch_bounds__(256)
 
 bool is_pow2(int n) { return n > 0 && (n & (n - 1)) == 0; }
 
+// ---- row-mode z pass (poisson_zrow.cuh) -------------------------------------------------------------------------
+// tile-major copy of the folded G_hat for it, columns in the consumer order of p2::ZRow (poisson_zrow.cuh):
+//   gt[(((fy * ntx + kxt) * TX + col) * (K2/4) + kq) * (NBLK+1) * 4 + r * 4 + i] = gm[fz = r + NBLK (4 kq + i)][fy][kx]
+__global__ void __launch_bounds__(256)
+    green_tiles_kernel(float* gt, const float* gm, int nz, int ny, int g_row, int NBLK, int K2) {
+  const int GP = (K2 / 4) * (NBLK + 1) * 4;
+  const int64_t total = (int64_t)(ny + 1) * g_row * GP;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+    const int e = (int)(q % GP);
+    const int64_t rr = q / GP;      // (fy * ntx + kxt) * TX + col = fy * g_row + kx
+    const int kx = (int)(rr % g_row), fy = (int)(rr / g_row);
+    const int i = e & 3, r = (e >> 2) % (NBLK + 1), kq = (e >> 2) / (NBLK + 1);
+    const int fz = r + NBLK * (4 * kq + i);
+    gt[q] = fz <= nz ? gm[((int64_t)fz * (ny + 1) + fy) * g_row + kx] : 0.0f;
+  }
+}
+
+bool zrow_enabled() {
+  static const int v = env_int("SOPHT_P2_ZROW", 1);
+  return v != 0;
+}
+// transform lengths the row-mode kernel is built for; 0 = not eligible
+int zrow_tx(int LZ, int ncomp, int nxl) {
+  if (!zrow_enabled() || ncomp != 3) return 0;
+  // measured on B200 (profiles/r02_zpass_experiments.txt): 2 nz = 1024: 5.99 ms against 6.32 ms for p2::ZConv at 512^3;
+  // 2 nz = 512: 0.60 against 0.57 ms at 256^3 (p2::ZConv runs four 128-thread CTAs per SM there) - opt-in only
+  static const int allow512 = env_int("SOPHT_P2_ZROW_512", 0);
+  int tx = 0;
+  if (LZ == 1024) tx = p2::ZRow<1024>::TX;
+  if (LZ == 512 && allow512) tx = p2::ZRow<512>::TX;
+  return tx && nxl % tx == 0 && nxl % 8 == 0 ? tx : 0;
+}
+int zrow_gp(int LZ) { return LZ == 1024 ? p2::ZRow<1024>::GP : p2::ZRow<512>::GP; }
+
+int build_green_tiles(float** gt, const float* gm, int nz, int ny, int g_row, cudaStream_t st) {
+  const int LZ = 2 * nz;
+  if (!zrow_tx(LZ, 3, g_row)) return SOPHT_OK;
+  const int GP = zrow_gp(LZ);
+  if (cudaMalloc(gt, sizeof(float) * (size_t)(ny + 1) * g_row * GP) != cudaSuccess)
+    SOPHT_FAIL(SOPHT_ERR_ALLOC, "poisson(pow2): out of device memory for the tile-major Green's function");
+  const int NBLK = LZ == 1024 ? p2::ZRow<1024>::NBLK : p2::ZRow<512>::NBLK;
+  const int K2 = LZ == 1024 ? p2::ZRow<1024>::K2 : p2::ZRow<512>::K2;
+  green_tiles_kernel<<<148 * 8, 256, 0, st>>>(*gt, gm, nz, ny, g_row, NBLK, K2);
+  SOPHT_CHECK_LAUNCH();
+  return SOPHT_OK;
+}
+
+template <int L>
+int launch_zrow_L(const p2::ZRowParams& p, int nunits, cudaStream_t st) {
+  using K = p2::ZRow<L>;
+  static int num_sm = 0;
+  if (!num_sm) {
+    SOPHT_CUDA(cudaFuncSetAttribute(p2::zrow_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)K::SMEM_BYTES));
+    int dev = 0;
+    SOPHT_CUDA(cudaGetDevice(&dev));
+    SOPHT_CUDA(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int g = nunits < num_sm ? nunits : num_sm;
+  SOPHT_PROF("poisson.z_conv", st);
+  p2::zrow_kernel<L><<<g, K::THREADS, K::SMEM_BYTES, st>>>(p, nunits);
+  SOPHT_CHECK_LAUNCH();
+  return SOPHT_OK;
+}
+// b: x-major (C, nz, 2ny, nxl) -> b2: kx-tile(8)-major, like slab_z_params
+int launch_zrow(const p2::SlabDims& d, float2* b, float2* b2, const float* gt, const float2* tw, cudaStream_t st) {
+  const int64_t nxl = d.nxl(), LY = 2 * d.ny;
+  const int LZ = 2 * d.nz, tx = zrow_tx(LZ, d.C, (int)nxl);
+  p2::ZRowParams p{};
+  p.in = b;
+  p.rs = LY * nxl, p.d_c = (int64_t)d.nz * LY * nxl, p.d_by = nxl;
+  p.out = b2;
+  p.o_by = (int64_t)d.nz * 8, p.o_bx8 = LY * p.o_by, p.o_c = LY * d.nz * nxl;
+  p.gt = gt;
+  p.ntx = (int)(nxl / tx);
+  p.n2y = (int)LY;
+  p.tw = tw;
+  const int nunits = (int)(p.ntx * LY);
+  return LZ == 1024 ? launch_zrow_L<1024>(p, nunits, st) : launch_zrow_L<512>(p, nunits, st);
+}
+
 struct Pow2Poisson : PoissonImpl {
   int nz, ny, nx;
   double dx;
@@ -274,6 +356,7 @@ struct Pow2Poisson : PoissonImpl {
   double origin;
   float* ghat_natural = nullptr;  // (2nz, 2ny, nx+1), kept for sopht_poisson_green_hat
   float *gm = nullptr, *gn = nullptr;
+  float* gt = nullptr;  // tile-major copy of gm for the row-mode z pass (null: not eligible)
   float2 *A = nullptr, *nyqA = nullptr, *B = nullptr, *B2 = nullptr, *nyqB = nullptr;
   float2 *twx = nullptr, *twx2 = nullptr, *twy = nullptr, *twz = nullptr;
   PoissonImpl* generic = nullptr;  // built lazily for views this path cannot take (x-stride != 1, ...)
@@ -290,6 +373,7 @@ struct Pow2Poisson : PoissonImpl {
     cudaFree(ghat_natural);
     cudaFree(gm);
     cudaFree(gn);
+    cudaFree(gt);
     cudaFree(A);
     cudaFree(nyqA);
     cudaFree(B);
@@ -323,6 +407,7 @@ struct Pow2Poisson : PoissonImpl {
     SOPHT_CUDA(cudaMalloc(&gn, sizeof(float) * (size_t)(nz + 1) * (ny + 1)));
     fold_green_kernel<<<148 * 8, 256, 0, st>>>(gm, gn, ghat_natural, nz, ny, nx, 0, nx);
     SOPHT_CHECK_LAUNCH();
+    if ((rc = build_green_tiles(&gt, gm, nz, ny, nx, st))) return rc;
     SOPHT_CUDA(cudaMalloc(&A, sizeof(float2) * rows * nx));
     SOPHT_CUDA(cudaMalloc(&nyqA, sizeof(float2) * rows));
     SOPHT_CUDA(cudaMalloc(&B, sizeof(float2) * rows * 2 * nx));
@@ -388,8 +473,11 @@ struct Pow2Poisson : PoissonImpl {
     if (use_side) SOPHT_CUDA(cudaEventRecord(ev_join, side));
     if ((rc = launch_yfwd(LY, p2::slab_y_params(d, TX, A, B, true, twy), dim3(nx / TX, C * nz, 1), st)))
       return rc;
-    if ((rc = launch_zconv(LZ, p2::slab_z_params(d, TX, B, B2, gm, nx, 0, twz), dim3(nx / TX, LY, 1), st)))
+    if (gt && zrow_tx(LZ, C, nx)) {
+      if ((rc = launch_zrow(d, B, B2, gt, twz, st))) return rc;
+    } else if ((rc = launch_zconv(LZ, p2::slab_z_params(d, TX, B, B2, gm, nx, 0, twz), dim3(nx / TX, LY, 1), st))) {
       return rc;
+    }
     if ((rc = launch_yinv(LY, p2::slab_y_params(d, TX, B2, A, false, twy), dim3(nx / TX, C * nz, 1), st)))
       return rc;
     if (use_side) SOPHT_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
@@ -409,6 +497,7 @@ struct Pow2Poisson : PoissonImpl {
 struct SlabPow2Poisson {
   p2::SlabDims d{};
   float *gm = nullptr, *gn = nullptr;  // this rank's kx slice of the folded G_hat, and the Nyquist plane's
+  float* gt = nullptr;                 // tile-major copy of gm for the row-mode z pass
   float2 *twx = nullptr, *twx2 = nullptr, *twy = nullptr, *twz = nullptr;
   // peer exchange: library-owned (cudaMalloc, so the IPC handle maps the exact base) buffers
   // (C, P, nzl, ny, nxl); peer_recv[q] / peer_send[q] are rank q's buffers mapped into this process
@@ -430,6 +519,7 @@ struct SlabPow2Poisson {
     cudaFree(xsend);
     cudaFree(gm);
     cudaFree(gn);
+    cudaFree(gt);
     cudaFree(twx);
     cudaFree(twx2);
     cudaFree(twy);
@@ -444,6 +534,7 @@ struct SlabPow2Poisson {
     // only this rank's kx range of G_hat is ever formed (the full doubled-domain transform does not fit at 1024^3)
     int rc = build_green_folded_slice(gm, gn, nz, ny, nx, d.rank * nxl, nxl, dx, mz, my, mx, origin, st);
     if (rc) return rc;
+    if (d.C == 3 && (rc = build_green_tiles(&gt, gm, nz, ny, nxl, st))) return rc;
     if ((rc = Pow2Poisson::upload_twiddles(&twx, nx, nx, st))) return rc;
     if ((rc = Pow2Poisson::upload_twiddles(&twx2, nx, 2 * nx, st))) return rc;
     if ((rc = Pow2Poisson::upload_twiddles(&twy, 2 * ny, 2 * ny, st))) return rc;
@@ -528,8 +619,12 @@ struct SlabPow2Poisson {
                           dim3(d.C * d.nz / TX, 1, 1), st)))
       return rc;
     float2* work2 = work + (int64_t)d.C * d.nz * LY * nxl;  // second half: the z pass's tile-major output
-    if ((rc = launch_zconv(LZ, p2::slab_z_params(d, TX, work, work2, gm, nxl, 0, twz), dim3(nxl / TX, LY, 1), st)))
+    if (gt && zrow_tx(LZ, d.C, nxl)) {
+      if ((rc = launch_zrow(d, work, work2, gt, twz, st))) return rc;
+    } else if ((rc = launch_zconv(LZ, p2::slab_z_params(d, TX, work, work2, gm, nxl, 0, twz), dim3(nxl / TX, LY, 1),
+                                  st))) {
       return rc;
+    }
     if ((rc = launch_zconv(LZ, p2::nyquist_z_params(d, TX, nyq_work, gn, twz), dim3(LY / TX, 1, 1), st)))
       return rc;
     const p2::ColParams yi = p2::slab_y_params(d, TX, work2, peer ? xsend : recv, false, twy);

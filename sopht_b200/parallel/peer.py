@@ -81,6 +81,12 @@ class PeerArena:
     def barrier(self) -> None:
         _lib.check(_lib.load().sopht_peer_barrier(self._handle, _lib.current_stream()))
 
+    def check(self) -> None:
+        """Raise if a device-side poll of this arena gave up waiting for a peer (a rank died, or the ranks issued
+        different sequences of exchanges / barriers). Synchronises the device; call it where the host waits anyway."""
+        stalled = ctypes.c_int(-1)
+        _lib.check(_lib.load().sopht_peer_arena_status(self._handle, ctypes.byref(stalled)))
+
     def __del__(self) -> None:
         h = getattr(self, "_handle", None)
         if h is not None and h.value:

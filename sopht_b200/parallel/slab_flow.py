@@ -101,6 +101,7 @@ class SlabUnboundedNavierStokesFlowSimulator3D:
         self._exchangers: dict = {}
         self._vel_absmax = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._have_absmax = False
+        self._vel_version = None
         self.step_mode = "fused-slab"
 
     # -- helpers ------------------------------------------------------------------------------------------
@@ -113,6 +114,8 @@ class SlabUnboundedNavierStokesFlowSimulator3D:
         h, n, z0 = self.part.halo, self.part.nz_local, self.part.z_start
         lo, hi = max(z0 - h, 0), min(z0 + n + h, self.grid_size[0])
         field[..., h - (z0 - lo) : h + n + (hi - z0 - n), :, :] = g[..., lo:hi, :, :].to(field.device, field.dtype)
+        if field is self.velocity_field:
+            self._have_absmax = False  # the maximum the last step left on the device no longer describes this field
 
     def _halos(self, *fields: torch.Tensor) -> None:
         if self._arena is not None:
@@ -157,16 +160,19 @@ class SlabUnboundedNavierStokesFlowSimulator3D:
             dc, ctypes.byref(fu), ctypes.byref(fpsi), float(rt(0.5 / self.dx)), fsv,
             ctypes.c_void_p(self._vel_absmax.data_ptr()), st))
         self._have_absmax = True
+        self._vel_version = self.velocity_field._version
         self.time += dt
 
     def compute_stable_timestep(self, dt_prefac: float = 1.0) -> float:
         """min(cfl dx / max sum|u|, 0.9 dx^2 / (6 nu)) with the maximum taken over all ranks
         (passive_transport_flow_simulators.py:139-155)."""
-        if not self._have_absmax:  # before the first step: the library's sum|u| + max kernel (writes buffer[0])
+        if not self._have_absmax or self._vel_version != self.velocity_field._version:  # before the first step / after a write: the library's sum|u| + max kernel (writes buffer[0])
             sv = self.part.stencil_view
             _lib.call("sopht_abs_sum_max", _lib.SOPHT_F32, sv(self.buffer_vector_field)[0],
                       sv(self.velocity_field), self._vel_absmax.data_ptr())
         m = self._vel_absmax.clone()
+        if self._arena is not None:
+            self._arena.check()  # the host synchronises here anyway: surface a timed-out peer exchange as an error
         if self.part.world_size > 1:
             dist.all_reduce(m, op=dist.ReduceOp.MAX, group=self.group)
         dt = stable_timestep_from_max(self.real_t(m.item()), 3, self.dx, self.cfl, self.kinematic_viscosity, self.real_t)

@@ -218,7 +218,7 @@ class UnboundedNavierStokesFlowSimulator3D(FlowSimulator):
         _lib.check(lib.sopht_ns3d_velocity_from_stream_function(
             dc, ctypes.byref(fu), ctypes.byref(fpsi), float(rt(0.5 / self.dx)), fsv,
             ctypes.c_void_p(self._vel_absmax.data_ptr()), st))
-        self._vel_absmax_version = self.velocity_field._version
+        self._vel_absmax_version = (self.velocity_field.data_ptr(), self.velocity_field._version)
 
     def _navier_stokes_time_step(self, dt: float, free_stream_velocity=(0.0, 0.0, 0.0)) -> None:
         """navier_stokes_flow_simulators.py:449-485."""
@@ -252,8 +252,7 @@ class UnboundedNavierStokesFlowSimulator3D(FlowSimulator):
         """Stable dt (navier_stokes_flow_simulators.py:501-512). After a fused step the velocity maximum is
         already on the device (reduced inside the velocity pass), so only one scalar is read back; the
         reference's side effect of leaving sum|u| in buffer_scalar_field is kept on the uncached path only."""
-        if (self._vel_absmax_version is not None
-                and self._vel_absmax_version == self.velocity_field._version):
+        if self._vel_absmax_version == (self.velocity_field.data_ptr(), self.velocity_field._version):
             dt = stable_timestep_from_max(
                 self.real_t(self._vel_absmax.item()), self.grid_dim, self.dx, self.cfl,
                 self.kinematic_viscosity, self.real_t)
@@ -263,6 +262,13 @@ class UnboundedNavierStokesFlowSimulator3D(FlowSimulator):
             grid_dim=self.grid_dim, dx=self.dx, cfl=self.cfl,
             kinematic_viscosity=self.kinematic_viscosity, real_t=self.real_t)
         return dt * dt_prefac
+
+    def invalidate_stable_dt_cache(self) -> None:
+        """Forget the velocity maximum the last fused step left on the device. torch's version counter sees in-place
+        torch writes to ``velocity_field`` (and a rebound tensor has another data pointer), but not writes made by
+        library kernels through raw pointers (``gen_add_fixed_val...`` etc. called on ``velocity_field`` by user code):
+        call this after such a write, or ``compute_stable_timestep`` keeps answering for the field of the last step."""
+        self._vel_absmax_version = None
 
     def get_vorticity_divergence_l2_norm(self) -> float:
         """L2 norm of div(vorticity) (navier_stokes_flow_simulators.py:514-522)."""

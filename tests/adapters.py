@@ -332,6 +332,27 @@ class CudaOps:
         return self.spne.UnboundedPoissonSolverPYFFTW2D(*grid, x_range=x_range, real_t=self.real_t, flags=flags)
 
 
+class COracleOps(OracleOps):
+    """The oracle with its stencil / elementwise passes executed by the C + OpenMP restatement
+    (oracle/c/ref_kernels.c through oracle/cstencils.py) - the CPU baseline bench.py times."""
+
+    name = "coracle"
+
+    def __init__(self, real_t):
+        super().__init__(real_t)
+        from oracle import cstencils
+
+        cstencils.load()
+        self.s = cstencils
+
+    def poisson_solver(self, grid, x_range):
+        if len(grid) == 3:
+            return self.p.UnboundedPoissonSolver3D(*grid, x_range=x_range, real_t=self.real_t, kernels=self.s)
+        return self.p.UnboundedPoissonSolver2D(*grid, x_range=x_range, real_t=self.real_t, kernels=self.s)
+
+
 def make_ops(kind: str, precision: str):
     real_t = np.float32 if precision == "single" else np.float64
+    if kind == "coracle":
+        return COracleOps(real_t)
     return OracleOps(real_t) if kind == "oracle" else CudaOps(real_t)

@@ -30,9 +30,11 @@ def test_cuda_poisson_generic_path_matches_reference_goldens(case, precision):
     case(make_ops("cuda", precision), precision, flags=POISSON_FORCE_GENERIC)
 
 
-# the last three reach the radix-32 transform lengths (2ny / 2nz = 512, 1024) and the three-pass L = 2048 row kernel
+# (256, 512, 32) / (512, 256, 16) reach the radix-32 transform lengths (2ny / 2nz = 512, 1024: the row-mode z kernel of
+# poisson_zrow.cuh), (8, 8, 2048) the three-pass L = 2048 row kernel, (1024, 8, 16) / (8, 1024, 16) the three-pass
+# L = 2048 z and y column kernels that the 1024^3 slab runs use
 @pytest.mark.parametrize("grid", [(8, 8, 16), (16, 32, 64), (32, 16, 128), (64, 128, 256), (128, 128, 256),
-                                  (256, 512, 32), (512, 256, 16), (8, 8, 2048)])
+                                  (256, 512, 32), (512, 256, 16), (8, 8, 2048), (1024, 8, 16), (8, 1024, 16)])
 def test_cuda_poisson_pow2_path_vs_oracle(grid):
     """fp32 power-of-two fast path (hand-written pruned FFT pipeline) against the scipy.fft oracle, which is
     itself pinned to the reference's test restatement; scalar, vector and strided-view solves."""
@@ -122,6 +124,49 @@ def test_cuda_fused_ns3d_passes_vs_oracle(precision, grid):
         dc, fd(dout), fd(dw), float(p), _lib.double_array(fsv), ctypes.c_void_p(vmax.data_ptr()), st))
     assert rel_l2(dout.cpu().numpy(), want) < REL_L2_TOL[precision]
     assert float(vmax.item()) == pytest.approx(float(np.abs(want).sum(axis=0).max()), rel=1e-5)
+
+
+# ---- ragged grids for the kernels the goldens only cover at 16^3 ----------------------
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("grid", [(9, 21, 70), (17, 19, 23), (40, 24, 130)])
+def test_cuda_stretching_divergence_brinkman_on_ragged_grids(precision, grid):
+    """Vortex-stretching flux / Euler / SSP-RK3 steps, divergence, Brinkman penalisation (+ the fixed-value variant)
+    and the level-set characteristic function on non-cubic, non-power-of-two grids and on strided component views,
+    against the oracle (the reference's tests use 16^3 only)."""
+    import numpy as np
+    from conftest import REL_L2_TOL, real_t_of, rel_l2
+
+    real_t = real_t_of(precision)
+    tol = REL_L2_TOL[precision]
+    rng = np.random.default_rng(23)
+    cu, orc = make_ops("cuda", precision), make_ops("oracle", precision)
+    w = rng.standard_normal((3, *grid)).astype(real_t)
+    u = rng.standard_normal((3, *grid)).astype(real_t)
+    p = real_t(0.21)
+
+    def both(fn, *outs):
+        got = [o.copy() for o in outs]
+        want = [o.copy() for o in outs]
+        fn(cu, *got)
+        fn(orc, *want)
+        for g_, w_ in zip(got, want):
+            assert rel_l2(g_, w_) < tol
+
+    both(lambda o, q: o.stretching_flux(q, w, u, p), np.full_like(w, 3.0))
+    both(lambda o, ww, q: o.stretching_timestep(ww, u, q, p), w, np.full_like(w, 3.0))
+    mid = np.zeros_like(w)
+    both(lambda o, ww, q: o.stretching_timestep(ww, u, q, p, stepper="ssprk3", midstep=mid.copy()), w,
+         np.full_like(w, 3.0))
+    both(lambda o, d: o.divergence_3d(d, w, p), np.full(grid, 5.0, real_t))
+    both(lambda o, d: o.divergence_3d(d, w, p, reset=False), np.full(grid, 5.0, real_t))
+    chi = rng.random(grid).astype(real_t)
+    both(lambda o, out: o.brinkmann(out, w[1], chi, u[2], 1e3), np.zeros(grid, real_t))  # strided component views
+    both(lambda o, out: o.brinkmann(out, w, chi, u, 1e3, vector=True), np.zeros_like(w))
+    ls = (rng.random(grid).astype(real_t) - real_t(0.5)) * real_t(0.2)
+    both(lambda o, out: o.char_func(out, ls, 0.03), np.zeros(grid, real_t))
+    g2 = grid[1:]
+    f2, chi2 = rng.standard_normal(g2).astype(real_t), rng.random(g2).astype(real_t)
+    both(lambda o, out: o.brinkmann_vs_fixed_val(out, f2, chi2, 1e3, 0.7), np.zeros(g2, real_t))
 
 
 # ---- FFTPyFFTW{2,3}D plan objects and the scipy-named helper (SURVEY 8a rows a16, a18) -------------------------------

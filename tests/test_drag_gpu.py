@@ -26,9 +26,10 @@ def _sphere(n, radius, centre):
                      centre[2] + radius * np.cos(phi)])
 
 
-def _run(dim, grid, pos, steps, nu, stiffness, damping):
+def _run(dim, grid, pos, steps, nu, stiffness, damping, fixed_dt=False):
     import torch
 
+    from oracle import cstencils
     from oracle import flow as oflow
     from oracle import ib as oib
     from sopht_b200.numeric.immersed_boundary_ops import VirtualBoundaryForcing
@@ -37,7 +38,8 @@ def _run(dim, grid, pos, steps, nu, stiffness, damping):
     kw = dict(grid_size=grid, x_range=1.0, kinematic_viscosity=nu, real_t=np.float32, with_forcing=True,
               with_free_stream_flow=True)
     sim = (UnboundedNavierStokesFlowSimulator3D if dim == 3 else UnboundedNavierStokesFlowSimulator2D)(**kw)
-    ref = (oflow.UnboundedNavierStokesFlowSimulator3D if dim == 3 else oflow.UnboundedNavierStokesFlowSimulator2D)(**kw)
+    ref = (oflow.UnboundedNavierStokesFlowSimulator3D if dim == 3 else oflow.UnboundedNavierStokesFlowSimulator2D)(
+        workers=8, kernels=cstencils, **kw)
     n = pos.shape[1]
     vb = VirtualBoundaryForcing(virtual_boundary_stiffness_coeff=stiffness, virtual_boundary_damping_coeff=damping,
                                 grid_dim=dim, dx=sim.dx, num_lag_nodes=n, real_t=np.float32)
@@ -49,9 +51,13 @@ def _run(dim, grid, pos, steps, nu, stiffness, damping):
     sim.velocity_field[0] = 1.0
     ref.velocity_field[0] = 1.0
     drag, drag_ref, lift, lift_ref = [], [], [], []
+    dt0 = ref.compute_stable_timestep(dt_prefac=0.5)
     for _ in range(steps):
-        dt = ref.compute_stable_timestep(dt_prefac=0.5)
-        assert sim.compute_stable_timestep(dt_prefac=0.5) == pytest.approx(dt, rel=1e-4)
+        if fixed_dt:  # a fixed number of steps with a fixed dt (the stable dt of the impulsive start)
+            dt = dt0
+        else:
+            dt = ref.compute_stable_timestep(dt_prefac=0.5)
+            assert sim.compute_stable_timestep(dt_prefac=0.5) == pytest.approx(dt, rel=1e-4)
         vb.time_step(dt)
         vb_ref.time_step(dt)
         vb.compute_interaction_force_on_eul_and_lag_grid(sim.eul_grid_forcing_field, sim.velocity_field, pos_d, vel_d)
@@ -92,4 +98,31 @@ def test_drag_flow_past_sphere_3d():
     pos = _sphere(300, diameter / 2, (0.3, 0.25, 0.25))
     ds2 = np.pi * diameter**2 / 300
     out = _run(3, grid, pos, steps=20, nu=1.0 * diameter / 100.0, stiffness=-5e4 * ds2, damping=-20.0 * ds2)
+    _check(*out)
+
+
+def test_drag_flow_past_cylinder_c1_200_steps():
+    """BASELINE configs[0] at full size: 512x256 grid, Re = 100, cylinder radius 0.03 at (2.5 r, y/2), 60 forcing
+    points, coupling (-5e4, -20) (examples/2d_examples/FlowPastCylinderCase/flow_past_cylinder.py:28-66); 200 coupled
+    steps with a fixed dt; drag = |sum of the Lagrangian forcing along x| (:125-126) within 0.5 % of the oracle."""
+    grid = (256, 512)
+    radius = 0.03
+    pos = _circle(60, radius, (2.5 * radius, 0.25))
+    ds = 2 * np.pi * radius / 60
+    out = _run(2, grid, pos, steps=200, nu=radius * 1.0 / 100.0, stiffness=-5e4 * ds, damping=-20.0 * ds,
+               fixed_dt=True)
+    _check(*out)
+
+
+def test_drag_flow_past_sphere_c2_200_steps():
+    """BASELINE configs[1] at full size: 128x128x256 grid, Re = 100, sphere of diameter 0.2 at (0.25, 0.25, 0.25),
+    2914 forcing points (96 along the equator), coupling (-1.5e5, -87.5) ds^2 (examples/3d_examples/
+    FlowPastSphereCase/flow_past_sphere_case.py:28-69); 200 coupled steps with a fixed dt; drag =
+    |sum of the Lagrangian forcing along x| (:168-170) within 0.5 % of the oracle."""
+    grid = (128, 128, 256)
+    diameter = 0.2
+    pos = _sphere(2914, diameter / 2, (0.25, 0.25, 0.25))
+    ds2 = np.pi * diameter**2 / 2914
+    out = _run(3, grid, pos, steps=200, nu=1.0 * diameter / 100.0, stiffness=-1.5e5 * ds2, damping=-87.5 * ds2,
+               fixed_dt=True)
     _check(*out)

@@ -19,6 +19,51 @@ def test_oracle_poisson_matches_reference_goldens(case, precision):
     case(make_ops("oracle", precision), precision)
 
 
+# ---- the C / OpenMP restatement (the CPU baseline of bench.py) against the same goldens --------------------
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("case", STENCIL_CASES, ids=lambda c: c.__name__)
+def test_c_oracle_stencils_match_reference_goldens(case, precision):
+    case(make_ops("coracle", precision), precision)
+
+
+@pytest.mark.parametrize("precision", ["single", "double"])
+@pytest.mark.parametrize("case", POISSON_CASES, ids=lambda c: c.__name__)
+def test_c_oracle_poisson_matches_reference_goldens(case, precision):
+    case(make_ops("coracle", precision), precision)
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_c_oracle_flow_step_matches_numpy_oracle(dim):
+    """Whole coupled steps (forcing + free stream, 3-D also with the convolution filter): C passes vs numpy passes."""
+    import numpy as np
+
+    from oracle import cstencils
+    from oracle import flow as oflow
+
+    rng = np.random.default_rng(3)
+    if dim == 3:
+        grid, cls, extra = (12, 20, 28), oflow.UnboundedNavierStokesFlowSimulator3D, dict(
+            filter_vorticity=True, filter_setting_dict={"order": 3, "type": "convolution"})
+    else:
+        grid, cls, extra = (36, 52), oflow.UnboundedNavierStokesFlowSimulator2D, {}
+    kw = dict(grid_size=grid, x_range=1.0, kinematic_viscosity=1e-2, real_t=np.float32, with_forcing=True,
+              with_free_stream_flow=True, **extra)
+    a, b = cls(**kw), cls(kernels=cstencils, **kw)
+    for name in ("vorticity_field", "velocity_field", "eul_grid_forcing_field"):
+        v = rng.standard_normal(getattr(a, name).shape).astype(np.float32)
+        getattr(a, name)[...] = v
+        getattr(b, name)[...] = v
+    dt = a.compute_stable_timestep(0.5)
+    assert b.compute_stable_timestep(0.5) == pytest.approx(dt, rel=1e-6)
+    fsv = [1.0, -0.5, 0.25][:dim]
+    for _ in range(3):
+        a.time_step(dt, fsv)
+        b.time_step(dt, fsv)
+    for name in ("vorticity_field", "velocity_field", "stream_func_field"):
+        x, y = getattr(a, name).astype(np.float64), getattr(b, name).astype(np.float64)
+        assert np.linalg.norm(x - y) / np.linalg.norm(x) < 1e-5, name
+
+
 # ---- immersed boundary: oracle vs the reference's own numba implementation ----------------------------
 class _OracleComm:
     def __init__(self, dim, dx, shift, n, real_t, n_components, kernel_type):

@@ -131,9 +131,13 @@ def test_oracle_periodic_flow_step_taylor_green_decay():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("step_mode", ["fused", "unfused"])
+@pytest.mark.parametrize("grid", [(12, 20, 24), (5, 9, 160), (40, 24, 132)])
 @pytest.mark.parametrize("dtype", ["float32", "float64"])
-def test_cuda_periodic_flow_step_matches_oracle(dtype):
-    """The CUDA simulator against the numpy restatement on a random periodic field (identical step counts), and the
+def test_cuda_periodic_flow_step_matches_oracle(dtype, grid, step_mode):
+    """The CUDA simulator - the fused step (marching kernels with wrap-around x / y neighbour loads on z-halo-padded
+    arrays) and the pass-by-pass composition - against the numpy restatement on a random periodic field (identical
+    step counts; ragged grids: several warps per row, partial warps, one-CTA and multi-chunk z ranges), and the
     Taylor-Green decay on the device."""
     import torch
 
@@ -141,8 +145,9 @@ def test_cuda_periodic_flow_step_matches_oracle(dtype):
     from sopht_b200.simulator import PeriodicNavierStokesFlowSimulator3D
 
     real_t = np.float32 if dtype == "float32" else np.float64
-    grid, x_range, nu = (12, 20, 24), 1.0, 1e-2
-    sim = PeriodicNavierStokesFlowSimulator3D(grid, x_range, nu, real_t=real_t)
+    x_range, nu = 1.0, 1e-2
+    sim = PeriodicNavierStokesFlowSimulator3D(grid, x_range, nu, real_t=real_t, step_mode=step_mode)
+    assert sim.step_mode == step_mode
     ref = oflow.PeriodicNavierStokesFlowSimulator3D(grid, x_range, nu, real_t=np.float64)
     rng = np.random.default_rng(8)
     w0 = rng.standard_normal((3, *grid)).astype(real_t)
@@ -157,9 +162,10 @@ def test_cuda_periodic_flow_step_matches_oracle(dtype):
         ref.time_step(1e-4)
     assert _rel_l2(sim.vorticity_field.cpu().numpy(), ref.vorticity_field) < tol
     assert _rel_l2(sim.velocity_field.cpu().numpy(), ref.velocity_field) < tol
-    assert sim.compute_stable_timestep() == pytest.approx(ref.compute_stable_timestep(), rel=1e-4)
+    # (the float64 restatement adds 10 eps(float64) to the diffusion limit, the simulator 10 eps(real_t))
+    assert sim.compute_stable_timestep() == pytest.approx(ref.compute_stable_timestep(), rel=3e-3)
 
-    tg = PeriodicNavierStokesFlowSimulator3D((8, 32, 32), x_range, 5e-3, real_t=real_t)
+    tg = PeriodicNavierStokesFlowSimulator3D((8, 32, 32), x_range, 5e-3, real_t=real_t, step_mode=step_mode)
     w, k = _taylor_green_2d_vorticity(tg.position_field.cpu().numpy().astype(np.float64), x_range)
     tg.vorticity_field[2] = torch.from_numpy(w.astype(real_t)).cuda()
     tg.compute_velocity_from_vorticity()

@@ -6,6 +6,8 @@
 Workloads (grid tuples are (nz, ny, nx) like the reference):
   u512    3D unbounded flow step 512^3 fp32 (no body): the north-star single-GPU size; weak-scaled with the rank
           count, so --gpus 8 runs 1024^3 (BASELINE configs[4])                                             [default]
+  c1      2D flow past rigid cylinder, 512x256 fp32, 60 IB nodes (BASELINE configs[0]); latency-bound: the step is
+          captured in a CUDA graph, reported as Gcell/s and steps/s
   c2      3D flow past rigid sphere, unbounded Poisson, 128x128x256 fp32, IB forcing (BASELINE configs[1])
   c3      3D Cosserat rod in cross-flow, 256x128x128 fp32, order-5 filter (BASELINE configs[2])
   u256    3D unbounded flow step 256^3 fp32 (no body)
@@ -49,6 +51,8 @@ WORKLOADS = {
     "c3": dict(grid=(256, 128, 128), body="rod", x_range=1.8, filter={"order": 5, "type": "convolution"},
                desc="3D Cosserat rod (straight, fixed) in cross-flow with IB forcing, 256x128x128 fp32, "
                     "order-5 convolution filter"),
+    "c1": dict(grid=(256, 512), body="cylinder", two_d=True,
+               desc="2D flow past rigid cylinder (Re=100), 512x256 grid, fp32"),
     "u256": dict(grid=(256, 256, 256), body=None, desc="3D unbounded flow step 256^3 fp32"),
     "u512": dict(grid=(512, 512, 512), body=None, desc="3D unbounded flow step 512^3 fp32"),
     "tg512": dict(grid=(512, 512, 512), body=None, periodic=True,
@@ -73,6 +77,16 @@ def global_grid(wl, world):
 
 
 NU = 1e-3
+
+
+def fixed_dt(wl, dx):
+    """The fixed time step of the timed loops: 0.1 dx for the body-free workloads; with an immersed body the
+    virtual-boundary coupling (stiffness from the reference's examples) bounds it much lower - 0.02 dx for the sphere,
+    0.005 dx for the rod (0.1 dx blows the coupled rod case up within six steps; the work per step does not depend on
+    dt, a run on NaNs would still not be a measurement)."""
+    return float({"sphere": 0.02, "rod": 0.005}.get(wl.get("body"), 0.1) * dx)
+
+
 CPU_KIND_DESC = ("C/OpenMP loop nest per reference kernel (oracle/c/ref_kernels.c, unfused passes like pystencils) + "
                  "scipy.fft in place of pyFFTW")
 X_RANGE = 1.0
@@ -328,7 +342,7 @@ def cpu_sample_grid(grid, max_cells=2**24):
 def time_cpu(wl, steps, warmup):
     cores = len(os.sched_getaffinity(0))
     sim, vb = build_cpu_case(wl, cores)
-    dt = float(0.1 * sim.dx)
+    dt = fixed_dt(wl, sim.dx)
     for _ in range(warmup):
         cpu_step(sim, vb, dt)
     t0 = time.perf_counter()
@@ -469,9 +483,13 @@ def parity_slab(world):
 def guarded(fn, *a, limit_s=240.0):
     """Run a parity check; a hang (a peer that never answers) must not take the bench line with it."""
     box = {}
+    import torch
+
+    device = torch.cuda.current_device()  # the current device is thread-local: the worker must select it itself
 
     def work():
         try:
+            torch.cuda.set_device(device)
             box["r"] = fn(*a)
         except Exception as e:  # noqa: BLE001
             box["r"] = {"value": None, "ok": False, "error": f"{type(e).__name__}: {e}"[:300]}
@@ -542,7 +560,7 @@ def run_ours(args, wl):
             _lib.current_stream()))
         own = sim.owned
         cells_local = int(np.prod(grid)) // world
-    dt = float(0.1 * sim.dx)
+    dt = fixed_dt(wl, sim.dx)
     cells = int(np.prod(grid))
 
     interactor = None
@@ -636,9 +654,34 @@ def run_ours(args, wl):
 
     for _ in range(max(args.warmup, 3)):
         device_step()
+    # small grids: the fixed-dt step (interaction + flow step) replayed from a CUDA graph - the launches of a step
+    # are issued more slowly by the host than the device executes them
+    use_graph = world == 1 and (args.graph == "on" or (args.graph == "auto" and cells <= 2**24))
+    timed_step = device_step
+    if use_graph:
+        def ib_part():
+            if rod_interactor is not None:
+                rod_interactor.time_step(dt)
+                rod_interactor()
+            if interactor is not None:
+                interactor.time_step(dt)
+                interactor.compute_interaction_force_on_eul_and_lag_grid(
+                    own(sim.eul_grid_forcing_field), own(sim.velocity_field), pos_d, vel_d)
+
+        ib_state = []
+        for obj in (interactor, getattr(rod_interactor, "forcing_grid", None), rod_interactor):
+            ib_state += [v for v in vars(obj).values() if isinstance(v, torch.Tensor)] if obj is not None else []
+        try:
+            timed_step = sim.graph_time_step(dt, before=ib_part if forcing else None, extra_state=ib_state,
+                                             free_stream_velocity=U_INF)
+            for _ in range(3):
+                timed_step()
+        except Exception as e:  # noqa: BLE001 - a step that cannot be captured is measured eagerly
+            print(f"bench: CUDA graph capture failed ({type(e).__name__}: {e}); eager launches", file=sys.stderr)
+            timed_step, use_graph = device_step, False
     n0 = _lib.launch_count()
     with ClockSampler(local) as clk:
-        ms = timed(device_step, args.steps)
+        ms = timed(timed_step, args.steps)
     launches = _lib.launch_count() - n0
     value = cells * args.steps / (ms * 1e-3) / 1e9
 
@@ -682,7 +725,8 @@ def run_ours(args, wl):
         "data": "synthetic",
         "config": workload_config(
             wl, grid, world, (n_lag if rod_interactor is not None else int(pos_h.shape[1])) if forcing else 0),
-        "path": {"step_mode": sim.step_mode, "poisson_path": sim._unbounded_poisson_solver.path},
+        "path": {"step_mode": sim.step_mode, "poisson_path": sim._unbounded_poisson_solver.path,
+                 "cuda_graph": bool(use_graph)},
         "parity": parity,
         "e2e": {"value": e2e_val, "unit": "Gcell/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -709,11 +753,13 @@ PERIODIC_BYTES_PER_CELL = 180  # stencils 60 + periodic Poisson 3 x 4
 PERIODIC_KERNEL_BYTES = {"ns3d.advect": 36.0, "ns3d.diffuse": 24.0, "ns3d.velocity": 24.0}
 
 
-def taylor_green_vorticity(grid, real_t=np.float32):
-    """Vorticity of u = (sin x cos y cos z, -cos x sin y cos z, 0) on [0, 2 pi)^3 mapped onto the unit box."""
+def taylor_green_vorticity(grid, real_t=np.float32, z_offset=0, nx_global=None):
+    """Vorticity of u = (sin x cos y cos z, -cos x sin y cos z, 0) on [0, 2 pi)^3 mapped onto the unit box
+    (grid: the planes to produce, starting at global plane z_offset)."""
     nz, ny, nx = grid
+    nx = nx_global or nx
     k = 2 * np.pi
-    z = (np.arange(nz) + 0.5) / nx * k
+    z = (np.arange(nz) + z_offset + 0.5) / nx * k
     y = (np.arange(ny) + 0.5) / nx * k
     x = (np.arange(nx) + 0.5) / nx * k
     Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
@@ -755,34 +801,96 @@ def parity_periodic():
                        "random state; UNPINNED: the reference has no periodic code", "fields": errs}
 
 
+def parity_periodic_slab(world):
+    """N > 1: the slab-decomposed periodic step (ring halo exchange, NVLink transposes) against the single-GPU periodic
+    step of the same library on the whole grid, every rank on its own planes."""
+    import torch
+    import torch.distributed as dist
+
+    from sopht_b200.parallel import SlabPeriodicNavierStokesFlowSimulator3D
+    from sopht_b200.simulator import PeriodicNavierStokesFlowSimulator3D
+
+    grid = (128, 64, 256)
+    slab = SlabPeriodicNavierStokesFlowSimulator3D(grid, 1.0, NU)
+    full = PeriodicNavierStokesFlowSimulator3D(grid, 1.0, NU, real_t=np.float32)
+    w0 = np.random.default_rng(7).standard_normal((3, *grid)).astype(np.float32)
+    full.vorticity_field[...] = torch.from_numpy(w0).cuda()
+    slab.set_owned(slab.vorticity_field, w0)
+    full.compute_velocity_from_vorticity()
+    slab.compute_velocity_from_vorticity()
+    dt = float(full.compute_stable_timestep(0.5))
+    for _ in range(3):
+        full.time_step(dt)
+        slab.time_step(dt)
+    errs = {}
+    for name in ("vorticity_field", "velocity_field", "stream_func_field"):
+        a = slab.owned(getattr(slab, name)).double()
+        b = getattr(full, name)[:, slab.z_slice].double()
+        num = (a - b).pow(2).sum()
+        dist.all_reduce(num)
+        errs[name] = float((num / getattr(full, name).double().pow(2).sum()).sqrt())
+    worst = max(errs.values())
+    torch.cuda.synchronize()
+    del slab, full
+    torch.cuda.empty_cache()
+    return {"value": worst, "metric": "max rel-L2 (vorticity, velocity, stream function)", "tolerance": 1e-5,
+            "ok": bool(worst < 1e-5), "against": f"single-GPU periodic step of the same library on the whole 128x64x256 "
+            f"grid, {world} z-slabs, 3 steps (UNPINNED by the reference: it has no periodic code)", "fields": errs}
+
+
 def run_periodic(args, wl):
     import torch
 
     from sopht_b200 import _lib
     from sopht_b200.simulator import PeriodicNavierStokesFlowSimulator3D
 
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        raise SystemExit("the periodic workloads are single-GPU bench lines in this round")
-    torch.cuda.set_device(0)
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     _lib.load()
-    grid = wl["grid"]
+    grid = global_grid(wl, world)
     cells = int(np.prod(grid))
-    parity = None if args.no_parity else guarded(parity_periodic)
-    sim = PeriodicNavierStokesFlowSimulator3D(grid, X_RANGE, NU, real_t=np.float32, step_mode=(
-        "auto" if args.step_mode == "auto" else args.step_mode))
-    sim.vorticity_field[...] = torch.from_numpy(taylor_green_vorticity(grid)).cuda()
+    cells_local = cells // world
+    if world == 1:
+        parity = None if args.no_parity else guarded(parity_periodic)
+        sim = PeriodicNavierStokesFlowSimulator3D(grid, X_RANGE, NU, real_t=np.float32, step_mode=(
+            "auto" if args.step_mode == "auto" else args.step_mode))
+        sim.vorticity_field[...] = torch.from_numpy(taylor_green_vorticity(grid)).cuda()
+    else:
+        from sopht_b200.parallel import SlabPeriodicNavierStokesFlowSimulator3D
+
+        parity = None if args.no_parity else guarded(parity_periodic_slab, world)
+        sim = SlabPeriodicNavierStokesFlowSimulator3D(grid, X_RANGE, NU)
+        z0, nzl = sim.part.z_start, sim.part.nz_local
+        w0 = taylor_green_vorticity((nzl, grid[1], grid[2]), z_offset=z0, nx_global=grid[2])
+        sim.owned(sim.vorticity_field)[...] = torch.from_numpy(w0).cuda()
     sim.compute_velocity_from_vorticity()
     dt = float(0.1 * sim.dx)
 
-    def timed(fn, steps):
+    def barrier():
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
 
     def device_step():
         sim.time_step(dt)
@@ -793,7 +901,7 @@ def run_periodic(args, wl):
     for _ in range(max(args.warmup, 3)):
         device_step()
     n0 = _lib.launch_count()
-    with ClockSampler(0) as clk:
+    with ClockSampler(local) as clk:
         ms = timed(device_step, args.steps)
     launches = _lib.launch_count() - n0
     value = cells * args.steps / (ms * 1e-3) / 1e9
@@ -802,12 +910,15 @@ def run_periodic(args, wl):
     ms_e2e = timed(e2e_step, args.steps)
     peak, peak_src = measured_peak_hbm()
     _lib.profile_enable(True)
-    torch.cuda.synchronize()
+    barrier()
     for _ in range(args.steps):
         device_step()
-    torch.cuda.synchronize()
+    barrier()
     report = _lib.profile_report()
     _lib.profile_enable(False)
+    if rank != 0:
+        return
+    cells_all, cells = cells, cells_local  # per-GPU figures below
     kernels = {}
     total = sum(v["ms"] for v in report.values()) or 1.0
     for label, v in report.items():
@@ -825,13 +936,13 @@ def run_periodic(args, wl):
             "achieved_gbs": 120.0 * cells * args.steps / (pois_ms * 1e-3) / 1e9 if pois_ms else None}
     if pois["achieved_gbs"]:
         pois["frac"] = pois["achieved_gbs"] / peak
-    whole = PERIODIC_BYTES_PER_CELL * cells * args.steps / (ms * 1e-3) / 1e9
+    whole = PERIODIC_BYTES_PER_CELL * cells * args.steps / (ms * 1e-3) / 1e9  # per GPU
     roof = {"bound": "hbm", "achieved": pois["achieved_gbs"], "peak": peak, "unit": "GB/s",
             "frac": pois.get("frac"), "traffic": None, "kernel": "periodic Poisson solve (all passes)",
             "algorithmic_bytes_per_launch": 120.0 * cells, "avg_launch_ms": pois["ms_per_step"],
             "share_of_step": pois_ms / total, "peak_source": peak_src}
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         from oracle import flow as oflow
 
         g = cpu_sample_grid(grid, 2**22)
@@ -847,19 +958,158 @@ def run_periodic(args, wl):
                "sample": f"3 steps (+1 warm-up) of the numpy restatement of the periodic step on a {g[0]}x{g[1]}x{g[2]} "
                          f"grid (bounded sample), {el * 1e3:.0f} ms/step"}
     line = {
-        "metric": "3D flow step Gcell-updates/s", "value": value, "unit": "Gcell/s", "n_gpus": 1,
+        "metric": "3D flow step Gcell-updates/s", "value": value, "unit": "Gcell/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(wl, grid, 1, 0),
-        "path": {"step_mode": sim.step_mode, "poisson_path": "periodic: cuFFT transforms + symbol kernel"},
+        "config": workload_config(wl, grid, world, 0),
+        "path": {"step_mode": sim.step_mode, "poisson_path": sim._poisson.path},
         "parity": parity,
-        "e2e": {"value": cells * args.steps / (ms_e2e * 1e-3) / 1e9, "unit": "Gcell/s",
+        "e2e": {"value": cells_all * args.steps / (ms_e2e * 1e-3) / 1e9, "unit": "Gcell/s",
                 "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
                 "note": "stable-dt read-back every step, then the step"},
         "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roof,
         "step_roofline": {"algorithmic_bytes_per_cell": PERIODIC_BYTES_PER_CELL, "achieved": whole, "unit": "GB/s",
                           "frac": whole / peak},
         "kernels": kernels, "poisson": pois, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# 2-D flow past a cylinder (BASELINE configs[0]); single GPU, latency-bound
+# ---------------------------------------------------------------------------------------------------------
+def cylinder_case():
+    radius = 0.03  # flow_past_cylinder.py:31-66
+    n = 60
+    a = 2 * np.pi * (np.arange(n) + 0.5) / n
+    pos = np.stack([2.5 * radius + radius * np.cos(a), 0.25 + radius * np.sin(a)])
+    ds = 2 * np.pi * radius / n
+    return pos, radius * 1.0 / 100.0, -5e4 * ds, -20.0 * ds
+
+
+def run_2d(args, wl):
+    import torch
+
+    from sopht_b200 import _lib
+
+    grid = wl["grid"]
+    cells = int(np.prod(grid))
+    pos, nu, stiff, damp = cylinder_case()
+    kw = dict(grid_size=grid, x_range=1.0, kinematic_viscosity=nu, real_t=np.float32, with_forcing=True,
+              with_free_stream_flow=True)
+    cores = len(os.sched_getaffinity(0))
+    if args.impl == "reference":
+        from oracle import cstencils
+        from oracle import flow as oflow
+        from oracle import ib as oib
+
+        cstencils.load()
+        cstencils.set_num_threads(cores)
+        ref = oflow.UnboundedNavierStokesFlowSimulator2D(workers=cores, kernels=cstencils, **kw)
+        vb = oib.VirtualBoundaryForcing(stiff, damp, 2, ref.dx, pos.shape[1], np.float32)
+        ref.velocity_field[0] = 1.0
+        vel = np.zeros_like(pos)
+        dt = float(0.05 * ref.dx)
+
+        def cpu_step():
+            vb.time_step(dt)
+            vb.compute_interaction_force_on_eul_and_lag_grid(ref.eul_grid_forcing_field, ref.velocity_field, pos, vel)
+            ref.time_step(dt, free_stream_velocity=[1.0, 0.0])
+
+        for _ in range(args.warmup):
+            cpu_step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            cpu_step()
+        el = time.perf_counter() - t0
+        val = cells * args.steps / el / 1e9
+        print(json.dumps({
+            "impl": "reference", "metric": "2D flow step Gcell-updates/s", "value": val, "unit": "Gcell/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3,
+            "steps_per_s": args.steps / el, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(wl, grid, 1, int(pos.shape[1])),
+            "cpu_baseline": {"value": val, "unit": "Gcell/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} full coupled steps; {CPU_KIND_DESC}"},
+            "e2e": {"value": val, "unit": "Gcell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}), flush=True)
+        return
+    from sopht_b200.numeric.immersed_boundary_ops import VirtualBoundaryForcing
+    from sopht_b200.simulator import UnboundedNavierStokesFlowSimulator2D
+
+    torch.cuda.set_device(0)
+    _lib.load()
+    sim = UnboundedNavierStokesFlowSimulator2D(**kw)
+    sim.velocity_field[0] = 1.0
+    vb = VirtualBoundaryForcing(virtual_boundary_stiffness_coeff=stiff, virtual_boundary_damping_coeff=damp,
+                                grid_dim=2, dx=sim.dx, num_lag_nodes=pos.shape[1], real_t=np.float32)
+    pos_h = torch.from_numpy(pos).pin_memory()
+    vel_h = torch.zeros_like(pos_h).pin_memory()
+    pos_d, vel_d = pos_h.cuda(), vel_h.cuda()
+    force_h = torch.zeros(2, pos.shape[1], dtype=torch.float32).pin_memory()
+    dt = float(0.05 * sim.dx)
+    u_inf = [1.0, 0.0]
+
+    def ib_part():
+        vb.time_step(dt)
+        vb.compute_interaction_force_on_eul_and_lag_grid(sim.eul_grid_forcing_field, sim.velocity_field, pos_d, vel_d)
+
+    def device_step():
+        ib_part()
+        sim.time_step(dt=dt, free_stream_velocity=u_inf)
+
+    def e2e_step():
+        step_dt = sim.compute_stable_timestep(dt_prefac=0.5)
+        p, v = pos_h.to("cuda", non_blocking=True), vel_h.to("cuda", non_blocking=True)
+        vb.time_step(step_dt)
+        vb.compute_interaction_force_on_eul_and_lag_grid(sim.eul_grid_forcing_field, sim.velocity_field, p, v)
+        force_h.copy_(vb.lag_grid_forcing_field, non_blocking=True)
+        sim.time_step(dt=step_dt, free_stream_velocity=u_inf)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    steps = max(args.steps, 200)  # a step is tens of microseconds: time at least a few milliseconds
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    ms_eager = timed(device_step, steps)
+    graphed = None
+    if args.graph != "off":
+        state = [v for v in vars(vb).values() if isinstance(v, torch.Tensor)]
+        graphed = sim.graph_time_step(dt, before=ib_part, extra_state=state, free_stream_velocity=u_inf)
+        for _ in range(3):
+            graphed()
+    n0 = _lib.launch_count()
+    with ClockSampler(0) as clk:
+        ms = timed(graphed or device_step, steps)
+    launches = _lib.launch_count() - n0
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, steps)
+    peak, peak_src = measured_peak_hbm()
+    bpc = 88.0  # 2-D unbounded step, fp32 (L2-resident at this size: reported, not a roofline claim)
+    line = {
+        "metric": "2D flow step Gcell-updates/s", "value": cells * steps / (ms * 1e-3) / 1e9, "unit": "Gcell/s",
+        "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / steps,
+        "steps_per_s": steps / (ms * 1e-3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(wl, grid, 1, int(pos.shape[1])),
+        "path": {"step_mode": "unfused kernels", "cuda_graph": graphed is not None,
+                 "eager_ms_per_step": ms_eager / steps, "launches_per_step": launches / steps},
+        "e2e": {"value": cells * steps / (ms_e2e * 1e-3) / 1e9, "unit": "Gcell/s", "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": int(pos_h.numel() * 16), "d2h_bytes_per_step": int(4 + force_h.numel() * 4)},
+        "gpu_launches": int(launches), "clocks": clk.summary(),
+        "roofline": {"bound": "hbm", "achieved": bpc * cells * steps / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": bpc * cells * steps / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                     "kernel": "whole 2-D step (0.5 MB fields are L2-resident: launch-latency-bound)",
+                     "peak_source": peak_src},
     }
     print(json.dumps(line), flush=True)
 
@@ -874,9 +1124,13 @@ def main():
     ap.add_argument("--step-mode", default="auto", choices=["auto", "fused", "unfused"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="replay the device-resident step from a CUDA graph (auto: grids up to 2^24 cells, one GPU)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
-    if wl.get("periodic"):
+    if wl.get("two_d"):
+        run_2d(args, wl)
+    elif wl.get("periodic"):
         if args.impl == "reference":
             raise SystemExit("the periodic workloads have no reference arm (the reference has no periodic case)")
         run_periodic(args, wl)

@@ -345,6 +345,12 @@ typedef struct sopht_poisson_slab *sopht_poisson_slab_t;
 int sopht_poisson_slab_create(sopht_poisson_slab_t *handle, int ncomp, int nz, int ny, int nx, int nranks,
                               int rank, double dx, const double *mz, const double *my, const double *mx,
                               double origin_value, void *stream);
+/* The same handle for the PERIODIC box (an extension, BASELINE config 4; nearest reference code: none): -lap(psi) = rhs
+ * with the spectral ((2 pi m / L)^2) or three-point symbol, mean mode dropped. nx is the REAL grid size; rows carry
+ * nx / 2 complex bins + the Nyquist bin, so the exchange buffers are (C, P, nz/P, ny, nx/2/P); y and z passes run in
+ * place - work_buffer / nyquist_work of yz() are unused (may be NULL). */
+int sopht_poisson_slab_create_periodic(sopht_poisson_slab_t *handle, int ncomp, int nz, int ny, int nx, int nranks,
+                                       int rank, double dx, int three_point_symbol, void *stream);
 /* rhs_field: this rank's (C, nz/P, ny, nx) slab (strided view allowed) */
 int sopht_poisson_slab_forward_x(sopht_poisson_slab_t handle, const sopht_field_t *rhs_field,
                                  void *send_buffer, void *nyquist_local, void *stream);
@@ -395,6 +401,9 @@ typedef struct sopht_peer_arena *sopht_peer_arena_t;
 int sopht_peer_arena_create(sopht_peer_arena_t *handle, size_t payload_bytes, int nranks, int rank,
                             unsigned char *ipc_handle_out);
 int sopht_peer_arena_open(sopht_peer_arena_t handle, const unsigned char *all_ipc_handles);
+/* periodic_z != 0: the ranks form a ring (the low neighbour of rank 0 is rank nranks - 1): halo exchange of a periodic
+ * box (BASELINE config 4). Default 0: the global z boundaries have no neighbour. */
+int sopht_peer_arena_set_periodic(sopht_peer_arena_t handle, int periodic_z);
 /* device pointer to this rank's payload; the host layer lays the same objects out at the same offsets on all ranks */
 void *sopht_peer_arena_payload(sopht_peer_arena_t handle);
 /* Fills the z halo planes of up to 4 local arrays (ncomp[q], nz_local + 2 halo, ny, nx), given by their byte offset
@@ -450,6 +459,10 @@ int sopht_ib_lagrangian_to_eulerian(int dtype, int dim, const sopht_field_t *eul
 /* One launch for the whole virtual-boundary interaction (cosine kernel): support, weights, velocity
  * gather, dv = U - V_body, F = k dX + c dv, spread of F (eul_grid_forcing_field may be NULL: Lagrangian
  * part only). ref: immersed_boundary_ops/VirtualBoundaryForcing.py:187-253 */
+/* running count of Lagrangian nodes that overflowed their tile's list in the atomic-free spread (see ib.cu section 6)
+ * and were spread with atomics instead; synchronises the device. */
+int sopht_ib_spread_stragglers(unsigned long long *count_out);
+
 int sopht_ib_virtual_boundary_forcing(int dtype, int dim, const sopht_field_t *eul_grid_forcing_field,
                                       const sopht_field_t *eul_grid_velocity_field,
                                       const sopht_field_t *lag_positions,

@@ -226,9 +226,11 @@ struct TwTable {
 // ---- passes. `Acc` maps a logical position (0..L-1) of THIS thread's column to a float2& in smem ---------
 // tw: the TwTable<L> above
 
-// forward first pass: global (pruned: positions >= L/2 are zero) -> butterfly R1 -> twiddle -> smem
-template <int L, class Load, class Acc>
-FFT_HD void fwd_first(Load ld, Acc sm, int t, const float2* __restrict__ tw) {
+// forward first pass: global -> butterfly R1 -> twiddle -> smem. FULL = false: the input is zero-padded to twice its
+// length (positions >= L/2 are zero and never read - the unbounded solver's doubled domain); FULL = true: all L
+// positions are data (the periodic solver).
+template <int L, bool FULL, class Load, class Acc>
+FFT_HD void fwd_first_x(Load ld, Acc sm, int t, const float2* __restrict__ tw) {
   using C = Cfg<L>;
   constexpr int R = C::R1, S = L / R, NB = C::E / R;
   float2 v[NB][R];
@@ -236,16 +238,23 @@ FFT_HD void fwd_first(Load ld, Acc sm, int t, const float2* __restrict__ tw) {
   for (int q = 0; q < NB; ++q) {
     const int j = t + q * C::T;
 #pragma unroll
-    for (int n = 0; n < R; ++n) v[q][n] = n < R / 2 ? ld(n * S + j) : make_float2(0.f, 0.f);
+    for (int n = 0; n < R; ++n) v[q][n] = (FULL || n < R / 2) ? ld(n * S + j) : make_float2(0.f, 0.f);
   }
 #pragma unroll
   for (int q = 0; q < NB; ++q) {
     const int j = t + q * C::T;
-    Dft<R>::run_half(v[q]);  // pruned: the upper half of the padded input is zero
+    if (FULL)
+      Dft<R>::run(v[q]);
+    else
+      Dft<R>::run_half(v[q]);  // pruned: the upper half of the padded input is zero
     sm.at(0, j) = v[q][0];
 #pragma unroll
     for (int k = 1; k < R; ++k) sm.at(k * S, j) = cmul(v[q][k], tw[k * S + j]);
   }
+}
+template <int L, class Load, class Acc>
+FFT_HD void fwd_first(Load ld, Acc sm, int t, const float2* __restrict__ tw) {
+  fwd_first_x<L, false>(ld, sm, t, tw);
 }
 
 // forward middle pass (three-pass configurations only): smem -> butterfly R2 -> twiddle -> smem
@@ -347,8 +356,9 @@ FFT_HD void inv_mid(Acc sm, int t, const float2* __restrict__ tw) {
 }
 
 // inverse last pass: smem -> conj twiddle -> inverse butterfly R1 -> st(position e, value) for e < L/2 only
-template <int L, class Acc, class Store>
-FFT_HD void inv_last(Acc sm, int t, const float2* __restrict__ tw, Store st) {
+// (FULL = true: every position)
+template <int L, bool FULL, class Acc, class Store>
+FFT_HD void inv_last_x(Acc sm, int t, const float2* __restrict__ tw, Store st) {
   using C = Cfg<L>;
   constexpr int R = C::R1, S = L / R, NB = C::E / R;
 #pragma unroll
@@ -360,22 +370,30 @@ FFT_HD void inv_last(Acc sm, int t, const float2* __restrict__ tw, Store st) {
     for (int k = 1; k < R; ++k) v[k] = cmul_conj(sm.at(k * S, j), tw[k * S + j]);
     dft<R, true>(v);
 #pragma unroll
-    for (int n = 0; n < R / 2; ++n) st(n * S + j, v[n]);
+    for (int n = 0; n < (FULL ? R : R / 2); ++n) st(n * S + j, v[n]);
   }
+}
+template <int L, class Acc, class Store>
+FFT_HD void inv_last(Acc sm, int t, const float2* __restrict__ tw, Store st) {
+  inv_last_x<L, false>(sm, t, tw, st);
 }
 
 
 // ---- which elements a thread consumes in its first pass (used to prefetch exactly those) -----------------
-template <int L, class F>
-FFT_HD void fwd_first_elems(int t, F f) {  // f(position e), e < L/2
+template <int L, bool FULL, class F>
+FFT_HD void fwd_first_elems_x(int t, F f) {  // f(position e), e < L/2 (FULL: e < L)
   using C = Cfg<L>;
   constexpr int R = C::R1, S = L / R, NB = C::E / R;
 #pragma unroll
   for (int q = 0; q < NB; ++q) {
     const int j = t + q * C::T;
 #pragma unroll
-    for (int n = 0; n < R / 2; ++n) f(n * S + j);
+    for (int n = 0; n < (FULL ? R : R / 2); ++n) f(n * S + j);
   }
+}
+template <int L, class F>
+FFT_HD void fwd_first_elems(int t, F f) {
+  fwd_first_elems_x<L, false>(t, f);
 }
 template <int L, class F>
 FFT_HD void inv_first_elems(int t, F f) {  // f(spectrum index k)

@@ -10,6 +10,8 @@
 // virtual-boundary kernel does support + weights + gather + penalty force + spread for a node in ONE
 // launch, computing the separable weights in registers (and still storing the public buffers).
 // Taps that fall outside the grid are skipped (the reference indexes out of bounds there).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace sopht {
@@ -297,6 +299,304 @@ __global__ void __launch_bounds__(256) vbf_fused_kernel(VbfArgs a, EulView vel, 
   }
 }
 
+// ---- 6. Lagrangian -> Eulerian spread without global floating-point atomics -----------------------------------
+// The reference spreads node by node in a serial loop (EulerianLagrangianGridCommunicator3D.py:348-380): every cell
+// receives its contributions in node order. `red.global.add` from one warp per node gives the same sum in a
+// run-dependent order (fp addition is not associative: results differ in the last bits from run to run) and
+// serialises on the cells shared by neighbouring nodes. Here the scatter is turned into a per-tile GATHER:
+//   bin:   a node belongs to the grid tile (8^3 cells / 16^2 in 2-D) that holds the low corner of its 4^dim support;
+//          one integer atomicAdd on the tile's counter gives it a slot in the tile's node list (capacity CAP; the
+//          rare node beyond it is a straggler and spreads with atomics right there);
+//   tile:  one CTA per tile, one thread per cell. The supports that can reach the tile start in the tile itself or in
+//          the previous tile along each axis (support width 4 <= tile size): the CTA merges those 2^dim lists in
+//          shared memory, sorts them by node index, and every thread walks the sorted list accumulating F_i * w for
+//          the nodes whose support covers its cell. The thread owns its cell: one plain read-modify-write, no atomics,
+//          and the summation order is the reference's (ascending node index) - bit-reproducible.
+// The tile counters are cleared by a cudaMemsetAsync in front of the bin kernel.
+template <int DIM>
+struct SpreadTile {
+  static constexpr int TS = DIM == 3 ? 8 : 16;                 // tile edge in cells (>= support width 4)
+  static constexpr int THREADS = DIM == 3 ? 512 : 256;         // one thread per cell
+  static constexpr int NSRC = DIM == 3 ? 8 : 4;                // source tiles of an output tile
+  static constexpr int CAP = 128;                              // list slots per tile (a body surface with one node per
+                                                               // cell^2 starts ~64 supports in an 8^3 tile)
+  static constexpr int MAXN = NSRC * CAP;                      // merged list: a power of two, two entries per thread
+};
+struct SpreadWork {
+  int* counts = nullptr;  // [ntiles] list lengths, [ntiles] "on the work list" flags, [1] work-list length: one memset
+  int* lists = nullptr;   // [ntiles][CAP]
+  int* active = nullptr;  // [ntiles] work list of the gather kernel
+  unsigned long long* stragglers = nullptr;  // running count of nodes that overflowed their tile's list
+  int64_t ntiles = 0;
+  int dev = -1;
+};
+static SpreadWork g_spread_work;
+
+static int spread_workspace(int64_t ntiles, int cap, SpreadWork** out) {
+  SpreadWork& w = g_spread_work;
+  int dev = 0;
+  SOPHT_CUDA(cudaGetDevice(&dev));
+  if (w.dev != dev || w.ntiles < ntiles) {
+    cudaFree(w.counts);
+    cudaFree(w.lists);
+    cudaFree(w.active);
+    if (!w.stragglers || w.dev != dev) {
+      cudaFree(w.stragglers);
+      SOPHT_CUDA(cudaMalloc(&w.stragglers, sizeof(unsigned long long)));
+      SOPHT_CUDA(cudaMemset(w.stragglers, 0, sizeof(unsigned long long)));
+    }
+    w.counts = w.lists = w.active = nullptr;
+    SOPHT_CUDA(cudaMalloc(&w.counts, sizeof(int) * (2 * ntiles + 1)));
+    SOPHT_CUDA(cudaMalloc(&w.lists, sizeof(int) * ntiles * cap));
+    SOPHT_CUDA(cudaMalloc(&w.active, sizeof(int) * ntiles));
+    w.ntiles = ntiles;
+    w.dev = dev;
+  }
+  *out = &w;
+  return SOPHT_OK;
+}
+
+struct TileGrid {
+  int nt[3];  // tiles per array axis (slowest first), 1 for unused axes
+};
+template <int DIM>
+__device__ __forceinline__ int tile_of_corner(const EulView& e, const TileGrid& tg, const int64_t idx[3], bool* any) {
+  // idx[d]: d = 0 is x; support corner = idx - 1. A support that misses the grid entirely has no tile.
+  int t = 0;
+  *any = true;
+#pragma unroll
+  for (int ax = 0; ax < DIM; ++ax) {
+    const int d = DIM - 1 - ax;
+    const int64_t c = idx[d] - 1;
+    if (c + 3 < 0 || c >= e.n[ax]) *any = false;
+    const int64_t cc = c < 0 ? 0 : c;
+    int ta = (int)(cc / SpreadTile<DIM>::TS);
+    if (ta >= tg.nt[ax]) ta = tg.nt[ax] - 1;
+    t = t * tg.nt[ax] + ta;
+  }
+  return t;
+}
+
+template <typename T, int DIM>
+__global__ void __launch_bounds__(256)
+    ib_bin_kernel(EulView eul, TileGrid tg, const T* lag, int64_t lag_sc, const T* weights, const int64_t* nearest,
+                  int64_t n_lag, int* counts, int* lists, unsigned long long* stragglers, int* flags, int* active,
+                  int* nactive) {
+  constexpr int NT = Taps<DIM>::N, CAP = SpreadTile<DIM>::CAP;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_lag) return;
+  int64_t idx[3] = {0, 0, 0};
+#pragma unroll
+  for (int d = 0; d < DIM; ++d) idx[d] = nearest[d * n_lag + i];
+  bool any;
+  const int tile = tile_of_corner<DIM>(eul, tg, idx, &any);
+  if (!any) return;
+  const int slot = atomicAdd(counts + tile, 1);
+  if (slot == 0) {
+    // first node of this tile: its supports reach this tile and the next one along each axis - put those output tiles
+    // on the work list of the gather kernel (once each: flags)
+    int tc[3] = {0, 0, 0};
+    int r = tile;
+#pragma unroll
+    for (int ax = DIM - 1; ax >= 0; --ax) {
+      tc[ax] = r % tg.nt[ax];
+      r /= tg.nt[ax];
+    }
+    for (int k = 0; k < SpreadTile<DIM>::NSRC; ++k) {
+      int t = 0;
+      bool ok = true;
+#pragma unroll
+      for (int ax = 0; ax < DIM; ++ax) {
+        const int ta = tc[ax] + ((k >> (DIM - 1 - ax)) & 1);
+        if (ta >= tg.nt[ax]) ok = false;
+        t = t * tg.nt[ax] + ta;
+      }
+      if (ok && atomicExch(flags + t, 1) == 0) active[atomicAdd(nactive, 1)] = t;
+    }
+  }
+  if (slot < CAP) {
+    lists[(int64_t)tile * CAP + slot] = (int)i;
+    return;
+  }
+  // straggler: more nodes start in this tile than its list holds - spread with atomics (order not reproducible)
+  atomicAdd(stragglers, 1ull);
+  T* ep = reinterpret_cast<T*>(eul.p);
+  for (int t = 0; t < NT; ++t) {
+    int off[3];
+    tap_offsets<DIM>(t, off);
+    const int64_t cell = tap_cell<DIM>(eul, idx, off);
+    if (cell >= 0) {
+      const T w = weights[(int64_t)t * n_lag + i];
+      for (int c = 0; c < eul.ncomp; ++c) atomicAdd(ep + c * eul.sc + cell, lag[c * lag_sc + i] * w);
+    }
+  }
+}
+
+template <typename T, int DIM>
+__global__ void __launch_bounds__(SpreadTile<DIM>::THREADS)
+    ib_tile_gather_kernel(EulView eul, TileGrid tg, const T* lag, int64_t lag_sc, const T* weights,
+                          const int64_t* nearest, int64_t n_lag, const int* counts, const int* lists,
+                          const int* active, const int* nactive) {
+  using ST = SpreadTile<DIM>;
+  constexpr int TS = ST::TS, CAP = ST::CAP, MAXN = ST::MAXN, NSRC = ST::NSRC;
+  __shared__ int s_node[MAXN];
+  __shared__ int s_corner[MAXN][3];  // per array axis (slowest first)
+  __shared__ T s_force[MAXN][3];
+  __shared__ int s_cnt[NSRC], s_src[NSRC];
+  const int tid = threadIdx.x;
+  const int na = *nactive;
+  // the blocks walk the list of tiles some support reaches (a few hundred for a body surface; the order of the list
+  // varies from run to run, a tile's result does not depend on it)
+  for (int a = blockIdx.x; a < na; a += gridDim.x) {
+    const int tile = active[a];
+    int tc[3] = {0, 0, 0};
+    {
+      int r = tile;
+#pragma unroll
+      for (int ax = DIM - 1; ax >= 0; --ax) {
+        tc[ax] = r % tg.nt[ax];
+        r /= tg.nt[ax];
+      }
+    }
+    __syncthreads();  // the previous tile's readers of the shared arrays are done
+    if (tid < NSRC) {
+      int t = 0;
+      bool ok = true;
+#pragma unroll
+      for (int ax = 0; ax < DIM; ++ax) {
+        const int ta = tc[ax] - ((tid >> (DIM - 1 - ax)) & 1);
+        if (ta < 0) ok = false;
+        t = t * tg.nt[ax] + ta;
+      }
+      const int c = ok ? counts[t] : 0;
+      s_cnt[tid] = c < CAP ? c : CAP;
+      s_src[tid] = ok ? t : -1;
+    }
+    __syncthreads();
+    int total = 0;
+    int src_start[NSRC];
+#pragma unroll
+    for (int k = 0; k < NSRC; ++k) {
+      src_start[k] = total;
+      total += s_cnt[k];
+    }
+    if (total == 0) continue;  // block-uniform
+    // merged list, padded with INT_MAX up to the next power of two >= total, then a bitonic sort by node index
+    int len = 2;
+    while (len < total) len <<= 1;
+    for (int e = tid; e < len; e += ST::THREADS) {
+      int mine = 0x7fffffff;
+#pragma unroll
+      for (int k = 0; k < NSRC; ++k)
+        if (e >= src_start[k] && e < src_start[k] + s_cnt[k]) mine = lists[(int64_t)s_src[k] * CAP + (e - src_start[k])];
+      s_node[e] = mine;
+    }
+    __syncthreads();
+    for (int k = 2; k <= len; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < len / 2; i += ST::THREADS) {
+          const int lo = 2 * i - (i & (j - 1)), hi = lo + j;  // the i-th compare-exchange pair of this stage
+          const int x = s_node[lo], y = s_node[hi];
+          const bool up = (lo & k) == 0;
+          if ((x > y) == up) {
+            s_node[lo] = y;
+            s_node[hi] = x;
+          }
+        }
+        __syncthreads();
+      }
+    for (int e = tid; e < total; e += ST::THREADS) {
+      const int node = s_node[e];
+#pragma unroll
+      for (int ax = 0; ax < DIM; ++ax) s_corner[e][ax] = (int)nearest[(int64_t)(DIM - 1 - ax) * n_lag + node] - 1;
+      for (int c = 0; c < eul.ncomp; ++c) s_force[e][c] = lag[c * lag_sc + node];
+    }
+    __syncthreads();
+    // this thread's cell
+    int cell[3] = {0, 0, 0};
+    {
+      int r = tid;
+#pragma unroll
+      for (int ax = DIM - 1; ax >= 0; --ax) {
+        cell[ax] = tc[ax] * TS + r % TS;
+        r /= TS;
+      }
+    }
+    bool inside = true;
+    int64_t o = 0;
+#pragma unroll
+    for (int ax = 0; ax < DIM; ++ax) {
+      if (cell[ax] >= eul.n[ax]) inside = false;
+      o += (int64_t)cell[ax] * eul.s[ax];
+    }
+    if (inside) {
+      T acc[3] = {T(0), T(0), T(0)};
+      bool hit = false;
+      for (int m = 0; m < total; ++m) {
+        int tap = 0;
+        bool cover = true;
+#pragma unroll
+        for (int ax = 0; ax < DIM; ++ax) {
+          const int d = cell[ax] - s_corner[m][ax];
+          if (d < 0 || d > 3) cover = false;
+          tap = tap * 4 + d;  // (kz*4 + ky)*4 + kx: array-axis order, like tap_offsets
+        }
+        if (cover) {
+          const T w = weights[(int64_t)tap * n_lag + s_node[m]];
+          for (int c = 0; c < eul.ncomp; ++c) acc[c] += s_force[m][c] * w;
+          hit = true;
+        }
+      }
+      if (hit) {
+        T* ep = reinterpret_cast<T*>(eul.p);
+        for (int c = 0; c < eul.ncomp; ++c) ep[c * eul.sc + o] += acc[c];
+      }
+    }
+  }
+}
+
+static bool spread_tiles_enabled() {
+  static const int v = [] {
+    const char* e = getenv("SOPHT_IB_SPREAD");
+    return !(e && e[0] == 'a');  // "atomics": one warp per node with red.global.add (the round-1 path)
+  }();
+  return v != 0;
+}
+
+template <typename T, int DIM>
+static int spread_tiles(const EulView& ev, const T* lag, int64_t lag_sc, const T* weights, const int64_t* nearest,
+                        int64_t n, cudaStream_t st) {
+  using ST = SpreadTile<DIM>;
+  static_assert((ST::MAXN & (ST::MAXN - 1)) == 0, "bitonic sort length");
+  TileGrid tg{{1, 1, 1}};
+  int64_t ntiles = 1;
+  for (int ax = 0; ax < DIM; ++ax) {
+    tg.nt[ax] = (ev.n[ax] + ST::TS - 1) / ST::TS;
+    ntiles *= tg.nt[ax];
+  }
+  if (ntiles > 0x7fffffff) SOPHT_FAIL(SOPHT_ERR_SHAPE, "ib spread: grid too large");
+  SpreadWork* w;
+  int rc = spread_workspace(ntiles, ST::CAP, &w);
+  if (rc) return rc;
+  int* cur = w->counts;
+  int* flags = cur + ntiles;
+  int* nactive = cur + 2 * ntiles;
+  SOPHT_CUDA(cudaMemsetAsync(cur, 0, sizeof(int) * (2 * ntiles + 1), st));
+  {
+    SOPHT_PROF("ib.spread_bin", st);
+    ib_bin_kernel<T, DIM><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ev, tg, lag, lag_sc, weights, nearest, n, cur,
+                                                                      w->lists, w->stragglers, flags, w->active,
+                                                                      nactive);
+    SOPHT_CHECK_LAUNCH();
+  }
+  SOPHT_PROF("ib.spread_tiles", st);
+  const int64_t blocks = ntiles < 148 * 4 ? ntiles : 148 * 4;
+  ib_tile_gather_kernel<T, DIM><<<(unsigned)blocks, ST::THREADS, 0, st>>>(ev, tg, lag, lag_sc, weights, nearest, n, cur,
+                                                                         w->lists, w->active, nactive);
+  SOPHT_CHECK_LAUNCH();
+  return SOPHT_OK;
+}
+
 // ---- host side ---------------------------------------------------------------------------------------
 static int make_eul_view(const char* fn, EulView* v, const sopht_field_t* f, int dim) {
   if (!valid_field(f, dim, dim + 1))
@@ -486,6 +786,13 @@ int sopht_ib_lagrangian_to_eulerian(int dtype, int dim, const sopht_field_t* eul
   RETURN_IF(check_transfer_args(__func__, dim, lag_grid_field, ev, interp_weights, nearest_index, &n, &lag_sc));
   if (n == 0) return SOPHT_OK;
   cudaStream_t st = as_stream(stream);
+  if (spread_tiles_enabled()) {
+#define CALL(T, D)                                                                                    \
+  return spread_tiles<T, D>(ev, (const T*)lag_grid_field->data, lag_sc, (const T*)interp_weights->data, \
+                            (const int64_t*)nearest_index->data, n, st);
+    DISPATCH_DIM_T(dim, dtype, CALL);
+#undef CALL
+  }
 #define CALL(T, D)                                                                                \
   ib_spread_kernel<T, D><<<warp_grid(n), 256, 0, st>>>(ev, (const T*)lag_grid_field->data, lag_sc, \
                                                        (const T*)interp_weights->data,            \
@@ -493,6 +800,16 @@ int sopht_ib_lagrangian_to_eulerian(int dtype, int dim, const sopht_field_t* eul
   DISPATCH_DIM_T(dim, dtype, CALL);
 #undef CALL
   SOPHT_CHECK_LAUNCH();
+  return SOPHT_OK;
+}
+
+/* running count of Lagrangian nodes that did not fit their tile's list in the privatised spread and fell back to
+ * atomics (0 for every body in the reference's examples); synchronises. */
+int sopht_ib_spread_stragglers(unsigned long long* count_out) {
+  if (!count_out) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: null pointer", __func__);
+  *count_out = 0;
+  if (g_spread_work.stragglers)
+    SOPHT_CUDA(cudaMemcpy(count_out, g_spread_work.stragglers, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return SOPHT_OK;
 }
 
@@ -562,15 +879,26 @@ int sopht_ib_virtual_boundary_forcing(int dtype, int dim, const sopht_field_t* e
   a.stiffness = stiffness;
   a.damping = damping;
   cudaStream_t st = as_stream(stream);
-  SOPHT_PROF("ib.virtual_boundary_fused", st);
-#define CALL(T, D)                                                               \
-  if (pos_dtype == SOPHT_F64)                                                    \
-    vbf_fused_kernel<T, double, D><<<warp_grid(n), 256, 0, st>>>(a, vv, fv);     \
-  else                                                                           \
-    vbf_fused_kernel<T, float, D><<<warp_grid(n), 256, 0, st>>>(a, vv, fv);
-  DISPATCH_DIM_T(dim, dtype, CALL);
+  const bool tiles = fv.p != nullptr && spread_tiles_enabled();
+  EulView fv_kernel = fv;
+  if (tiles) fv_kernel.p = nullptr;  // forces only; the spread is the privatised tile gather below
+  {
+    SOPHT_PROF("ib.virtual_boundary_fused", st);
+#define CALL(T, D)                                                                      \
+  if (pos_dtype == SOPHT_F64)                                                           \
+    vbf_fused_kernel<T, double, D><<<warp_grid(n), 256, 0, st>>>(a, vv, fv_kernel);     \
+  else                                                                                  \
+    vbf_fused_kernel<T, float, D><<<warp_grid(n), 256, 0, st>>>(a, vv, fv_kernel);
+    DISPATCH_DIM_T(dim, dtype, CALL);
 #undef CALL
-  SOPHT_CHECK_LAUNCH();
+    SOPHT_CHECK_LAUNCH();
+  }
+  if (tiles) {
+#define CALL(T, D)                                                                                         \
+  return spread_tiles<T, D>(fv, (const T*)lag_forcing->data, n, (const T*)interp_weights->data, a.nearest, n, st);
+    DISPATCH_DIM_T(dim, dtype, CALL);
+#undef CALL
+  }
   return SOPHT_OK;
 }
 

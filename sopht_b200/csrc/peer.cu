@@ -166,6 +166,7 @@ struct sopht_peer_arena {
   int nranks = 1, rank = 0;
   char* peer[MAX_RANKS] = {};
   bool opened = false;
+  bool ring = false;  // periodic z direction: rank 0's low neighbour is rank P - 1 and vice versa
   uint32_t halo_epoch = 0, barrier_epoch = 0;
   uint64_t budget_ns = 30ull * 1000000000ull;  // SOPHT_PEER_TIMEOUT_S
 };
@@ -244,6 +245,12 @@ int sopht_peer_arena_status(sopht_peer_arena_t h, int* stalled_rank_out) {
   return SOPHT_OK;
 }
 
+int sopht_peer_arena_set_periodic(sopht_peer_arena_t h, int periodic_z) {
+  if (!h) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle", __func__);
+  h->ring = periodic_z != 0;
+  return SOPHT_OK;
+}
+
 void* sopht_peer_arena_payload(sopht_peer_arena_t h) { return h ? h->base + HEADER : nullptr; }
 
 int sopht_peer_halo_exchange(sopht_peer_arena_t h, int nfields, const int64_t* payload_offsets_bytes,
@@ -270,8 +277,12 @@ int sopht_peer_halo_exchange(sopht_peer_arena_t h, int nfields, const int64_t* p
   a.nz_local = nz_local, a.halo = halo, a.plane_bytes = plane_bytes;
   a.self = h->base;
   a.rank = h->rank, a.rank_lo = h->rank - 1, a.rank_hi = h->rank + 1;
-  a.lo = h->rank > 0 ? h->peer[h->rank - 1] : nullptr;
-  a.hi = h->rank + 1 < h->nranks ? h->peer[h->rank + 1] : nullptr;
+  if (h->ring) {
+    a.rank_lo = (h->rank + h->nranks - 1) % h->nranks;
+    a.rank_hi = (h->rank + 1) % h->nranks;
+  }
+  a.lo = a.rank_lo >= 0 ? h->peer[a.rank_lo] : nullptr;
+  a.hi = a.rank_hi < h->nranks ? h->peer[a.rank_hi] : nullptr;
   a.epoch = ++h->halo_epoch;
   a.budget_ns = h->budget_ns;
   const int64_t vecs = (int64_t)halo * plane_bytes / 16 * total_comp * 2;

@@ -40,4 +40,9 @@ PoissonImpl* make_neumann_poisson(int dtype, int dim, int nz, int ny, int nx, do
 PoissonImpl* make_periodic_poisson(int dtype, int three_point_symbol, int dim, int nz, int ny, int nx, double dx,
                                    cudaStream_t st, int* rc);
 
+// fp32, 3-D, power-of-two grids: the periodic solve on the hand-written FFT pipeline (poisson_pow2.cu)
+bool periodic_pow2_eligible(int dtype, int dim, int nz, int ny, int nx);
+PoissonImpl* make_periodic_pow2_poisson(int three_point_symbol, int nz, int ny, int nx, double dx, cudaStream_t st,
+                                        int* rc);
+
 }  // namespace sopht

@@ -82,7 +82,10 @@ int sopht_poisson_periodic_create(sopht_poisson_t* handle, int dtype, int dim, i
     SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: grid sizes must be positive", __func__);
   if (!(dx > 0)) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: dx must be positive", __func__);
   int rc = SOPHT_OK;
-  PoissonImpl* impl = make_periodic_poisson(dtype, three_point_symbol, dim, nz, ny, nx, dx, as_stream(stream), &rc);
+  PoissonImpl* impl =
+      periodic_pow2_eligible(dtype, dim, nz, ny, nx)
+          ? make_periodic_pow2_poisson(three_point_symbol, nz, ny, nx, dx, as_stream(stream), &rc)
+          : make_periodic_poisson(dtype, three_point_symbol, dim, nz, ny, nx, dx, as_stream(stream), &rc);
   if (!impl) return rc;
   *handle = new sopht_poisson{dtype, dim, dim == 3 ? nz : 1, ny, nx, impl};
   return SOPHT_OK;

@@ -247,6 +247,52 @@ int launch_zconv(int L, const p2::ZParams& p, dim3 grid, cudaStream_t st) {
   return SOPHT_OK;
 }
 
+// ---- periodic box: the same kernels with nothing padded and nothing dropped (FULL), z pass with the symbol -------------
+int launch_xfwd_full(int L, const p2::XParams& p, int64_t rows, cudaStream_t st) {
+#define M(LL)                                                                                          \
+  {                                                                                                    \
+    constexpr int RX = rows_per_cta<LL>();                                                             \
+    return launch<p2::XFwd<LL, RX, true>>(p, dim3((unsigned)(rows / RX), 1, 1), "poisson.x_fwd", st);  \
+  }
+  P2_SWITCH_L(L, M)
+#undef M
+  return SOPHT_OK;
+}
+int launch_xinv_full(int L, const p2::XParams& p, int64_t rows, cudaStream_t st) {
+#define M(LL)                                                                                   \
+  {                                                                                             \
+    constexpr int RX = rows_per_cta<LL>();                                                      \
+    using K = p2::XInv<LL, RX, true>;                                                           \
+    const dim3 grid((unsigned)(rows / RX), 1, 1);                                               \
+    if (p.peer_read && stage_fits<K>(1))                                                        \
+      return launch_variant<K, auto_min_ctas<K>(), true>(p, grid, "poisson.x_inv", st, 0);      \
+    return launch<K>(p, grid, "poisson.x_inv", st);                                             \
+  }
+  P2_SWITCH_L(L, M)
+#undef M
+  return SOPHT_OK;
+}
+int launch_yfwd_full(int L, const p2::ColParams& p, dim3 grid, cudaStream_t st) {
+#define M(LL) \
+  return launch<p2::YFwd<LL, TX, true>>(p, grid, grid.y > 1 ? "poisson.y_fwd" : "poisson.y_fwd.nyquist", st);
+  P2_SWITCH_L(L, M)
+#undef M
+  return SOPHT_OK;
+}
+int launch_yinv_full(int L, const p2::ColParams& p, dim3 grid, cudaStream_t st) {
+#define M(LL) \
+  return launch<p2::YInv<LL, TX, true>>(p, grid, grid.y > 1 ? "poisson.y_inv" : "poisson.y_inv.nyquist", st);
+  P2_SWITCH_L(L, M)
+#undef M
+  return SOPHT_OK;
+}
+int launch_zsym(int L, const p2::ZSymParams& p, dim3 grid, cudaStream_t st) {
+#define M(LL) return launch<p2::ZSym<LL, TX>>(p, grid, p.nyq ? "poisson.z_sym.nyquist" : "poisson.z_sym", st);
+  P2_SWITCH_L(L, M)
+#undef M
+  return SOPHT_OK;
+}
+
 // folded spectrum: gm[(fz*(ny+1) + fy)*nx + kx] (kx < nx), gn[fz*(ny+1) + fy] (kx = nx); x2 because the
 // half-length x transform's unnormalised round trip is nx * 2ny * 2nz, half the doubled cell count.
 // gm keeps the kx range [kx0, kx0 + g_row) only (the whole spectrum on one GPU, a rank's slice otherwise)
@@ -491,11 +537,103 @@ struct Pow2Poisson : PoissonImpl {
 };
 
 
+// ---- periodic Poisson solve on the pow2 pipeline (BASELINE config 4; an extension, see poisson_neumann.cu) -----------
+// -lap(psi) = rhs on the periodic box: x real-to-half-spectrum (complex length nx/2, Hermitian split), y, z forward,
+// x norm / symbol, z, y inverse, x inverse - five kernels, every pass in place on ONE spectrum buffer (C, nz, ny, nx/2)
+// + the kx = nx/2 plane: 40 B per cell and component, no cuFFT.
+// With P > 1 ranks the same object runs the three local phases of the z-slab decomposed solve (x passes on nz / P
+// planes, y / z passes on nx / 2 / P kx bins), the transposes fused into the x kernels like SlabPow2Poisson's.
+struct PeriodicSymbols {
+  float *lz = nullptr, *ly = nullptr, *lx = nullptr;
+  float norm = 1.f;
+  ~PeriodicSymbols() {
+    cudaFree(lz);
+    cudaFree(ly);
+    cudaFree(lx);
+  }
+  static int upload(float** dst, int period, int count, double dx, bool three_point, cudaStream_t st) {
+    const double pi = 3.14159265358979323846;
+    std::vector<float> h(count);
+    for (int k = 0; k < count; ++k) {
+      if (!three_point) {
+        const int m = k <= period / 2 ? k : k - period;
+        const double w = 2.0 * pi * m / (period * dx);
+        h[k] = (float)(w * w);
+      } else {
+        const double sn = sin(pi * k / period);
+        h[k] = (float)(4.0 * sn * sn / (dx * dx));
+      }
+    }
+    SOPHT_CUDA(cudaMalloc(dst, sizeof(float) * count));
+    SOPHT_CUDA(cudaMemcpyAsync(*dst, h.data(), sizeof(float) * count, cudaMemcpyHostToDevice, st));
+    SOPHT_CUDA(cudaStreamSynchronize(st));
+    return SOPHT_OK;
+  }
+  int init(int nz, int ny, int nx, double dx, bool three_point, cudaStream_t st) {
+    int rc;
+    if ((rc = upload(&lz, nz, nz, dx, three_point, st))) return rc;
+    if ((rc = upload(&ly, ny, ny, dx, three_point, st))) return rc;
+    if ((rc = upload(&lx, nx, nx / 2 + 1, dx, three_point, st))) return rc;
+    norm = (float)(1.0 / ((double)(nx / 2) * ny * nz));  // unnormalised round trip of the three transform lengths
+    return SOPHT_OK;
+  }
+};
+
+// y / z parameter blocks on a kx slab of nxl bins of a (C, nz, ny, nxl) spectrum, in place
+p2::ColParams periodic_y_params(const p2::SlabDims& d, float2* a, const float2* tw) {
+  const int64_t nxl = d.nxl();
+  p2::ColParams yp{};
+  yp.in = a, yp.out = a;
+  yp.in_cs = 1, yp.out_cs = 1;
+  yp.log2_bz = p2::ilog2(d.nz);
+  yp.in_rs = yp.out_rs = nxl;
+  yp.in_bx = yp.out_bx = TX;
+  yp.in_by = yp.out_by = (int64_t)d.ny * nxl;
+  yp.in_bc = yp.out_bc = (int64_t)d.nz * d.ny * nxl;
+  yp.tw = tw;
+  return yp;
+}
+p2::ColParams periodic_nyquist_y_params(const p2::SlabDims& d, float2* a, const float2* tw) {  // (C, nz, ny) plane
+  p2::ColParams yn{};
+  yn.in = a, yn.out = a;
+  yn.in_rs = yn.out_rs = 1;
+  yn.in_cs = yn.out_cs = d.ny;
+  yn.in_bx = yn.out_bx = (int64_t)TX * d.ny;
+  yn.tw = tw;
+  return yn;
+}
+p2::ZSymParams periodic_z_params(const p2::SlabDims& d, float2* a, const PeriodicSymbols& sym, const float2* tw) {
+  const int64_t nxl = d.nxl();
+  p2::ZSymParams zp{};
+  zp.data = a;
+  zp.rs = (int64_t)d.ny * nxl, zp.cs = 1, zp.d_bx = TX, zp.d_by = nxl, zp.d_c = (int64_t)d.nz * d.ny * nxl;
+  zp.ncomp = d.C;
+  zp.lz = sym.lz, zp.ly = sym.ly, zp.lx = sym.lx, zp.norm = sym.norm;
+  zp.kx0 = d.rank * (int)nxl;
+  zp.nyq = 0;
+  zp.tw = tw;
+  return zp;
+}
+p2::ZSymParams periodic_nyquist_z_params(const p2::SlabDims& d, float2* a, const PeriodicSymbols& sym,
+                                         const float2* tw) {
+  p2::ZSymParams zn{};
+  zn.data = a;
+  zn.rs = d.ny, zn.cs = 1, zn.d_bx = TX, zn.d_by = 0, zn.d_c = (int64_t)d.nz * d.ny;
+  zn.ncomp = d.C;
+  zn.lz = sym.lz, zn.ly = sym.ly, zn.lx = sym.lx, zn.norm = sym.norm;
+  zn.nyq = 1;
+  zn.kx_fixed = d.nx;  // SlabDims::nx counts complex bins per row = real nx / 2: the Nyquist bin
+  zn.tw = tw;
+  return zn;
+}
+
 // ---- z-slab decomposed solve: the three local phases between the all-to-all transposes ----------------------
 // (the exchanges themselves are issued by the host layer on its process group; see SlabDims in
 // poisson_pow2_phases.cuh and sopht_b200/parallel/slab_poisson.py)
 struct SlabPow2Poisson {
-  p2::SlabDims d{};
+  p2::SlabDims d{};       // periodic mode: d.nx counts the complex bins of a row (real nx / 2)
+  bool periodic = false;  // periodic box: FULL kernels, symbol instead of G_hat, y / z passes in place
+  PeriodicSymbols sym;
   float *gm = nullptr, *gn = nullptr;  // this rank's kx slice of the folded G_hat, and the Nyquist plane's
   float* gt = nullptr;                 // tile-major copy of gm for the row-mode z pass
   float2 *twx = nullptr, *twx2 = nullptr, *twy = nullptr, *twz = nullptr;
@@ -526,6 +664,18 @@ struct SlabPow2Poisson {
     cudaFree(twz);
   }
 
+  int init_periodic(double dx, bool three_point, cudaStream_t st) {
+    periodic = true;
+    const int nz = d.nz, ny = d.ny, lx = d.nx;
+    int rc;
+    if ((rc = sym.init(nz, ny, 2 * lx, dx, three_point, st))) return rc;
+    if ((rc = Pow2Poisson::upload_twiddles(&twx, lx, lx, st))) return rc;
+    if ((rc = Pow2Poisson::upload_twiddles(&twx2, lx, 2 * lx, st))) return rc;
+    if ((rc = Pow2Poisson::upload_twiddles(&twy, ny, ny, st))) return rc;
+    if ((rc = Pow2Poisson::upload_twiddles(&twz, nz, nz, st))) return rc;
+    return SOPHT_OK;
+  }
+
   int init(double dx, const double* mz, const double* my, const double* mx, double origin, cudaStream_t st) {
     const int nz = d.nz, ny = d.ny, nx = d.nx, nxl = d.nxl();
     if (cudaMalloc(&gm, sizeof(float) * (size_t)(nz + 1) * (ny + 1) * nxl) != cudaSuccess ||
@@ -549,10 +699,11 @@ struct SlabPow2Poisson {
   }
 
   int check_local(const char* fn, const sopht_field_t* f) const {
+    const int nx_real = periodic ? 2 * d.nx : d.nx;
     if (!valid_field(f, 4, 4) || f->shape[0] != d.C || f->shape[1] != d.nzl() || f->shape[2] != d.ny ||
-        f->shape[3] != d.nx)
+        f->shape[3] != nx_real)
       SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: expected this rank's (%d, %d, %d, %d) z-slab", fn, d.C, d.nzl(), d.ny,
-                 d.nx);
+                 nx_real);
     if (!real_view_ok(f))
       SOPHT_FAIL(SOPHT_ERR_STRIDE, "%s: rows must be contiguous, 8-byte aligned, even plane/row strides", fn);
     return SOPHT_OK;
@@ -602,6 +753,7 @@ struct SlabPow2Poisson {
         p2::slab_x_params(d, reinterpret_cast<const float*>(rhs->data), nullptr, rhs->stride[0], rhs->stride[1],
                           rhs->stride[2], send ? send : xrecv, nyq_local, twx, twx2);
     if (!send) xp = p2::slab_x_params_peer(xp, d, peer_recv);
+    if (periodic) return launch_xfwd_full(d.nx, xp, (int64_t)d.C * d.nzl() * d.ny, st);
     return launch_xfwd(d.nx, xp, (int64_t)d.C * d.nzl() * d.ny, st);
   }
 
@@ -613,6 +765,19 @@ struct SlabPow2Poisson {
     if (peer && !peers_open) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: peer exchange is not open", __func__);
     if (peer) recv = xrecv;
     int rc;
+    if (periodic) {  // in place on the received kx slab; the y inverse leaves it where the reverse transpose reads it
+      const dim3 gy(nxl / TX, d.C * d.nz, 1), gyn(d.C * d.nz / TX, 1, 1);
+      if ((rc = launch_yfwd_full(d.ny, periodic_y_params(d, recv, twy), gy, st))) return rc;
+      if ((rc = launch_yfwd_full(d.ny, periodic_nyquist_y_params(d, nyq_all, twy), gyn, st))) return rc;
+      if ((rc = launch_zsym(d.nz, periodic_z_params(d, recv, sym, twz), dim3(nxl / TX, d.ny, 1), st))) return rc;
+      if ((rc = launch_zsym(d.nz, periodic_nyquist_z_params(d, nyq_all, sym, twz), dim3(d.ny / TX, 1, 1), st)))
+        return rc;
+      p2::ColParams yi = periodic_y_params(d, recv, twy);
+      if (peer) yi.out = xsend;
+      if ((rc = launch_yinv_full(d.ny, yi, gy, st))) return rc;
+      return launch_yinv_full(d.ny, periodic_nyquist_y_params(d, nyq_all, twy), gyn, st);
+    }
+    if (!work || !nyq_work) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null work buffer", __func__);
     if ((rc = launch_yfwd(LY, p2::slab_y_params(d, TX, recv, work, true, twy), dim3(nxl / TX, d.C * d.nz, 1), st)))
       return rc;
     if ((rc = launch_yfwd(LY, p2::nyquist_y_params(d, TX, nyq_all, nyq_work, true, twy),
@@ -642,8 +807,73 @@ struct SlabPow2Poisson {
     p2::XParams xp = p2::slab_x_params(d, nullptr, reinterpret_cast<float*>(sol->data), sol->stride[0],
                                        sol->stride[1], sol->stride[2], recv2, nyq_local, twx, twx2);
     if (pull) xp = p2::slab_x_params_peer(xp, d, peer_send);
+    if (periodic) return launch_xinv_full(d.nx, xp, (int64_t)d.C * d.nzl() * d.ny, st);
     return launch_xinv(d.nx, xp, (int64_t)d.C * d.nzl() * d.ny, st);
   }
+};
+
+
+struct PeriodicPow2Poisson : PoissonImpl {
+  int nz, ny, nx;  // real grid
+  bool three_point;
+  PeriodicSymbols sym;
+  float2 *A = nullptr, *nyqA = nullptr;
+  float2 *twx = nullptr, *twx2 = nullptr, *twy = nullptr, *twz = nullptr;
+  PoissonImpl* generic = nullptr;
+  double dx;
+
+  ~PeriodicPow2Poisson() override {
+    cudaFree(A);
+    cudaFree(nyqA);
+    cudaFree(twx);
+    cudaFree(twx2);
+    cudaFree(twy);
+    cudaFree(twz);
+    delete generic;
+  }
+  int init(cudaStream_t st) {
+    int rc;
+    if ((rc = sym.init(nz, ny, nx, dx, three_point, st))) return rc;
+    const size_t rows = (size_t)3 * nz * ny;
+    SOPHT_CUDA(cudaMalloc(&A, sizeof(float2) * rows * (nx / 2)));
+    SOPHT_CUDA(cudaMalloc(&nyqA, sizeof(float2) * rows));
+    if ((rc = Pow2Poisson::upload_twiddles(&twx, nx / 2, nx / 2, st))) return rc;
+    if ((rc = Pow2Poisson::upload_twiddles(&twx2, nx / 2, nx, st))) return rc;
+    if ((rc = Pow2Poisson::upload_twiddles(&twy, ny, ny, st))) return rc;
+    if ((rc = Pow2Poisson::upload_twiddles(&twz, nz, nz, st))) return rc;
+    return SOPHT_OK;
+  }
+  int solve(const sopht_field_t* sol, const sopht_field_t* rhs, cudaStream_t st) override {
+    const bool vec = sol->ndim == 4;
+    const int o = vec ? 1 : 0;
+    const int C = vec ? (int)sol->shape[0] : 1;
+    if (C > 3 || !Pow2Poisson::view_ok(sol, o) || !Pow2Poisson::view_ok(rhs, o)) {
+      if (!generic) {
+        int rc = SOPHT_OK;
+        generic = make_periodic_poisson(SOPHT_F32, three_point, 3, nz, ny, nx, dx, st, &rc);
+        if (!generic) return rc;
+      }
+      return generic->solve(sol, rhs, st);
+    }
+    const int LX = nx / 2;
+    const int64_t rows = (int64_t)C * nz * ny;
+    const p2::SlabDims d{C, nz, ny, LX, 1, 0};
+    int rc;
+    p2::XParams xp = p2::slab_x_params(d, reinterpret_cast<const float*>(rhs->data), nullptr,
+                                       vec ? rhs->stride[0] : 0, rhs->stride[o], rhs->stride[o + 1], A, nyqA, twx,
+                                       twx2);
+    if ((rc = launch_xfwd_full(LX, xp, rows, st))) return rc;
+    if ((rc = launch_yfwd_full(ny, periodic_y_params(d, A, twy), dim3(LX / TX, C * nz, 1), st))) return rc;
+    if ((rc = launch_yfwd_full(ny, periodic_nyquist_y_params(d, nyqA, twy), dim3(C * nz / TX, 1, 1), st))) return rc;
+    if ((rc = launch_zsym(nz, periodic_z_params(d, A, sym, twz), dim3(LX / TX, ny, 1), st))) return rc;
+    if ((rc = launch_zsym(nz, periodic_nyquist_z_params(d, nyqA, sym, twz), dim3(ny / TX, 1, 1), st))) return rc;
+    if ((rc = launch_yinv_full(ny, periodic_y_params(d, A, twy), dim3(LX / TX, C * nz, 1), st))) return rc;
+    if ((rc = launch_yinv_full(ny, periodic_nyquist_y_params(d, nyqA, twy), dim3(C * nz / TX, 1, 1), st))) return rc;
+    xp = p2::slab_x_params(d, nullptr, reinterpret_cast<float*>(sol->data), vec ? sol->stride[0] : 0, sol->stride[o],
+                           sol->stride[o + 1], A, nyqA, twx, twx2);
+    return launch_xinv_full(LX, xp, rows, st);
+  }
+  const char* path_name() const override { return three_point ? "periodic_pow2_three_point" : "periodic_pow2_spectral"; }
 };
 
 }  // namespace
@@ -660,6 +890,23 @@ PoissonImpl* make_pow2_poisson(int nz, int ny, int nx, double dx, const double* 
   p->mz.assign(mz, mz + 2 * nz);
   p->my.assign(my, my + 2 * ny);
   p->mx.assign(mx, mx + 2 * nx);
+  *rc = p->init(st);
+  if (*rc) {
+    delete p;
+    return nullptr;
+  }
+  return p;
+}
+
+bool periodic_pow2_eligible(int dtype, int dim, int nz, int ny, int nx) {
+  static const int off = env_int("SOPHT_PERIODIC_FORCE_CUFFT", 0);
+  return !off && dtype == SOPHT_F32 && dim == 3 && is_pow2(nx) && is_pow2(ny) && is_pow2(nz) && nx >= 32 &&
+         nx <= 4096 && ny >= 16 && ny <= 2048 && nz >= 16 && nz <= 2048;
+}
+PoissonImpl* make_periodic_pow2_poisson(int three_point_symbol, int nz, int ny, int nx, double dx, cudaStream_t st,
+                                        int* rc) {
+  auto* p = new PeriodicPow2Poisson();
+  p->nz = nz, p->ny = ny, p->nx = nx, p->dx = dx, p->three_point = three_point_symbol != 0;
   *rc = p->init(st);
   if (*rc) {
     delete p;
@@ -703,6 +950,31 @@ int sopht_poisson_slab_create(sopht_poisson_slab_t* handle, int ncomp, int nz, i
   return SOPHT_OK;
 }
 
+int sopht_poisson_slab_create_periodic(sopht_poisson_slab_t* handle, int ncomp, int nz, int ny, int nx, int nranks,
+                                       int rank, double dx, int three_point_symbol, void* stream) {
+  if (!handle) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: null handle pointer", __func__);
+  if (!periodic_pow2_eligible(SOPHT_F32, 3, nz, ny, nx))
+    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: the slab solver needs a power-of-two fp32 3-D grid", __func__);
+  if (ncomp < 1 || ncomp > 3) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: 1..3 components", __func__);
+  if (nranks < 1 || (nranks & (nranks - 1)) || rank < 0 || rank >= nranks)
+    SOPHT_FAIL(SOPHT_ERR_ARG, "%s: nranks must be a power of two and 0 <= rank < nranks", __func__);
+  const int lx = nx / 2;
+  if (nz % nranks || lx % nranks || (lx / nranks) % TX || ((int64_t)ncomp * (nz / nranks) * ny) % 32 ||
+      (ncomp * nz) % TX || ny % TX)
+    SOPHT_FAIL(SOPHT_ERR_SHAPE, "%s: nz/nranks planes and nx/2/nranks >= %d kx bins per rank are required", __func__,
+               TX);
+  if (!(dx > 0)) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: dx must be positive", __func__);
+  auto* h = new sopht_poisson_slab();
+  h->impl.d = p2::SlabDims{ncomp, nz, ny, lx, nranks, rank};
+  const int rc = h->impl.init_periodic(dx, three_point_symbol != 0, as_stream(stream));
+  if (rc) {
+    delete h;
+    return rc;
+  }
+  *handle = h;
+  return SOPHT_OK;
+}
+
 int sopht_poisson_slab_forward_x(sopht_poisson_slab_t h, const sopht_field_t* rhs_field, void* send_buffer,
                                  void* nyquist_local, void* stream) {
   if (!h || !nyquist_local) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
@@ -712,8 +984,7 @@ int sopht_poisson_slab_forward_x(sopht_poisson_slab_t h, const sopht_field_t* rh
 
 int sopht_poisson_slab_yz(sopht_poisson_slab_t h, void* recv_buffer, void* nyquist_all, void* work_buffer,
                           void* nyquist_work, void* stream) {
-  if (!h || !nyquist_all || !work_buffer || !nyquist_work)
-    SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
+  if (!h || !nyquist_all) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
   return h->impl.yz(reinterpret_cast<float2*>(recv_buffer), reinterpret_cast<float2*>(nyquist_all),
                     reinterpret_cast<float2*>(work_buffer), reinterpret_cast<float2*>(nyquist_work),
                     as_stream(stream));

@@ -145,7 +145,7 @@ struct L2Prefetch {
 #define SOPHT_P2_L2_PREFETCH 0
 #endif
 
-template <int L, int TX>
+template <int L, int TX, bool FULL = false>
 struct YFwd {
   static constexpr int SYNC_THREADS = Cfg<L>::T * TX;  // whole CTA (narrower groups: see profiles/r01_poisson_layout_experiments.txt)
   using Params = ColParams;
@@ -154,7 +154,7 @@ struct YFwd {
   static constexpr int NITER = 1;
   static constexpr int SMEM_ELEMS = ColAcc<L, TX>::ROWS * TX;
   static constexpr int EXTRA_ELEMS = TwTable<L>::SIZE;
-  static constexpr int STAGE_ELEMS = (L / 2) * TX;
+  static constexpr int STAGE_ELEMS = (FULL ? L : L / 2) * TX;
   static constexpr bool STAGE_SHARED = false;  // a thread reads back only what it copied itself
   static constexpr bool WANT_STAGE = Cfg<L>::E >= 32;
   static constexpr bool DEFAULT_TWO_CTAS = true, DEFAULT_STAGED = false;
@@ -165,7 +165,7 @@ struct YFwd {
   FFT_HD static void prefetch(const Params& p, int bx, int by, int, int tid, float2* stage) {
     const int col = tid % TX, t = tid / TX;
     StageCopy<TX> cp{stage + col, p.in_plane(by) + bx * p.in_bx + col * p.in_cs, (unsigned)p.in_rs};
-    fft::fwd_first_elems<L>(t, cp);
+    fft::fwd_first_elems_x<L, FULL>(t, cp);
   }
   // unstaged variants: the next tile's first-phase inputs are pulled into L2 while this tile is transformed
   static constexpr bool L2_PREFETCH = SOPHT_P2_L2_PREFETCH;
@@ -173,7 +173,7 @@ struct YFwd {
     const int col = tid % TX, t = tid / TX;
     L2Prefetch pf{p.in_plane(by) + bx * p.in_bx + col * p.in_cs, (unsigned)p.in_rs,
                   (col & 3) == 0 && p.in_cs == 1};
-    fft::fwd_first_elems<L>(t, pf);
+    fft::fwd_first_elems_x<L, FULL>(t, pf);
   }
   template <int P>
   FFT_HD static void phase(const Params& p, int bx, int by, int, int tid, float2* smem, const float2* stage) {
@@ -182,10 +182,10 @@ struct YFwd {
     const float2* tw = smem + SMEM_ELEMS;
     if (P == 0) {
       if (stage) {
-        fft::fwd_first<L>(StageLoad<TX>{stage + col}, sm, t, tw);
+        fft::fwd_first_x<L, FULL>(StageLoad<TX>{stage + col}, sm, t, tw);
       } else {
         GlobalLoad ld{p.in_plane(by) + bx * p.in_bx + col * p.in_cs, (unsigned)p.in_rs};
-        fft::fwd_first<L>(ld, sm, t, tw);
+        fft::fwd_first_x<L, FULL>(ld, sm, t, tw);
       }
     } else if (P == NPHASE - 1) {
       GlobalStoreIdx st{p.out_plane(by) + bx * p.out_bx + col * p.out_cs, (unsigned)p.out_rs};
@@ -196,7 +196,7 @@ struct YFwd {
   }
 };
 
-template <int L, int TX>
+template <int L, int TX, bool FULL = false>
 struct YInv {
   static constexpr int SYNC_THREADS = Cfg<L>::T * TX;  // whole CTA (narrower groups: see profiles/r01_poisson_layout_experiments.txt)
   using Params = ColParams;
@@ -239,7 +239,7 @@ struct YInv {
       }
     } else if (P == NPHASE - 1) {
       GlobalStore st{p.out_plane(by) + bx * p.out_bx + col * p.out_cs, (unsigned)p.out_rs};
-      fft::inv_last<L>(sm, t, tw, st);
+      fft::inv_last_x<L, FULL>(sm, t, tw, st);
     } else {
       fft::inv_mid<L>(sm, t, tw);
     }
@@ -344,6 +344,92 @@ struct ZConv {
   }
 };
 
+// ---- Z, periodic box: forward, x 1 / symbol, inverse - in place, nothing padded, nothing dropped ------------------------
+// spectrum *= norm / (lx[kx] + ly[ky] + lz[kz]) (three 1-D tables: (2 pi m / L)^2 or the three-point symbol), mean mode -> 0
+struct ZSymParams {
+  float2* data;            // tile origin = data + bx*d_bx + by*d_by + c*d_c, rows rs apart, columns cs apart
+  int64_t rs, cs, d_bx, d_by, d_c;
+  int ncomp;
+  const float *lz, *ly, *lx;
+  float norm;
+  int kx0;                 // global kx of column 0 of tile bx = 0 (a rank's kx slab)
+  int nyq;                 // 0: columns are kx (ky = by); 1: columns are ky (ky = bx*TX + col), kx = kx_fixed
+  int kx_fixed;
+  const float2* tw;
+};
+template <int L>
+struct SymCol {
+  const float* lz;  // shared-memory copy, L entries
+  float lyx, norm;
+  FFT_HD float operator()(int blk, int klast) const {
+    const int kz = fft::spectrum_index<L>(blk, klast);
+    const float lam = lz[kz] + lyx;
+    return lam > 0.f ? norm / lam : 0.f;
+  }
+};
+template <int L, int TX>
+struct ZSym {
+  static constexpr int SYNC_THREADS = Cfg<L>::T * TX;
+  using Params = ZSymParams;
+  static constexpr int THREADS = Cfg<L>::T * TX;
+  static constexpr int NP = Cfg<L>::NP;
+  static constexpr int NPHASE = 2 * NP - 1;
+  static constexpr int NITER = 0;
+  static constexpr int SMEM_ELEMS = ColAcc<L, TX>::ROWS * TX;
+  static constexpr int EXTRA_ELEMS = TwTable<L>::SIZE + L / 2;  // twiddles, lz (L floats)
+  static constexpr int STAGE_ELEMS = L * TX;
+  static constexpr bool STAGE_SHARED = false;
+  static constexpr bool WANT_STAGE = Cfg<L>::E >= 32;
+  static constexpr bool DEFAULT_TWO_CTAS = true, DEFAULT_STAGED = false;
+  static constexpr bool L2_PREFETCH = SOPHT_P2_L2_PREFETCH;
+  FFT_HD static int niter(const Params& p) { return p.ncomp; }
+  FFT_HD static void init(const Params& p, int tid, float2* smem) {
+    TwTable<L>::template fill<THREADS>(smem + SMEM_ELEMS, p.tw, tid);
+    float* lz = reinterpret_cast<float*>(smem + SMEM_ELEMS + TwTable<L>::SIZE);
+    for (int i = tid; i < L; i += THREADS) lz[i] = p.lz[i];
+  }
+  FFT_HD static const float2* col_ptr(const Params& p, int bx, int by, int c, int col) {
+    return p.data + bx * p.d_bx + by * p.d_by + c * p.d_c + col * p.cs;
+  }
+  FFT_HD static void prefetch(const Params& p, int bx, int by, int c, int tid, float2* stage) {
+    const int col = tid % TX, t = tid / TX;
+    StageCopy<TX> cp{stage + col, col_ptr(p, bx, by, c, col), (unsigned)p.rs};
+    fft::fwd_first_elems_x<L, true>(t, cp);
+  }
+  FFT_HD static void l2_prefetch(const Params& p, int bx, int by, int c, int tid) {
+    const int col = tid % TX, t = tid / TX;
+    L2Prefetch pf{col_ptr(p, bx, by, c, col), (unsigned)p.rs, (col & 3) == 0 && p.cs == 1};
+    fft::fwd_first_elems_x<L, true>(t, pf);
+  }
+  template <int P>
+  FFT_HD static void phase(const Params& p, int bx, int by, int c, int tid, float2* smem, const float2* stage) {
+    const int col = tid % TX, t = tid / TX;
+    ColAcc<L, TX> sm{smem, col};
+    float2* base = const_cast<float2*>(col_ptr(p, bx, by, c, col));
+    const float2* tw = smem + SMEM_ELEMS;
+    const float* lz = reinterpret_cast<const float*>(smem + SMEM_ELEMS + TwTable<L>::SIZE);
+    if (P == 0) {
+      if (stage) {
+        fft::fwd_first_x<L, true>(StageLoad<TX>{stage + col}, sm, t, tw);
+      } else {
+        GlobalLoad ld{base, (unsigned)p.rs};
+        fft::fwd_first_x<L, true>(ld, sm, t, tw);
+      }
+    } else if (P == NP - 1) {
+      const int ky = p.nyq ? bx * TX + col : by;
+      const int kx = p.nyq ? p.kx_fixed : p.kx0 + bx * TX + col;
+      fft::fwd_last_mul_inv_first<L>(sm, t, SymCol<L>{lz, p.ly[ky] + p.lx[kx], p.norm});
+    } else if (P == NPHASE - 1) {
+      GlobalStore st{base, (unsigned)p.rs};
+      fft::inv_last_x<L, true>(sm, t, tw, st);
+    } else if (P < NP - 1) {
+      fft::fwd_mid<L>(sm, t, tw);
+    } else {
+      fft::inv_mid<L>(sm, t, tw);
+    }
+  }
+};
+
 // ---- X forward: real rows -> half spectrum (row mode) -----------------------------------------------------
 struct XParams {
   const float* real_in;    // XFwd: rhs;  element (c,z,y,x) at c*sc + z*sz + y*sy + x
@@ -401,7 +487,7 @@ struct RowStore {
   FFT_HD void operator()(int e, float2 v) const { p[e] = v; }
 };
 
-template <int L, int RX>
+template <int L, int RX, bool FULL = false>
 struct XFwd {
   using Params = XParams;
   static constexpr int T = Cfg<L>::T;
@@ -414,7 +500,7 @@ struct XFwd {
   static constexpr int NITER = 1;
   static constexpr int SMEM_ELEMS = RowAcc<L>::PITCH * RX;
   static constexpr int EXTRA_ELEMS = TwTable<L>::SIZE + L;  // twiddle table, tw2
-  static constexpr int STAGE_ELEMS = (L / 2) * RX;
+  static constexpr int STAGE_ELEMS = (FULL ? L : L / 2) * RX;
   static constexpr bool STAGE_SHARED = false;
   static constexpr bool WANT_STAGE = false;
   static constexpr bool DEFAULT_TWO_CTAS = false, DEFAULT_STAGED = false;
@@ -432,8 +518,8 @@ struct XFwd {
   }
   FFT_HD static void prefetch(const Params& p, int bx, int, int, int tid, float2* stage) {
     const int t = tid % T, r = tid / T;
-    StageCopy<1> cp{stage + r * (L / 2), row_ptr(p, p.real_in, (int64_t)bx * RX + r), 1u};
-    fft::fwd_first_elems<L>(t, cp);
+    StageCopy<1> cp{stage + r * (FULL ? L : L / 2), row_ptr(p, p.real_in, (int64_t)bx * RX + r), 1u};
+    fft::fwd_first_elems_x<L, FULL>(t, cp);
   }
   // next tile's real rows (L / 2 float2 = L / 8 sectors per row, spread over the row's T threads);
   // measured: 2-5 % slower with it (contiguous rows: the hardware already streams them), so off
@@ -441,7 +527,7 @@ struct XFwd {
   FFT_HD static void l2_prefetch(const Params& p, int bx, int, int, int tid) {
     const int t = tid % T, r = tid / T;
     const float2* row = row_ptr(p, p.real_in, (int64_t)bx * RX + r);
-    for (int s = t; s < L / 8; s += T) fft::prefetch_l2(row + s * 4);
+    for (int s = t; s < (FULL ? L / 4 : L / 8); s += T) fft::prefetch_l2(row + s * 4);
   }
   template <int P>
   FFT_HD static void phase(const Params& p, int bx, int, int, int tid, float2* smem, const float2* stage) {
@@ -452,10 +538,10 @@ struct XFwd {
     const float2* tw2 = smem + SMEM_ELEMS + TwTable<L>::SIZE;
     if (P == 0) {
       if (stage) {
-        fft::fwd_first<L>(StageLoad<1>{stage + r * (L / 2)}, sm, t, tw);
+        fft::fwd_first_x<L, FULL>(StageLoad<1>{stage + r * (FULL ? L : L / 2)}, sm, t, tw);
       } else {
         RowLoad ld{row_ptr(p, p.real_in, row)};
-        fft::fwd_first<L>(ld, sm, t, tw);
+        fft::fwd_first_x<L, FULL>(ld, sm, t, tw);
       }
     } else if (P == NP - 1) {
       fft::fwd_last<L>(sm, t, InPlaceSink<L>{sm});
@@ -489,7 +575,7 @@ struct XFwd {
   }
 };
 
-template <int L, int RX>
+template <int L, int RX, bool FULL = false>
 struct XInv {
   using Params = XParams;
   static constexpr int T = Cfg<L>::T;
@@ -505,7 +591,7 @@ struct XInv {
   static constexpr bool WANT_STAGE = false;
   static constexpr bool DEFAULT_TWO_CTAS = false, DEFAULT_STAGED = false;
   FFT_HD static int niter(const Params&) { return 1; }
-  FFT_HD static void init(const Params& p, int tid, float2* smem) { XFwd<L, RX>::init(p, tid, smem); }
+  FFT_HD static void init(const Params& p, int tid, float2* smem) { XFwd<L, RX, FULL>::init(p, tid, smem); }
   FFT_HD static void prefetch(const Params& p, int bx, int, int, int tid, float2* stage) {
     const int t = tid % T, r = tid / T;
     const int64_t row = (int64_t)bx * RX + r;
@@ -564,8 +650,8 @@ struct XInv {
     } else if (P == 1) {
       fft::inv_first<L>(InPlaceSrc<L>{sm}, sm, t);
     } else if (P == NPHASE - 1) {
-      RowStore st{const_cast<float2*>(XFwd<L, RX>::row_ptr(p, p.real_out, row))};
-      fft::inv_last<L>(sm, t, tw, st);
+      RowStore st{const_cast<float2*>(XFwd<L, RX, FULL>::row_ptr(p, p.real_out, row))};
+      fft::inv_last_x<L, FULL>(sm, t, tw, st);
     } else {
       fft::inv_mid<L>(sm, t, tw);
     }

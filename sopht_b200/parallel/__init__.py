@@ -5,14 +5,16 @@ single-GPU path uses."""
 
 from .peer import PeerArena
 from .slab import HaloExchanger, SlabPartition, exchange_halos
-from .slab_flow import SlabUnboundedNavierStokesFlowSimulator3D
+from .slab_flow import SlabPeriodicNavierStokesFlowSimulator3D, SlabUnboundedNavierStokesFlowSimulator3D
 from .slab_ib import SlabVirtualBoundaryForcing
-from .slab_poisson import SlabTransposePlan, SlabUnboundedPoissonSolver3D
+from .slab_poisson import SlabPeriodicPoissonSolver3D, SlabTransposePlan, SlabUnboundedPoissonSolver3D
 
 __all__ = [
     "HaloExchanger",
     "PeerArena",
     "SlabPartition",
+    "SlabPeriodicNavierStokesFlowSimulator3D",
+    "SlabPeriodicPoissonSolver3D",
     "SlabTransposePlan",
     "SlabUnboundedNavierStokesFlowSimulator3D",
     "SlabUnboundedPoissonSolver3D",

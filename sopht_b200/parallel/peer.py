@@ -25,7 +25,7 @@ class _DeviceSpan:
 
 
 class PeerArena:
-    def __init__(self, payload_bytes: int, group=None) -> None:
+    def __init__(self, payload_bytes: int, group=None, periodic_z: bool = False) -> None:
         if not torch.cuda.is_available():
             msg = "the peer arena needs CUDA devices (no CPU fallback)"
             raise _lib.SophtLibraryError(msg)
@@ -47,6 +47,8 @@ class PeerArena:
             buf = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
             _lib.check(lib.sopht_peer_arena_open(handle, ctypes.cast(buf, ctypes.c_void_p)))
             dist.barrier(group=group)
+        if periodic_z:  # the ranks form a ring: halo exchange of a periodic box
+            _lib.check(lib.sopht_peer_arena_set_periodic(handle, 1))
         self._base = int(lib.sopht_peer_arena_payload(handle))
         self._size = int(payload_bytes)
         self._used = 0

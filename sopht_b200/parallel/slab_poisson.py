@@ -116,22 +116,9 @@ class SlabUnboundedPoissonSolver3D:
             raise _lib.SophtLibraryError(msg)
         device = torch.device("cuda", torch.cuda.current_device())
         lib = _lib.load()
-        mx = _reflected_axis(self.x_range, self.dx, grid_size_x, real_t)
-        my = _reflected_axis(self.y_range, self.dx, grid_size_y, real_t)
-        mz = _reflected_axis(self.z_range, self.dx, grid_size_z, real_t)
-        origin = real_t(1 / (4 * np.pi * self.dx))  # UnboundedPoissonSolverPYFFTW3D.py:79
-        handle = ctypes.c_void_p()
-        _lib.check(lib.sopht_poisson_slab_create(
-            ctypes.byref(handle), n_components, grid_size_z, grid_size_y, grid_size_x, world, rank,
-            float(self.dx), _lib.double_array(mz), _lib.double_array(my), _lib.double_array(mx),
-            float(origin), _lib.current_stream()))
-        self._handle = handle
-        self.path = "pow2-slab"
-        self.plan = SlabTransposePlan(self.part, n_components, torch.float32, device, group)
         nz, ny = grid_size_z, grid_size_y
-        # two halves: the x-major spectrum the y forward pass writes, the kx-tile-major one the z pass writes
-        self._work = torch.zeros((2, n_components, nz, 2 * ny, self.plan.nxl, 2), dtype=torch.float32, device=device)
-        self._nyq_work = torch.zeros((n_components, nz, 2 * ny, 2), dtype=torch.float32, device=device)
+        self._handle = self._create_handle(lib, n_components, world, rank)
+        self._make_buffers(n_components, device, group)
         # transposes fused into the kernels over NVLink peer memory (default on >1 rank; SOPHT_SLAB_PEER=0 or
         # peer_exchange=False keeps the NCCL all-to-all path)
         if peer_exchange is None:
@@ -140,11 +127,32 @@ class SlabUnboundedPoissonSolver3D:
         self._peer_arena = peer_arena  # its device-side barrier replaces the all-reduce between y inverse and x inverse
         if self.peer_exchange:
             self._open_peer_exchange(lib, world, device, group)
-            self.path = "pow2-slab-peer"
+            self.path += "-peer"
             nzl = self.plan.nzl
             self._nyq_gather = torch.zeros((world, n_components, nzl, ny, 2), dtype=torch.float32, device=device)
             self._barrier_flag = torch.zeros(1, dtype=torch.float32, device=device)
             self.plan.send = self.plan.recv = None  # exchange buffers live in the library
+
+    def _create_handle(self, lib, n_components: int, world: int, rank: int) -> ctypes.c_void_p:
+        real_t = self.real_t
+        mx = _reflected_axis(self.x_range, self.dx, self.grid_size_x, real_t)
+        my = _reflected_axis(self.y_range, self.dx, self.grid_size_y, real_t)
+        mz = _reflected_axis(self.z_range, self.dx, self.grid_size_z, real_t)
+        origin = real_t(1 / (4 * np.pi * self.dx))  # UnboundedPoissonSolverPYFFTW3D.py:79
+        handle = ctypes.c_void_p()
+        _lib.check(lib.sopht_poisson_slab_create(
+            ctypes.byref(handle), n_components, self.grid_size_z, self.grid_size_y, self.grid_size_x, world, rank,
+            float(self.dx), _lib.double_array(mz), _lib.double_array(my), _lib.double_array(mx),
+            float(origin), _lib.current_stream()))
+        self.path = "pow2-slab"
+        return handle
+
+    def _make_buffers(self, n_components: int, device, group) -> None:
+        nz, ny = self.grid_size_z, self.grid_size_y
+        self.plan = SlabTransposePlan(self.part, n_components, torch.float32, device, group)
+        # two halves: the x-major spectrum the y forward pass writes, the kx-tile-major one the z pass writes
+        self._work = torch.zeros((2, n_components, nz, 2 * ny, self.plan.nxl, 2), dtype=torch.float32, device=device)
+        self._nyq_work = torch.zeros((n_components, nz, 2 * ny, 2), dtype=torch.float32, device=device)
 
     def _open_peer_exchange(self, lib, world: int, device, group) -> None:
         mine = (ctypes.c_ubyte * 128)()
@@ -180,7 +188,8 @@ class SlabUnboundedPoissonSolver3D:
         def middle() -> None:
             _lib.check(lib.sopht_poisson_slab_yz(
                 self._handle, p(plan.recv.data_ptr()), p(plan.nyq_all.data_ptr()),
-                p(self._work.data_ptr()), p(self._nyq_work.data_ptr()), st))
+                p(self._work.data_ptr()) if self._work is not None else None,
+                p(self._nyq_work.data_ptr()) if self._nyq_work is not None else None, st))
 
         def inverse_x() -> None:
             _lib.check(lib.sopht_poisson_slab_inverse_x(
@@ -199,8 +208,9 @@ class SlabUnboundedPoissonSolver3D:
             dist.all_gather_into_tensor(self._nyq_gather, plan.nyq_local, group=plan.group)
             plan.nyq_all.view(plan.ncomp, part.world_size, nzl, -1, 2).copy_(self._nyq_gather.transpose(0, 1))
         _lib.check(lib.sopht_poisson_slab_yz(
-            self._handle, None, p(plan.nyq_all.data_ptr()), p(self._work.data_ptr()),
-            p(self._nyq_work.data_ptr()), st))
+            self._handle, None, p(plan.nyq_all.data_ptr()),
+            p(self._work.data_ptr()) if self._work is not None else None,
+            p(self._nyq_work.data_ptr()) if self._nyq_work is not None else None, st))
         if self._peer_arena is not None:
             self._peer_arena.barrier()
         else:
@@ -209,3 +219,36 @@ class SlabUnboundedPoissonSolver3D:
         plan.nyq_local.copy_(plan.nyq_all[:, part.rank * nzl : (part.rank + 1) * nzl])
         _lib.check(lib.sopht_poisson_slab_inverse_x(
             self._handle, ctypes.byref(fs), None, p(plan.nyq_local.data_ptr()), st))
+
+
+class SlabPeriodicPoissonSolver3D(SlabUnboundedPoissonSolver3D):
+    """-del^2(solution) = rhs on the PERIODIC global box (mean mode dropped), z-slab decomposed: the distributed
+    counterpart of PeriodicPoissonSolver3D (an extension for BASELINE config 4 - the reference has nothing periodic,
+    parity is against the numpy restatement and analytic modes). Same choreography as the unbounded solver; rows carry
+    nx / 2 complex bins (+ the Nyquist plane), the y and z passes run in place on the received kx slab."""
+
+    def __init__(self, grid_size_z: int, grid_size_y: int, grid_size_x: int, x_range: float = 1.0,
+                 num_threads: int = 1, real_t: type = np.float32, n_components: int = 3, group: Any = None,
+                 peer_exchange: bool | None = None, peer_arena: Any = None, symbol: str = "spectral") -> None:
+        if symbol not in ("spectral", "three_point"):
+            msg = "symbol must be 'spectral' or 'three_point'"
+            raise ValueError(msg)
+        self.symbol = symbol
+        super().__init__(grid_size_z, grid_size_y, grid_size_x, x_range=x_range, num_threads=num_threads,
+                         real_t=real_t, n_components=n_components, group=group, peer_exchange=peer_exchange,
+                         peer_arena=peer_arena)
+
+    def _create_handle(self, lib, n_components: int, world: int, rank: int) -> ctypes.c_void_p:
+        handle = ctypes.c_void_p()
+        _lib.check(lib.sopht_poisson_slab_create_periodic(
+            ctypes.byref(handle), n_components, self.grid_size_z, self.grid_size_y, self.grid_size_x, world, rank,
+            float(self.dx), int(self.symbol == "three_point"), _lib.current_stream()))
+        self.path = "periodic-pow2-slab"
+        return handle
+
+    def _make_buffers(self, n_components: int, device, group) -> None:
+        # the spectrum has nx / 2 bins per row: the transposes move (C, P, nz/P, ny, nx/2/P)
+        spec_part = SlabPartition((self.grid_size_z, self.grid_size_y, self.grid_size_x // 2), self.part.world_size,
+                                  self.part.rank)
+        self.plan = SlabTransposePlan(spec_part, n_components, torch.float32, device, group)
+        self._work = self._nyq_work = None  # y / z passes run in place

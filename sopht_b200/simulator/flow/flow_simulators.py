@@ -92,3 +92,33 @@ class FlowSimulator:
         """Final simulator time step."""
         self._flow_time_step(dt=dt, **kwargs)
         self._update_simulator_time(dt=dt)
+
+    def graph_time_step(self, dt: float, before=None, extra_state=(), **kwargs):
+        """The time step with FIXED dt (and free stream ...) captured into a CUDA graph: returns a callable that
+        replays it with one launch and advances `time`. `before` (optional callable, e.g. the immersed-body
+        interaction of the coupled step) is captured in front of the flow step; `extra_state` lists tensors `before`
+        updates in place. For the small grids of BASELINE configs[0-2], where the 15-40 launches of a step are issued
+        more slowly than the device executes them. Not part of the reference API (it has no device)."""
+        from sopht_b200 import _lib
+
+        def body() -> None:
+            if before is not None:
+                before()
+            self._flow_time_step(dt=dt, **kwargs)
+
+        state = [getattr(self, n) for n in ("vorticity_field", "velocity_field", "eul_grid_forcing_field",
+                                            "primary_field", "stream_func_field", "buffer_vector_field")
+                 if isinstance(getattr(self, n, None), torch.Tensor)]
+        absmax = getattr(self, "_vel_absmax", None)
+        if isinstance(absmax, torch.Tensor):
+            state.append(absmax)
+        graph = _lib.StepGraph(body, list(state) + list(extra_state))
+
+        def replay() -> None:
+            graph()
+            if hasattr(self, "_vel_absmax_version"):
+                self._vel_absmax_version = (self.velocity_field.data_ptr(), self.velocity_field._version)
+            self._update_simulator_time(dt=dt)
+
+        replay.graph = graph
+        return replay

@@ -368,6 +368,23 @@ int sopht_poisson_slab_inverse_x(sopht_poisson_slab_t handle, const sopht_field_
  * separates the phases with a barrier. */
 int sopht_poisson_slab_enable_peer_exchange(sopht_poisson_slab_t handle, unsigned char *ipc_handles_out);
 int sopht_poisson_slab_open_peers(sopht_poisson_slab_t handle, const unsigned char *all_ipc_handles);
+/* Pipelined variant of the peer-exchange solve (needs enable_peer_exchange / open_peers): every call works on ONE
+ * component, the transposes are cudaMemcpy2DAsync copies (copy engines, no SM) between the ranks' exchange blocks, so
+ * the host layer can run the transposes of one component under the y / z passes of another:
+ *   pipe_forward_x(c)  -> pipe_transpose(c, 0, streams)  -> [all ranks: barrier] -> pipe_yz(c)
+ *   -> pipe_transpose(c, 1, streams) -> [barrier] -> pipe_inverse_x(c)
+ * pipe_transpose enqueues this rank's P copies (kx chunk q of its rows -> rank q; backward: z block p of its kx slab ->
+ * rank p) round robin on `streams` (cudaStream_t array); forward it also delivers nyquist_local (C, nz/P, ny) into every
+ * rank's copy of the Nyquist plane, which lives inside the exchange block. work_buffer (unbounded solve only):
+ * 2 x (nz, 2 ny, nx/P) complex64, nyquist_work (nz, 2 ny). */
+int sopht_poisson_slab_pipe_forward_x(sopht_poisson_slab_t handle, const sopht_field_t *rhs_field, int component,
+                                      void *nyquist_local, void *stream);
+int sopht_poisson_slab_pipe_transpose(sopht_poisson_slab_t handle, int component, int backward, void **streams,
+                                      int nstreams, const void *nyquist_local);
+int sopht_poisson_slab_pipe_yz(sopht_poisson_slab_t handle, int component, void *work_buffer, void *nyquist_work,
+                               void *stream);
+int sopht_poisson_slab_pipe_inverse_x(sopht_poisson_slab_t handle, const sopht_field_t *solution_field, int component,
+                                      void *nyquist_local, void *stream);
 int sopht_poisson_slab_destroy(sopht_poisson_slab_t handle);
 
 /* ------------------------------------------------------------------------ */
@@ -546,6 +563,15 @@ int sopht_ns3d_advect_rotational(int dtype, const sopht_field_t *out_vorticity_f
  * ref: navier_stokes_flow_simulators.py:466-471, :498; stencil_ops_3d/diffusion_timestep_3d.py:12-80 */
 int sopht_ns3d_diffuse(int dtype, const sopht_field_t *out_field, const sopht_field_t *field,
                        double nu_dt_by_dx2, const sopht_field_t *zero_field, void *stream);
+
+/* The same pass followed by the sine penalisation of the boundary ring for the default width 2, where the reference's
+ * copy-and-scale reduces to a per-axis factor: ramp_{x,y,z} are DEVICE arrays of nx / ny / nz factors of `dtype`
+ * ({0, sin(pi/4), 1, ..., 1, sin(pi/4), 0}), applied in the reference's order x, y, z. Needs 16-byte aligned unit-stride
+ * rows (otherwise SOPHT_ERR_STRIDE: call sopht_ns3d_diffuse + sopht_penalise_field_boundary_3d).
+ * ref: navier_stokes_flow_simulators.py:466-478; stencil_ops_3d/penalise_field_boundary_3d.py:182-208 */
+int sopht_ns3d_diffuse_penalise(int dtype, const sopht_field_t *out_field, const sopht_field_t *field,
+                                double nu_dt_by_dx2, const sopht_field_t *zero_field, const void *ramp_x,
+                                const void *ramp_y, const void *ramp_z, void *stream);
 
 /* velocity = prefactor * curl_c(psi) (ring <- 0) + free_stream_velocity (HOST array of 3, may be NULL);
  * if max_abs_sum_out (device pointer to one element of dtype) is not NULL it receives max_cells sum_c |u_c|,

@@ -150,6 +150,10 @@ _HANDLE_SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     "sopht_poisson_slab_create_periodic": (
         ctypes.c_int, [ctypes.POINTER(_P), _I, _I, _I, _I, _I, _I, _D, _I, _P]),
     "sopht_poisson_slab_forward_x": (ctypes.c_int, [_P, _F, _P, _P, _P]),
+    "sopht_poisson_slab_pipe_forward_x": (ctypes.c_int, [_P, _F, _I, _P, _P]),
+    "sopht_poisson_slab_pipe_transpose": (ctypes.c_int, [_P, _I, _I, ctypes.POINTER(_P), _I, _P]),
+    "sopht_poisson_slab_pipe_yz": (ctypes.c_int, [_P, _I, _P, _P, _P]),
+    "sopht_poisson_slab_pipe_inverse_x": (ctypes.c_int, [_P, _F, _I, _P, _P]),
     "sopht_poisson_slab_yz": (ctypes.c_int, [_P, _P, _P, _P, _P, _P]),
     "sopht_poisson_slab_inverse_x": (ctypes.c_int, [_P, _F, _P, _P, _P]),
     "sopht_poisson_slab_enable_peer_exchange": (ctypes.c_int, [_P, _P]),
@@ -182,6 +186,7 @@ _HANDLE_SIGNATURES: dict[str, tuple[Any, list[Any]]] = {
     # fused 3-D Navier-Stokes passes
     "sopht_ns3d_advect_rotational": (ctypes.c_int, [_I, _F, _F, _F, _D, _P]),
     "sopht_ns3d_diffuse": (ctypes.c_int, [_I, _F, _F, _D, _F, _P]),
+    "sopht_ns3d_diffuse_penalise": (ctypes.c_int, [_I, _F, _F, _D, _F, _P, _P, _P, _P]),
     "sopht_ns3d_velocity_from_stream_function": (ctypes.c_int, [_I, _F, _F, _D, _PD, _P, _P]),
     "sopht_ns3d_advect_rotational_periodic_xy": (ctypes.c_int, [_I, _F, _F, _F, _D, _P]),
     "sopht_ns3d_diffuse_periodic_xy": (ctypes.c_int, [_I, _F, _F, _D, _F, _P]),

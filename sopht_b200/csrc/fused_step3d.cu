@@ -409,10 +409,15 @@ __global__ void __launch_bounds__(32 * VBY, 2)
 }
 
 // out = f + q * Lap_7pt(f) [, zero <- 0]; blockIdx.z = chunk * ncomp + comp. 4 + 4 (+4) B per cell (fp32).
-template <typename T, bool PXY>
-__global__ void __launch_bounds__(32 * VBY)
+// RAMP: the result is multiplied by rx[i] * ry[j] * rz[k] (in that order) on the way out - the sine penalisation of the
+// boundary ring for the default width 2, where the reference's copy-and-scale (penalise_field_boundary_3d.py:182-208)
+// degenerates to a per-axis factor {0, sin(pi/4), 1, ..., 1, sin(pi/4), 0}: the boundary cell takes the value of its
+// neighbour times sin(0) = 0, the neighbour is scaled in place.
+template <typename T, bool PXY, bool RAMP = false>
+__global__ void __launch_bounds__(32 * VBY, sizeof(T) == 4 ? 4 : 1)  // fp32: 64 registers, four CTAs per SM
     diffuse_vec_kernel(Vec3Out<T> out, Vec3View<T> in, Vec3Out<T> zero, int has_zero, int ncomp, T q, int nz,
-                       int ny, int nx, int kchunk) {
+                       int ny, int nx, int kchunk, const T* __restrict__ rx = nullptr,
+                       const T* __restrict__ ry = nullptr, const T* __restrict__ rz = nullptr) {
   constexpr int W = Vec<T>::W;
   const int lane = threadIdx.x;
   const int i0 = (blockIdx.x * 32 + lane) * W;
@@ -432,9 +437,16 @@ __global__ void __launch_bounds__(32 * VBY)
 
   Vec<T> fprev = sv::vload_if(act && k0 > 0, f + (int64_t)(k0 - 1) * in.sz);
   Vec<T> fcur = sv::vload_if(act, f + (int64_t)k0 * in.sz);
+  Vec<T> rampx = sv::vzero<T>();
+  T rampy = T(1);
+  if (RAMP) {
+    if (act) rampx = sv::vload(rx + i0);
+    rampy = ry[j];
+  }
 #pragma unroll 2
   for (int k = k0; k < k1; ++k) {
     const T* pk = f + (int64_t)k * in.sz;
+    const T rk = RAMP ? __ldg(rz + k) : T(1);  // issued with the plane's other loads
     const Vec<T> fnext = sv::vload_if(act && k + 1 < nz, pk + in.sz);
     const Vec<T> fup = sv::vload_if(up, pk + nb.up);
     const Vec<T> fdn = sv::vload_if(dn, pk + nb.dn);
@@ -453,6 +465,10 @@ __global__ void __launch_bounds__(32 * VBY)
             v.v[m] = fcur.v[m] + flux;
           }
         }
+      }
+      if (RAMP) {
+#pragma unroll
+        for (int m = 0; m < W; ++m) v.v[m] = ((v.v[m] * rampx.v[m]) * rampy) * rk;
       }
       sv::vstore(o_p + (int64_t)k * out.sz, v);
       if (has_zero) sv::vstore(z_p + (int64_t)k * zero.sz, sv::vzero<T>());
@@ -756,7 +772,8 @@ static int ns3d_advect(const char* fn, bool pxy, int dtype, const sopht_field_t*
 
 static int ns3d_diffuse(const char* fn, bool pxy, int dtype, const sopht_field_t* out_field,
                         const sopht_field_t* field, double nu_dt_by_dx2, const sopht_field_t* zero_field,
-                        void* stream) {
+                        void* stream, const void* ramp_x = nullptr, const void* ramp_y = nullptr,
+                        const void* ramp_z = nullptr) {
   SOPHT_CHECK_DTYPE(dtype);
   RETURN_IF(check_vec3(fn, out_field));
   RETURN_IF(check_vec3(fn, field));
@@ -786,7 +803,19 @@ static int ns3d_diffuse(const char* fn, bool pxy, int dtype, const sopht_field_t
   diffuse_vec_kernel<T, P><<<grid, block, 0, st>>>(                                                     \
       out_view<T>(out_field), in_view<T>(field), zero_field ? out_view<T>(zero_field) : out_view<T>(out_field), \
       zero_field != nullptr, 3, (T)nu_dt_by_dx2, nz, ny, nx, kchunk)
-    if (dtype == SOPHT_F32) {
+    if (ramp_x) {
+      if (pxy) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: no boundary ramps in a periodic box", fn);
+      if (dtype == SOPHT_F32)
+        diffuse_vec_kernel<float, false, true><<<grid, block, 0, st>>>(
+            out_view<float>(out_field), in_view<float>(field),
+            zero_field ? out_view<float>(zero_field) : out_view<float>(out_field), zero_field != nullptr, 3,
+            (float)nu_dt_by_dx2, nz, ny, nx, kchunk, (const float*)ramp_x, (const float*)ramp_y, (const float*)ramp_z);
+      else
+        diffuse_vec_kernel<double, false, true><<<grid, block, 0, st>>>(
+            out_view<double>(out_field), in_view<double>(field),
+            zero_field ? out_view<double>(zero_field) : out_view<double>(out_field), zero_field != nullptr, 3,
+            nu_dt_by_dx2, nz, ny, nx, kchunk, (const double*)ramp_x, (const double*)ramp_y, (const double*)ramp_z);
+    } else if (dtype == SOPHT_F32) {
       if (pxy) SOPHT_LAUNCH_DIFFUSE(float, true); else SOPHT_LAUNCH_DIFFUSE(float, false);
     } else {
       if (pxy) SOPHT_LAUNCH_DIFFUSE(double, true); else SOPHT_LAUNCH_DIFFUSE(double, false);
@@ -796,6 +825,7 @@ static int ns3d_diffuse(const char* fn, bool pxy, int dtype, const sopht_field_t
     return SOPHT_OK;
   }
   if (pxy) SOPHT_FAIL(SOPHT_ERR_STRIDE, "%s: the periodic kernels need 16-byte aligned, unit-stride rows", fn);
+  if (ramp_x) SOPHT_FAIL(SOPHT_ERR_STRIDE, "%s: the fused penalisation needs 16-byte aligned, unit-stride rows", fn);
   const int tx = dtype == SOPHT_F32 ? Tile<float>::TX : Tile<double>::TX, ty = Tile<float>::TY;
   const int kchunk = pick_kchunk(nz, ny, nx, 3, tx, ty);
   const int nchunk = (nz + kchunk - 1) / kchunk;
@@ -939,6 +969,17 @@ int sopht_wrap_z_halos(int dtype, const sopht_field_t* field, void* stream) {
     wrap_z_kernel<double><<<blocks, 256, 0, st>>>(base, cs, ps, rs, ncomp, nzp, ny, row_vecs);
   SOPHT_CHECK_LAUNCH();
   return SOPHT_OK;
+}
+
+/* diffuse + the width-2 sine penalisation of the boundary ring in one pass: ramp_{x,y,z} are DEVICE arrays of nx / ny / nz
+ * factors of `dtype` (1 in the interior; the ramp values of penalise_field_boundary_3d.py:62-94 on the two cells next to
+ * each face, i.e. {0, sin(pi/4)} for width 2). ref: navier_stokes_flow_simulators.py:466-478 */
+int sopht_ns3d_diffuse_penalise(int dtype, const sopht_field_t* out_field, const sopht_field_t* field,
+                                double nu_dt_by_dx2, const sopht_field_t* zero_field, const void* ramp_x,
+                                const void* ramp_y, const void* ramp_z, void* stream) {
+  if (!ramp_x || !ramp_y || !ramp_z) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: null ramp array", __func__);
+  return ns3d_diffuse(__func__, false, dtype, out_field, field, nu_dt_by_dx2, zero_field, stream, ramp_x, ramp_y,
+                      ramp_z);
 }
 
 /* periodic box: x and y wrap around inside the kernels; z keeps the ghost-ring rule, so the arrays carry one halo plane

@@ -286,8 +286,27 @@ int launch_yinv_full(int L, const p2::ColParams& p, dim3 grid, cudaStream_t st) 
 #undef M
   return SOPHT_OK;
 }
-int launch_zsym(int L, const p2::ZSymParams& p, dim3 grid, cudaStream_t st) {
-#define M(LL) return launch<p2::ZSym<LL, TX>>(p, grid, p.nyq ? "poisson.z_sym.nyquist" : "poisson.z_sym", st);
+// columns per CTA of the periodic z pass: its rows lie ny * nx/2 * 8 bytes apart and are read AND written in place, so
+// wider rows (16 columns = one 128-byte line) pay where shared memory allows it (L <= 1024)
+int zsym_tx(int L, int ncols) {
+  static const int want = env_int("SOPHT_ZSYM_TX", 16);
+  return want == 16 && L <= 1024 && ncols % 16 == 0 ? 16 : TX;
+}
+int launch_zsym(int L, const p2::ZSymParams& p, dim3 grid, cudaStream_t st, int tx = TX) {
+  const char* label = p.nyq ? "poisson.z_sym.nyquist" : "poisson.z_sym";
+  if (tx == 16) {
+    switch (L) {
+      case 16: return launch<p2::ZSym<16, 16>>(p, grid, label, st);
+      case 32: return launch<p2::ZSym<32, 16>>(p, grid, label, st);
+      case 64: return launch<p2::ZSym<64, 16>>(p, grid, label, st);
+      case 128: return launch<p2::ZSym<128, 16>>(p, grid, label, st);
+      case 256: return launch<p2::ZSym<256, 16>>(p, grid, label, st);
+      case 512: return launch<p2::ZSym<512, 16>>(p, grid, label, st);
+      case 1024: return launch<p2::ZSym<1024, 16>>(p, grid, label, st);
+      default: break;
+    }
+  }
+#define M(LL) return launch<p2::ZSym<LL, TX>>(p, grid, label, st);
   P2_SWITCH_L(L, M)
 #undef M
   return SOPHT_OK;
@@ -602,11 +621,12 @@ p2::ColParams periodic_nyquist_y_params(const p2::SlabDims& d, float2* a, const 
   yn.tw = tw;
   return yn;
 }
-p2::ZSymParams periodic_z_params(const p2::SlabDims& d, float2* a, const PeriodicSymbols& sym, const float2* tw) {
+p2::ZSymParams periodic_z_params(const p2::SlabDims& d, float2* a, const PeriodicSymbols& sym, const float2* tw,
+                                 int tx = TX) {
   const int64_t nxl = d.nxl();
   p2::ZSymParams zp{};
   zp.data = a;
-  zp.rs = (int64_t)d.ny * nxl, zp.cs = 1, zp.d_bx = TX, zp.d_by = nxl, zp.d_c = (int64_t)d.nz * d.ny * nxl;
+  zp.rs = (int64_t)d.ny * nxl, zp.cs = 1, zp.d_bx = tx, zp.d_by = nxl, zp.d_c = (int64_t)d.nz * d.ny * nxl;
   zp.ncomp = d.C;
   zp.lz = sym.lz, zp.ly = sym.ly, zp.lx = sym.lx, zp.norm = sym.norm;
   zp.kx0 = d.rank * (int)nxl;
@@ -645,6 +665,10 @@ struct SlabPow2Poisson {
   bool peers_open = false;
 
   size_t exchange_bytes() const { return sizeof(float2) * (size_t)d.C * d.nz * d.ny * d.nxl(); }
+  // pipelined solve: the kx = nx (Nyquist) plane of every rank, (C, nz, ny), lives behind the spectrum in the xrecv
+  // block so that the peers can fill their planes of it with a copy-engine copy
+  size_t nyquist_bytes() const { return sizeof(float2) * (size_t)d.C * d.nz * d.ny; }
+  float2* nyq_all_peer(int q) const { return peer_recv[q] + exchange_bytes() / sizeof(float2); }
 
   ~SlabPow2Poisson() {
     if (peers_open)
@@ -711,7 +735,8 @@ struct SlabPow2Poisson {
 
   int enable_peer_exchange(unsigned char* handles_out) {
     if (!xrecv) {
-      if (cudaMalloc(&xrecv, exchange_bytes()) != cudaSuccess || cudaMalloc(&xsend, exchange_bytes()) != cudaSuccess)
+      if (cudaMalloc(&xrecv, exchange_bytes() + nyquist_bytes()) != cudaSuccess ||
+          cudaMalloc(&xsend, exchange_bytes()) != cudaSuccess)
         SOPHT_FAIL(SOPHT_ERR_ALLOC, "poisson(slab): out of device memory for the exchange buffers");
     }
     cudaIpcMemHandle_t h0, h1;
@@ -769,7 +794,9 @@ struct SlabPow2Poisson {
       const dim3 gy(nxl / TX, d.C * d.nz, 1), gyn(d.C * d.nz / TX, 1, 1);
       if ((rc = launch_yfwd_full(d.ny, periodic_y_params(d, recv, twy), gy, st))) return rc;
       if ((rc = launch_yfwd_full(d.ny, periodic_nyquist_y_params(d, nyq_all, twy), gyn, st))) return rc;
-      if ((rc = launch_zsym(d.nz, periodic_z_params(d, recv, sym, twz), dim3(nxl / TX, d.ny, 1), st))) return rc;
+      const int ztx = zsym_tx(d.nz, nxl);
+      if ((rc = launch_zsym(d.nz, periodic_z_params(d, recv, sym, twz, ztx), dim3(nxl / ztx, d.ny, 1), st, ztx)))
+        return rc;
       if ((rc = launch_zsym(d.nz, periodic_nyquist_z_params(d, nyq_all, sym, twz), dim3(d.ny / TX, 1, 1), st)))
         return rc;
       p2::ColParams yi = periodic_y_params(d, recv, twy);
@@ -796,6 +823,104 @@ struct SlabPow2Poisson {
     if ((rc = launch_yinv(LY, yi, dim3(nxl / TX, d.C * d.nz, 1), st))) return rc;
     return launch_yinv(LY, p2::nyquist_y_params(d, TX, nyq_work, nyq_all, false, twy),
                        dim3(d.C * d.nz / TX, 1, 1), st);
+  }
+
+  // ---- pipelined solve: one component at a time, transposes by the copy engines -------------------------------------
+  // The fused transposes above keep the SMs busy with NVLink stores / loads for 2 x 4.3 ms of a 25 ms step at 1024^3 on
+  // 8 GPUs while nothing else runs. Here every phase works on ONE component: the x forward pass writes a plain
+  // row-major spectrum S[c] (the xsend block reinterpreted as (C, rows, nx)), cudaMemcpy2DAsync copies (DMA, no SM)
+  // move its kx chunks into the peers' xrecv blocks while the SMs run the y / z passes of the previous component, and
+  // the way back mirrors it. The host layer (parallel/slab_poisson.py) orders the phases with events and the
+  // peer-arena barrier.
+  p2::SlabDims comp_dims_x() const { return p2::SlabDims{1, d.nzl(), d.ny, d.nx, 1, 0}; }  // this rank's rows, whole rows
+  int64_t rows_local() const { return (int64_t)d.nzl() * d.ny; }
+
+  int pipe_forward_x(const sopht_field_t* rhs, int c, float2* nyq_local, cudaStream_t st) const {
+    int rc = check_local(__func__, rhs);
+    if (rc) return rc;
+    if (!peers_open) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: peer exchange is not open", __func__);
+    const p2::SlabDims dx_ = comp_dims_x();
+    p2::XParams xp = p2::slab_x_params(dx_, reinterpret_cast<const float*>(rhs->data) + (int64_t)c * rhs->stride[0],
+                                       nullptr, 0, rhs->stride[1], rhs->stride[2], xsend + (int64_t)c * rows_local() * d.nx,
+                                       nyq_local + (int64_t)c * rows_local(), twx, twx2);
+    return periodic ? launch_xfwd_full(d.nx, xp, rows_local(), st) : launch_xfwd(d.nx, xp, rows_local(), st);
+  }
+  int pipe_inverse_x(const sopht_field_t* sol, int c, float2* nyq_local, cudaStream_t st) const {
+    int rc = check_local(__func__, sol);
+    if (rc) return rc;
+    if (!peers_open) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: peer exchange is not open", __func__);
+    const p2::SlabDims dx_ = comp_dims_x();
+    p2::XParams xp = p2::slab_x_params(dx_, nullptr, reinterpret_cast<float*>(sol->data) + (int64_t)c * sol->stride[0], 0,
+                                       sol->stride[1], sol->stride[2], xsend + (int64_t)c * rows_local() * d.nx,
+                                       nyq_local + (int64_t)c * rows_local(), twx, twx2);
+    return periodic ? launch_xinv_full(d.nx, xp, rows_local(), st) : launch_xinv(d.nx, xp, rows_local(), st);
+  }
+  // forward: chunk q of my S[c] rows -> slot `rank` of rank q's recv[c]; my Nyquist bins -> everybody's nyq_all.
+  // backward: z block p of my recv[c] -> kx chunk `rank` of rank p's S[c] rows. Copies go round robin over `streams`.
+  int pipe_transpose(int c, int backward, cudaStream_t* streams, int nstreams, const float2* nyq_local) const {
+    if (!peers_open) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: peer exchange is not open", __func__);
+    if (nstreams < 1 || !streams) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: at least one stream", __func__);
+    const int64_t rows = rows_local(), nxl = d.nxl(), nx = d.nx;
+    const int64_t comp_chunks = (int64_t)d.P * rows * nxl;  // elements of one component of an exchange buffer
+    for (int k = 0; k < d.P; ++k) {
+      const int q = (d.rank + k) % d.P;  // start with the self copy, then ring order: all links busy at once
+      cudaStream_t st = streams[k % nstreams];
+      if (!backward) {
+        const float2* src = xsend + (int64_t)c * rows * nx + q * nxl;
+        float2* dst = peer_recv[q] + c * comp_chunks + (int64_t)d.rank * rows * nxl;
+        SOPHT_CUDA(cudaMemcpy2DAsync(dst, sizeof(float2) * nxl, src, sizeof(float2) * nx, sizeof(float2) * nxl, rows,
+                                     cudaMemcpyDeviceToDevice, st));
+        if (nyq_local)
+          SOPHT_CUDA(cudaMemcpyAsync(nyq_all_peer(q) + ((int64_t)c * d.nz + (int64_t)d.rank * d.nzl()) * d.ny,
+                                     nyq_local + (int64_t)c * rows, sizeof(float2) * rows, cudaMemcpyDeviceToDevice,
+                                     st));
+      } else {
+        const float2* src = xrecv + c * comp_chunks + (int64_t)q * rows * nxl;
+        float2* dst = peer_send[q] + (int64_t)c * rows * nx + (int64_t)d.rank * nxl;
+        SOPHT_CUDA(cudaMemcpy2DAsync(dst, sizeof(float2) * nx, src, sizeof(float2) * nxl, sizeof(float2) * nxl, rows,
+                                     cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    return SOPHT_OK;
+  }
+  // y forward, z, y inverse of component c on the received kx slab, in place in xrecv[c] (and the Nyquist plane)
+  int pipe_yz(int c, float2* work, float2* nyq_work, cudaStream_t st) const {
+    if (!peers_open) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: peer exchange is not open", __func__);
+    const int LY = 2 * d.ny, LZ = 2 * d.nz, nxl = d.nxl();
+    p2::SlabDims d1 = d;
+    d1.C = 1;
+    float2* recv = xrecv + (int64_t)c * d.nz * d.ny * nxl;
+    float2* nyq = nyq_all_peer(d.rank) + (int64_t)c * d.nz * d.ny;
+    int rc;
+    if (periodic) {
+      const dim3 gy(nxl / TX, d.nz, 1), gyn(d.nz / TX, 1, 1);
+      if ((rc = launch_yfwd_full(d.ny, periodic_y_params(d1, recv, twy), gy, st))) return rc;
+      if ((rc = launch_yfwd_full(d.ny, periodic_nyquist_y_params(d1, nyq, twy), gyn, st))) return rc;
+      const int ztx = zsym_tx(d.nz, nxl);
+      if ((rc = launch_zsym(d.nz, periodic_z_params(d1, recv, sym, twz, ztx), dim3(nxl / ztx, d.ny, 1), st, ztx)))
+        return rc;
+      if ((rc = launch_zsym(d.nz, periodic_nyquist_z_params(d1, nyq, sym, twz), dim3(d.ny / TX, 1, 1), st))) return rc;
+      if ((rc = launch_yinv_full(d.ny, periodic_y_params(d1, recv, twy), gy, st))) return rc;
+      return launch_yinv_full(d.ny, periodic_nyquist_y_params(d1, nyq, twy), gyn, st);
+    }
+    if (!work || !nyq_work) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null work buffer", __func__);
+    float2* work2 = work + (int64_t)d.nz * LY * nxl;  // second half: the z pass's tile-major output
+    if ((rc = launch_yfwd(LY, p2::slab_y_params(d1, TX, recv, work, true, twy), dim3(nxl / TX, d.nz, 1), st))) return rc;
+    if ((rc = launch_yfwd(LY, p2::nyquist_y_params(d1, TX, nyq, nyq_work, true, twy), dim3(d.nz / TX, 1, 1), st)))
+      return rc;
+    if ((rc = launch_zconv(LZ, p2::slab_z_params(d1, TX, work, work2, gm, nxl, 0, twz), dim3(nxl / TX, LY, 1), st)))
+      return rc;
+    if ((rc = launch_zconv(LZ, p2::nyquist_z_params(d1, TX, nyq_work, gn, twz), dim3(LY / TX, 1, 1), st))) return rc;
+    if ((rc = launch_yinv(LY, p2::slab_y_params(d1, TX, work2, recv, false, twy), dim3(nxl / TX, d.nz, 1), st)))
+      return rc;
+    return launch_yinv(LY, p2::nyquist_y_params(d1, TX, nyq_work, nyq, false, twy), dim3(d.nz / TX, 1, 1), st);
+  }
+  // this rank's planes of the processed Nyquist plane of component c -> nyq_local[c] (the x inverse reads it)
+  int pipe_nyquist_slice(int c, float2* nyq_local, cudaStream_t st) const {
+    const float2* src = nyq_all_peer(d.rank) + ((int64_t)c * d.nz + (int64_t)d.rank * d.nzl()) * d.ny;
+    SOPHT_CUDA(cudaMemcpyAsync(nyq_local + (int64_t)c * rows_local(), src, sizeof(float2) * rows_local(),
+                               cudaMemcpyDeviceToDevice, st));
+    return SOPHT_OK;
   }
 
   int inverse_x(const sopht_field_t* sol, float2* recv2, float2* nyq_local, cudaStream_t st) const {
@@ -865,7 +990,8 @@ struct PeriodicPow2Poisson : PoissonImpl {
     if ((rc = launch_xfwd_full(LX, xp, rows, st))) return rc;
     if ((rc = launch_yfwd_full(ny, periodic_y_params(d, A, twy), dim3(LX / TX, C * nz, 1), st))) return rc;
     if ((rc = launch_yfwd_full(ny, periodic_nyquist_y_params(d, nyqA, twy), dim3(C * nz / TX, 1, 1), st))) return rc;
-    if ((rc = launch_zsym(nz, periodic_z_params(d, A, sym, twz), dim3(LX / TX, ny, 1), st))) return rc;
+    const int ztx = zsym_tx(nz, LX);
+    if ((rc = launch_zsym(nz, periodic_z_params(d, A, sym, twz, ztx), dim3(LX / ztx, ny, 1), st, ztx))) return rc;
     if ((rc = launch_zsym(nz, periodic_nyquist_z_params(d, nyqA, sym, twz), dim3(ny / TX, 1, 1), st))) return rc;
     if ((rc = launch_yinv_full(ny, periodic_y_params(d, A, twy), dim3(LX / TX, C * nz, 1), st))) return rc;
     if ((rc = launch_yinv_full(ny, periodic_nyquist_y_params(d, nyqA, twy), dim3(C * nz / TX, 1, 1), st))) return rc;
@@ -1005,6 +1131,38 @@ int sopht_poisson_slab_enable_peer_exchange(sopht_poisson_slab_t h, unsigned cha
 int sopht_poisson_slab_open_peers(sopht_poisson_slab_t h, const unsigned char* all_ipc_handles) {
   if (!h || !all_ipc_handles) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
   return h->impl.open_peers(all_ipc_handles);
+}
+
+/* ---- pipelined solve (one component per call, copy-engine transposes): see SlabPow2Poisson::pipe_* ---- */
+int sopht_poisson_slab_pipe_forward_x(sopht_poisson_slab_t h, const sopht_field_t* rhs_field, int component,
+                                      void* nyquist_local, void* stream) {
+  if (!h || !nyquist_local) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
+  if (component < 0 || component >= h->impl.d.C) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: bad component", __func__);
+  return h->impl.pipe_forward_x(rhs_field, component, reinterpret_cast<float2*>(nyquist_local), as_stream(stream));
+}
+int sopht_poisson_slab_pipe_transpose(sopht_poisson_slab_t h, int component, int backward, void** streams,
+                                      int nstreams, const void* nyquist_local) {
+  if (!h) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle", __func__);
+  if (component < 0 || component >= h->impl.d.C) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: bad component", __func__);
+  if (nstreams < 1 || nstreams > 16 || !streams) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: 1..16 streams", __func__);
+  cudaStream_t st[16];
+  for (int i = 0; i < nstreams; ++i) st[i] = as_stream(streams[i]);
+  return h->impl.pipe_transpose(component, backward, st, nstreams, reinterpret_cast<const float2*>(nyquist_local));
+}
+int sopht_poisson_slab_pipe_yz(sopht_poisson_slab_t h, int component, void* work_buffer, void* nyquist_work,
+                               void* stream) {
+  if (!h) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle", __func__);
+  if (component < 0 || component >= h->impl.d.C) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: bad component", __func__);
+  return h->impl.pipe_yz(component, reinterpret_cast<float2*>(work_buffer), reinterpret_cast<float2*>(nyquist_work),
+                         as_stream(stream));
+}
+int sopht_poisson_slab_pipe_inverse_x(sopht_poisson_slab_t h, const sopht_field_t* solution_field, int component,
+                                      void* nyquist_local, void* stream) {
+  if (!h || !nyquist_local) SOPHT_FAIL(SOPHT_ERR_HANDLE, "%s: null handle or buffer", __func__);
+  if (component < 0 || component >= h->impl.d.C) SOPHT_FAIL(SOPHT_ERR_ARG, "%s: bad component", __func__);
+  int rc = h->impl.pipe_nyquist_slice(component, reinterpret_cast<float2*>(nyquist_local), as_stream(stream));
+  if (rc) return rc;
+  return h->impl.pipe_inverse_x(solution_field, component, reinterpret_cast<float2*>(nyquist_local), as_stream(stream));
 }
 
 int sopht_poisson_slab_destroy(sopht_poisson_slab_t h) {

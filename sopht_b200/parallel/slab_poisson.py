@@ -132,6 +132,13 @@ class SlabUnboundedPoissonSolver3D:
             self._nyq_gather = torch.zeros((world, n_components, nzl, ny, 2), dtype=torch.float32, device=device)
             self._barrier_flag = torch.zeros(1, dtype=torch.float32, device=device)
             self.plan.send = self.plan.recv = None  # exchange buffers live in the library
+        # component-pipelined solve with copy-engine transposes (opt-in: SOPHT_SLAB_PIPELINE=1; measured slower than
+        # the transposes fused into the x kernels on 2 GPUs - the DMA traffic competes with the HBM-bound y / z passes)
+        self.pipelined = (self.peer_exchange and peer_arena is not None
+                          and os.environ.get("SOPHT_SLAB_PIPELINE", "0") != "0")
+        if self.pipelined:
+            self._init_pipeline(n_components, device)
+            self.path += "-pipelined"
 
     def _create_handle(self, lib, n_components: int, world: int, rank: int) -> ctypes.c_void_p:
         real_t = self.real_t
@@ -165,6 +172,70 @@ class SlabUnboundedPoissonSolver3D:
         _lib.check(lib.sopht_poisson_slab_open_peers(self._handle, ctypes.cast(buf, ctypes.c_void_p)))
         dist.barrier(group=group)
 
+    # -- pipelined solve ---------------------------------------------------------------------------------------
+    def _init_pipeline(self, n_components: int, device) -> None:
+        nz, ny = self.grid_size_z, self.grid_size_y
+        if self._work is not None:  # one component at a time: a third of the workspace
+            self._work = torch.zeros((2, 1, nz, 2 * ny, self.plan.nxl, 2), dtype=torch.float32, device=device)
+            self._nyq_work = torch.zeros((1, nz, 2 * ny, 2), dtype=torch.float32, device=device)
+        self._copy_streams = [torch.cuda.Stream(device=device) for _ in range(4)]
+        # high priority: its one-warp barrier kernels must slip in between the persistent compute kernels
+        self._ctrl_stream = torch.cuda.Stream(device=device, priority=-1)
+        self._stream_array = (ctypes.c_void_p * len(self._copy_streams))(
+            *[ctypes.c_void_p(s.cuda_stream) for s in self._copy_streams])
+        self._n_components = n_components
+
+    def _transpose(self, lib, c: int, backward: bool, after: torch.cuda.Event) -> torch.cuda.Event:
+        """Enqueue the copy-engine transposes of component c once `after` has fired; returns the event that fires when
+        EVERY rank's copies of this component have landed (copies -> all-ranks barrier on the control stream)."""
+        plan = self.plan
+        for s in self._copy_streams:
+            s.wait_event(after)
+        nyq = None if backward else ctypes.c_void_p(plan.nyq_local.data_ptr())
+        _lib.check(lib.sopht_poisson_slab_pipe_transpose(
+            self._handle, c, int(backward), self._stream_array, len(self._copy_streams), nyq))
+        for s in self._copy_streams:
+            ev = torch.cuda.Event()
+            ev.record(s)
+            self._ctrl_stream.wait_event(ev)
+        with torch.cuda.stream(self._ctrl_stream):
+            self._peer_arena.barrier()
+        done = torch.cuda.Event()
+        done.record(self._ctrl_stream)
+        return done
+
+    def _solve_pipelined(self, fr, fs) -> None:
+        """Per component: x forward -> DMA transpose -> y, z, y inverse -> DMA transpose back -> x inverse, with the
+        transposes of one component running under the compute of the others (three compute phases on the caller's
+        stream, copies on four side streams, the all-ranks barriers on a control stream)."""
+        lib, plan = _lib.load(), self.plan
+        p = ctypes.c_void_p
+        main = torch.cuda.current_stream()
+        st = _lib.current_stream()
+        ncomp = self._n_components
+        nyq_local = p(plan.nyq_local.data_ptr())
+        work = p(self._work.data_ptr()) if self._work is not None else None
+        nyq_work = p(self._nyq_work.data_ptr()) if self._nyq_work is not None else None
+        arrived = []
+        for c in range(ncomp):
+            _lib.check(lib.sopht_poisson_slab_pipe_forward_x(self._handle, ctypes.byref(fr), c, nyq_local, st))
+            ev = torch.cuda.Event()
+            ev.record(main)
+            arrived.append(self._transpose(lib, c, False, ev))
+        returned = []
+        for c in range(ncomp):
+            main.wait_event(arrived[c])
+            _lib.check(lib.sopht_poisson_slab_pipe_yz(self._handle, c, work, nyq_work, st))
+            ev = torch.cuda.Event()
+            ev.record(main)
+            returned.append(self._transpose(lib, c, True, ev))
+            if c >= 1:
+                main.wait_event(returned[c - 1])
+                _lib.check(lib.sopht_poisson_slab_pipe_inverse_x(
+                    self._handle, ctypes.byref(fs), c - 1, nyq_local, st))
+        main.wait_event(returned[ncomp - 1])
+        _lib.check(lib.sopht_poisson_slab_pipe_inverse_x(self._handle, ctypes.byref(fs), ncomp - 1, nyq_local, st))
+
     def __del__(self) -> None:
         h = getattr(self, "_handle", None)
         if h is not None and h.value:
@@ -197,6 +268,9 @@ class SlabUnboundedPoissonSolver3D:
 
         if not self.peer_exchange:
             plan.solve(forward_x, middle, inverse_x)
+            return
+        if self.pipelined:
+            self._solve_pipelined(fr, fs)
             return
         # peer-memory path: the kernels themselves move the spectrum over NVLink (x forward pushes its chunks into the
         # owners' buffers, x inverse pulls its chunks from the y-inverse outputs); collectives only order the phases

@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import ctypes
 import logging
+import os
 from typing import Any, Literal
 
 import numpy as np
@@ -205,12 +206,18 @@ class UnboundedNavierStokesFlowSimulator3D(FlowSimulator):
         _lib.check(lib.sopht_ns3d_advect_rotational(
             dc, ctypes.byref(fb), ctypes.byref(fw), ctypes.byref(fu), float(rt(dt / (2 * self.dx))), st))
         ff = fd(self.eul_grid_forcing_field, dc) if self.with_forcing else None
-        _lib.check(lib.sopht_ns3d_diffuse(
-            dc, ctypes.byref(fw), ctypes.byref(fb),
-            float(rt(self.kinematic_viscosity * dt / self.dx / self.dx)),
-            ctypes.byref(ff) if ff is not None else None, st))
-        self._filter_vector_field(vector_field=self.vorticity_field)
-        self._penalise_field_towards_boundary(vector_field=self.vorticity_field)
+        nu_dt_by_dx2 = float(rt(self.kinematic_viscosity * dt / self.dx / self.dx))
+        ramps = self._penalty_ramps()
+        if ramps is not None:  # width-2 penalisation folded into the diffusion pass (no filter in between)
+            _lib.check(lib.sopht_ns3d_diffuse_penalise(
+                dc, ctypes.byref(fw), ctypes.byref(fb), nu_dt_by_dx2, ctypes.byref(ff) if ff is not None else None,
+                ctypes.c_void_p(ramps[0].data_ptr()), ctypes.c_void_p(ramps[1].data_ptr()),
+                ctypes.c_void_p(ramps[2].data_ptr()), st))
+        else:
+            _lib.check(lib.sopht_ns3d_diffuse(
+                dc, ctypes.byref(fw), ctypes.byref(fb), nu_dt_by_dx2, ctypes.byref(ff) if ff is not None else None, st))
+            self._filter_vector_field(vector_field=self.vorticity_field)
+            self._penalise_field_towards_boundary(vector_field=self.vorticity_field)
         self._unbounded_poisson_solver.vector_field_solve(
             solution_vector_field=self.stream_func_field, rhs_vector_field=self.vorticity_field)
         fpsi = fd(self.stream_func_field, dc)
@@ -219,6 +226,33 @@ class UnboundedNavierStokesFlowSimulator3D(FlowSimulator):
             dc, ctypes.byref(fu), ctypes.byref(fpsi), float(rt(0.5 / self.dx)), fsv,
             ctypes.c_void_p(self._vel_absmax.data_ptr()), st))
         self._vel_absmax_version = (self.velocity_field.data_ptr(), self.velocity_field._version)
+
+    def _penalty_ramps(self):
+        """Per-axis factors (x, y, z device arrays) that ARE the sine penalisation for the default zone width 2
+        (penalise_field_boundary_3d.py:182-208: the boundary cell takes its neighbour's value times sin(0) = 0, the
+        neighbour is scaled by sin(pi/4)); None when the fused form does not apply (other widths, vorticity filter,
+        rows that are not 16-byte multiples)."""
+        if getattr(self, "_ramps_cache", False) is not False:
+            return self._ramps_cache
+        self._ramps_cache = None
+        nz, ny, nx = self.grid_size
+        elem = np.dtype(self.real_t).itemsize
+        if (self.penalty_zone_width == 2 and not self.filter_vorticity and (nx * elem) % 16 == 0
+                and min(nz, ny, nx) >= 4 and os.environ.get("SOPHT_FUSE_PENALISE", "1") != "0"):
+            from sopht_b200.numeric.eulerian_grid_ops.stencil_ops_3d import _sine_ramps
+
+            out = []
+            for axis, n in ((2, nx), (1, ny), (0, nz)):  # x, y, z
+                idx = [0, 0, 0]
+                idx[axis] = slice(None)
+                coords = self.position_field[2 - axis][tuple(idx)].cpu().numpy()
+                r = _sine_ramps(coords, 2, self.dx, self.real_t)
+                f = np.ones(n, dtype=self.real_t)
+                f[:2] = r[:2]
+                f[-2:] = r[2:]
+                out.append(torch.from_numpy(f).to(self.vorticity_field.device))
+            self._ramps_cache = out
+        return self._ramps_cache
 
     def _navier_stokes_time_step(self, dt: float, free_stream_velocity=(0.0, 0.0, 0.0)) -> None:
         """navier_stokes_flow_simulators.py:449-485."""

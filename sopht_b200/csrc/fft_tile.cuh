@@ -26,6 +26,243 @@
 namespace sopht {
 namespace fft {
 
+// Two implementations of the complex arithmetic and the in-register DFTs below. A translation unit that defines
+// SOPHT_FFT_USE_PACKED before including this file gets the packed-FP32 form on sm_100a (used where the kernel is bound by
+// issue slots); everything else keeps the scalar form (measured: the HBM-bound x / y kernels are 2-19 % slower with the
+// packed form, profiles/r02_zpass_experiments.txt).
+#if defined(SOPHT_FFT_USE_PACKED) && defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+#define SOPHT_FFT_PACKED 1
+#endif
+
+#if defined(SOPHT_FFT_USE_PACKED)
+// Complex arithmetic. On the device the (re, im) pair of a float2 is one 64-bit register pair and sm_100a has packed
+// FP32 instructions on such pairs (FADD2 / FMUL2 / FFMA2: add.f32x2, mul.f32x2, fma.rn.f32x2) whose operands take a
+// per-operand half swap (.LO_HI), a per-half sign (.NP) and a scalar broadcast (.F32) for free: a complex add is ONE
+// instruction instead of two, a complex product TWO (FMUL2 + FFMA2) instead of four, multiplication by -i / +i folds
+// into the operand modifiers of the next add. The FP32 pipe retires the same number of results per clock either way
+// (tools/micro/f32x2_rate.cu: 120 results / clk / SM scalar and packed) - what the packed forms halve is the ISSUE
+// slots, which is what bounds the z pass (profiles/r02_zpass_experiments.txt). ptxas recognises the forms below from
+// the intrinsics with make_float2 operand shuffles; the host build (tests/host) keeps plain scalar arithmetic.
+
+FFT_HD float2 cadd(float2 a, float2 b) {
+#ifdef SOPHT_FFT_PACKED
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+FFT_HD float2 csub(float2 a, float2 b) {
+#ifdef SOPHT_FFT_PACKED
+  return __fadd2_rn(a, make_float2(-b.x, -b.y));
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+FFT_HD float2 cmul(float2 a, float2 b) {
+#ifdef SOPHT_FFT_PACKED
+  const float2 t = __fmul2_rn(make_float2(a.y, a.y), make_float2(b.y, b.x));  // (ay by, ay bx)
+  return __ffma2_rn(make_float2(a.x, a.x), b, make_float2(-t.x, t.y));
+#else
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+#endif
+}
+FFT_HD float2 cmul_conj(float2 a, float2 b) {  // a * conj(b)
+#ifdef SOPHT_FFT_PACKED
+  const float2 t = __fmul2_rn(make_float2(a.x, a.x), b);  // (ax bx, ax by)
+  return __ffma2_rn(make_float2(a.y, a.y), make_float2(b.y, b.x), make_float2(t.x, -t.y));
+#else
+  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+#endif
+}
+FFT_HD float2 cscale(float2 a, float s) {  // a * s, s real
+#ifdef SOPHT_FFT_PACKED
+  return __fmul2_rn(a, make_float2(s, s));
+#else
+  return make_float2(a.x * s, a.y * s);
+#endif
+}
+// 8-byte store of a packed result: handing the store ONE 64-bit register (the pair the packed instruction wrote) keeps
+// ptxas from copying the pair into a common scratch pair first (MOV, MOV, STS chains that serialise on that pair)
+FFT_HD void store2(float2* p, float2 v) {
+#ifdef SOPHT_FFT_PACKED
+  unsigned long long u;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(u) : "f"(v.x), "f"(v.y));
+  *reinterpret_cast<unsigned long long*>(p) = u;
+#else
+  *p = v;
+#endif
+}
+FFT_HD float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+FFT_HD float2 mul_pi(float2 a) { return make_float2(-a.y, a.x); }  // a * (+i)
+// a * (-i) in a forward transform, a * (+i) in an inverse one
+template <bool INV>
+FFT_HD float2 mul_qi(float2 a) {
+  return INV ? mul_pi(a) : mul_mi(a);
+}
+
+// w32(j) = exp(-2 pi i j / 32); j is a compile-time constant after unrolling.
+FFT_HD float2 w32(int j) {
+  constexpr float c[32] = {
+      1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654757f,
+      0.55557023301960229f, 0.38268343236508984f, 0.19509032201612833f, 0.f, -0.19509032201612819f,
+      -0.38268343236508973f, -0.55557023301960196f, -0.70710678118654746f, -0.83146961230254535f,
+      -0.92387953251128674f, -0.98078528040323043f, -1.f, -0.98078528040323043f, -0.92387953251128685f,
+      -0.83146961230254546f, -0.70710678118654768f, -0.55557023301960218f, -0.38268343236509034f,
+      -0.19509032201612866f, 0.f, 0.1950903220161283f, 0.38268343236509f, 0.55557023301960184f,
+      0.70710678118654735f, 0.83146961230254524f, 0.92387953251128652f, 0.98078528040323032f};
+  constexpr float s[32] = {
+      0.f, -0.19509032201612825f, -0.38268343236508978f, -0.55557023301960218f, -0.70710678118654746f,
+      -0.83146961230254524f, -0.92387953251128674f, -0.98078528040323043f, -1.f, -0.98078528040323043f,
+      -0.92387953251128674f, -0.83146961230254546f, -0.70710678118654757f, -0.55557023301960218f,
+      -0.38268343236508989f, -0.19509032201612861f, 0.f, 0.19509032201612836f, 0.38268343236508967f,
+      0.55557023301960196f, 0.70710678118654746f, 0.83146961230254524f, 0.92387953251128652f,
+      0.98078528040323032f, 1.f, 0.98078528040323043f, 0.92387953251128663f, 0.83146961230254546f,
+      0.70710678118654768f, 0.55557023301960218f, 0.38268343236509039f, 0.19509032201612872f};
+  return make_float2(c[j & 31], s[j & 31]);
+}
+#ifdef __CUDACC__
+// The same 32 values as (re, im) pairs in constant memory: a packed product takes the pair as ONE 64-bit uniform-register
+// operand (LDCU.64, hoisted out of the tile loops) where immediates would cost two MOVs per pair and use.
+static __constant__ float2 kW32[32] = {
+    {1.f, 0.f}, {0.98078528040323043f, -0.19509032201612825f}, {0.92387953251128674f, -0.38268343236508978f},
+    {0.83146961230254524f, -0.55557023301960218f}, {0.70710678118654757f, -0.70710678118654746f},
+    {0.55557023301960229f, -0.83146961230254524f}, {0.38268343236508984f, -0.92387953251128674f},
+    {0.19509032201612833f, -0.98078528040323043f}, {0.f, -1.f}, {-0.19509032201612819f, -0.98078528040323043f},
+    {-0.38268343236508973f, -0.92387953251128674f}, {-0.55557023301960196f, -0.83146961230254546f},
+    {-0.70710678118654746f, -0.70710678118654757f}, {-0.83146961230254535f, -0.55557023301960218f},
+    {-0.92387953251128674f, -0.38268343236508989f}, {-0.98078528040323043f, -0.19509032201612861f}, {-1.f, 0.f},
+    {-0.98078528040323043f, 0.19509032201612836f}, {-0.92387953251128685f, 0.38268343236508967f},
+    {-0.83146961230254546f, 0.55557023301960196f}, {-0.70710678118654768f, 0.70710678118654746f},
+    {-0.55557023301960218f, 0.83146961230254524f}, {-0.38268343236509034f, 0.92387953251128652f},
+    {-0.19509032201612866f, 0.98078528040323032f}, {0.f, 1.f}, {0.1950903220161283f, 0.98078528040323043f},
+    {0.38268343236509f, 0.92387953251128663f}, {0.55557023301960184f, 0.83146961230254546f},
+    {0.70710678118654735f, 0.70710678118654768f}, {0.83146961230254524f, 0.55557023301960218f},
+    {0.92387953251128652f, 0.38268343236509039f}, {0.98078528040323032f, 0.19509032201612872f}};
+#endif
+FFT_HD float2 w32c(int j) {
+#ifdef SOPHT_FFT_PACKED
+  float2 w = kW32[j & 31];
+  return w;
+#else
+  return w32(j);
+#endif
+}
+
+// a * exp(-+ 2 pi i j / 32) (forward: minus; INV: plus). Only w^1, w^2, w^3 are ever multiplied with (three constant
+// pairs that stay in uniform registers): w^4 = h (1 - i) is one add and one real scaling, w^(8 - r) = -i conj(w^r), and
+// the quadrant factor (-i)^q is a half swap / sign that the consuming add takes as an operand modifier.
+template <bool INV = false>
+FFT_HD float2 rot32(float2 a, int j) {
+  j &= 31;
+  if (INV) j = (32 - j) & 31;  // conj(w^j) = w^(32 - j)
+  constexpr float h = 0.70710678118654757f;
+  const int q = j >> 3, r = j & 7;
+  float2 b = a;
+  if (r == 4)
+    b = cscale(cadd(a, mul_mi(a)), h);
+  else if (r >= 1 && r <= 3)
+    b = cmul(a, w32c(r));
+  else if (r >= 5)
+    b = mul_mi(cmul_conj(a, w32c(8 - r)));
+  if (q == 1) return mul_mi(b);
+  if (q == 2) return make_float2(-b.x, -b.y);
+  if (q == 3) return mul_pi(b);
+  return b;
+}
+
+// ---- in-register DFTs, natural order in and out: v[k] <- sum_n v[n] exp(-+ 2 pi i n k / R) (INV: plus, unnormalised) --
+template <int R, bool INV = false>
+struct Dft;
+
+// run_half: the same transform when the upper half of the input (v[R/2..R-1]) is known to be zero - the first
+// radix-2 stage degenerates into copies. Written out because x + 0.0f is not foldable under IEEE rules
+// (-0.0f + 0.0f = +0.0f), so the compiler keeps those additions when it is merely handed literal zeros.
+template <bool INV>
+struct Dft<1, INV> {
+  FFT_HD static void run(float2*) {}
+  FFT_HD static void run_half(float2*) {}
+};
+template <bool INV>
+struct Dft<2, INV> {
+  FFT_HD static void run(float2* v) {
+    const float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+  }
+  FFT_HD static void run_half(float2* v) { v[1] = v[0]; }
+};
+template <bool INV>
+struct Dft<4, INV> {
+  FFT_HD static void run(float2* v) {
+    const float2 a = cadd(v[0], v[2]), b = csub(v[0], v[2]);
+    const float2 c = cadd(v[1], v[3]), d = mul_qi<INV>(csub(v[1], v[3]));
+    v[0] = cadd(a, c);
+    v[1] = cadd(b, d);
+    v[2] = csub(a, c);
+    v[3] = csub(b, d);
+  }
+  FFT_HD static void run_half(float2* v) {
+    const float2 a = v[0], c = v[1], d = mul_qi<INV>(v[1]);
+    v[0] = cadd(a, c);
+    v[1] = cadd(a, d);
+    v[2] = csub(a, c);
+    v[3] = csub(a, d);
+  }
+};
+
+// R = RA*RB: n = RB*a + b, k = ka + RA*kb. HALF: inputs n >= R/2 are zero, i.e. a >= RA/2 in every sub-transform.
+template <int RA, int RB, bool INV, bool HALF = false>
+FFT_HD void dft_composite(float2* v) {
+  constexpr int R = RA * RB;
+  float2 u[RB][RA];
+#pragma unroll
+  for (int b = 0; b < RB; ++b) {
+#pragma unroll
+    for (int a = 0; a < RA; ++a) u[b][a] = v[RB * a + b];
+    if (HALF)
+      Dft<RA, INV>::run_half(u[b]);
+    else
+      Dft<RA, INV>::run(u[b]);
+#pragma unroll
+    for (int ka = 1; ka < RA; ++ka)
+      if (b > 0) u[b][ka] = rot32<INV>(u[b][ka], (32 / R) * b * ka);
+  }
+#pragma unroll
+  for (int ka = 0; ka < RA; ++ka) {
+    float2 w[RB];
+#pragma unroll
+    for (int b = 0; b < RB; ++b) w[b] = u[b][ka];
+    Dft<RB, INV>::run(w);
+#pragma unroll
+    for (int kb = 0; kb < RB; ++kb) v[ka + RA * kb] = w[kb];
+  }
+}
+template <bool INV>
+struct Dft<8, INV> {
+  FFT_HD static void run(float2* v) { dft_composite<4, 2, INV>(v); }
+  FFT_HD static void run_half(float2* v) { dft_composite<4, 2, INV, true>(v); }
+};
+template <bool INV>
+struct Dft<16, INV> {
+  FFT_HD static void run(float2* v) { dft_composite<4, 4, INV>(v); }
+  FFT_HD static void run_half(float2* v) { dft_composite<4, 4, INV, true>(v); }
+};
+template <bool INV>
+struct Dft<32, INV> {
+  FFT_HD static void run(float2* v) { dft_composite<8, 4, INV>(v); }
+  FFT_HD static void run_half(float2* v) { dft_composite<8, 4, INV, true>(v); }
+};
+
+// forward (INV = false) or unnormalised inverse (conjugated twiddles) DFT of v[0 .. R-1]
+template <int R, bool INV>
+FFT_HD void dft(float2* v) {
+  Dft<R, INV>::run(v);
+}
+
+#else  // scalar form
+
+FFT_HD float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }  // a * s, s real
+FFT_HD void store2(float2* p, float2 v) { *p = v; }
 FFT_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 FFT_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 FFT_HD float2 cmul(float2 a, float2 b) {
@@ -162,6 +399,8 @@ FFT_HD void dft(float2* v) {
   Dft<R>::run(v);
   if (INV) swap_xy<R>(v);
 }
+
+#endif  // SOPHT_FFT_USE_PACKED
 
 // ---- decomposition table --------------------------------------------------------------------------------
 template <int L>
@@ -328,8 +567,7 @@ FFT_HD void fwd_last_mul_inv_first(Acc sm, int t, G g) {
 #pragma unroll
     for (int k = 0; k < R; ++k) {
       const float s = g(blk, k);
-      v[k].x *= s;
-      v[k].y *= s;
+      v[k] = cscale(v[k], s);
     }
     dft<R, true>(v);
 #pragma unroll

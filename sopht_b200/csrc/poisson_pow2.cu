@@ -380,9 +380,15 @@ int build_green_tiles(float** gt, const float* gm, int nz, int ny, int g_row, cu
   return SOPHT_OK;
 }
 
+// SOPHT_P2_ZQUAD (default 1): 2 nz = 1024 runs the warp-quartet form (poisson_zquad.cuh) instead of zrow_kernel
+bool zquad_enabled() {
+  static const int v = env_int("SOPHT_P2_ZQUAD", 1);
+  return v != 0;
+}
 template <int L>
 int launch_zrow_L(const p2::ZRowParams& p, int nunits, cudaStream_t st) {
   using K = p2::ZRow<L>;
+  if (L == 1024 && zquad_enabled()) return launch_zquad(p, nunits, st);
   static int num_sm = 0;
   if (!num_sm) {
     SOPHT_CUDA(cudaFuncSetAttribute(p2::zrow_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -484,7 +484,7 @@ struct RowLoad {
 };
 struct RowStore {
   float2* p;
-  FFT_HD void operator()(int e, float2 v) const { p[e] = v; }
+  FFT_HD void operator()(int e, float2 v) const { fft::store2(p + e, v); }
 };
 
 template <int L, int RX, bool FULL = false>

@@ -182,8 +182,7 @@ __device__ __forceinline__ void zrow_mid(RowAcc<L> sm, int t, const float* gcol)
     fft::dft<R, false>(v);
 #pragma unroll
     for (int k = 0; k < R; ++k) {
-      v[k].x *= g[k];
-      v[k].y *= g[k];
+      v[k] = fft::cscale(v[k], g[k]);
     }
     fft::dft<R, true>(v);
 #pragma unroll
@@ -317,4 +316,7 @@ __global__ void __launch_bounds__(ZRow<L>::THREADS, 1) zrow_kernel(const ZRowPar
 #endif  // __CUDACC__
 
 }  // namespace p2
+
+// warp-quartet form of the same pass for 2 nz = 1024 (poisson_zquad.cuh; its own translation unit: packed FP32 math)
+int launch_zquad(const p2::ZRowParams& p, int nunits, cudaStream_t st);
 }  // namespace sopht

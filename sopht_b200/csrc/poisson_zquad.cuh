@@ -158,7 +158,8 @@ __global__ void __launch_bounds__(ZQuad<L>::THREADS, 1) zquad_kernel(const ZRowP
       const int kx = kxt * K::TX + c;
       asm volatile("" : "+f"(wl.x), "+f"(wl.y));
       zrow_inv_last<L>(sm, t, wl, TileStore{p.out + g * p.o_c + (kx >> 3) * p.o_bx8 + ky * p.o_by + (kx & 7)});
-      quartet_sync(g);  // the next first pass overwrites the exchange columns
+      // no barrier here: the next first pass of THIS thread overwrites exactly the positions (k S + t of column c) it has
+      // just read, nobody else's
       if (++j == 3) j = 0, jpar ^= 1;
     }
   }

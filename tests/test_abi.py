@@ -56,3 +56,30 @@ def test_no_cpu_fallback():
     k = gen_set_fixed_val_pyst_kernel_3d(np.float32)
     with pytest.raises(_lib.SophtLibraryError):
         k(field=np.zeros((4, 4, 4), np.float32), fixed_val=1.0)
+
+
+def test_install_as_sopht_aliases_the_reference_import_paths():
+    """`import sopht...` of a script written against the reference resolves to this package (sopht/__init__.py,
+    sopht/numeric/eulerian_grid_ops/__init__.py:3-133 export lists)."""
+    import importlib
+    import sys
+
+    import sopht_b200
+
+    saved = {k: v for k, v in sys.modules.items() if k == "sopht" or k.startswith("sopht.")}
+    try:
+        sopht_b200.install_as_sopht(force=True)
+        spne = importlib.import_module("sopht.numeric.eulerian_grid_ops")
+        spnib = importlib.import_module("sopht.numeric.immersed_boundary_ops")
+        sps = importlib.import_module("sopht.simulator")
+        spu = importlib.import_module("sopht.utils")
+        assert callable(spne.gen_diffusion_timestep_euler_forward_pyst_kernel_3d)
+        assert hasattr(spne, "UnboundedPoissonSolverPYFFTW3D") and hasattr(spne, "FFTPyFFTW2D")
+        assert hasattr(spnib, "VirtualBoundaryForcing") and hasattr(spnib, "EulerianLagrangianGridCommunicator3D")
+        assert hasattr(sps, "UnboundedNavierStokesFlowSimulator3D") and hasattr(sps, "CosseratRodFlowInteraction")
+        assert spu.get_real_t("single").__name__ == "float32" and hasattr(spu, "VectorField")
+        sopht_b200.install_as_sopht()  # idempotent
+    finally:
+        for k in [k for k in sys.modules if k == "sopht" or k.startswith("sopht.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

@@ -3,6 +3,15 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from sopht_b200.numeric.eulerian_grid_ops import UnboundedPoissonSolverPYFFTW3D
+if os.environ.get("SOPHT_L2_FETCH"):  # experiment: cudaLimitMaxL2FetchGranularity (32 / 64 / 128 bytes)
+    import ctypes
+    torch.cuda.init()
+    torch.zeros(1, device="cuda")
+    rt = ctypes.CDLL("libcudart.so.12")
+    val = ctypes.c_size_t(0)
+    rc = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(int(os.environ["SOPHT_L2_FETCH"])))
+    rt.cudaDeviceGetLimit(ctypes.byref(val), 5)
+    print(f"cudaLimitMaxL2FetchGranularity: rc={rc} now {val.value}")
 nz, ny, nx = (int(a) for a in sys.argv[1:4])
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 s = UnboundedPoissonSolverPYFFTW3D(nz, ny, nx, x_range=1.0, real_t=np.float32)

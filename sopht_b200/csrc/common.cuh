@@ -1,5 +1,6 @@
 // Shared helpers for libsopht_b200: view descriptors, argument checks, launch accounting.
 #pragma once
+#include <stdlib.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -157,6 +158,42 @@ inline View2<T> scalar2(const sopht_field_t* f) {
 }
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// ---- programmatic dependent launch (PDL), opt-in: SOPHT_PDL=1 ---------------------------------------------------------
+// A kernel launched through launch_pdl with the attribute may become resident while its predecessor in the stream is
+// still draining: it runs its prologue (shared-memory tables, barrier initialisation - nothing that reads or writes what
+// the predecessor produces) and then blocks in pdl_wait() until the predecessor grid has completed and its writes are
+// visible; a kernel calls pdl_launch_dependents() when it enters its last tile. Both are no-ops in a launch without the
+// attribute. MEASURED SLOWER on the Poisson chain (B200, gpurun_out/r2b_pdl_timings.txt): 512^3 step 14.1 -> 16.4 ms,
+// C2 0.505 -> 0.510 ms, C3 0.819 -> 0.846 ms - the early-resident CTAs of the next persistent kernel hold shared memory
+// and registers that the single-wave kernel in front of them still needs (the z pass wants a whole SM per CTA). Off by
+// default; kept for grids where the chain is launch-bound.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+inline bool pdl_enabled() {
+  static const int v = [] {
+    const char* e = getenv("SOPHT_PDL");
+    return e ? atoi(e) : 0;
+  }();
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 // grid for "one thread per cell, x fastest" kernels
 struct Grid3 {

@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(K::THREADS, MINB)
   if (s >= ntile) return;
   K::init(p, threadIdx.x, p2_smem);  // shared-memory tables (twiddles are read from phase 0 on)
   if (K::EXTRA_ELEMS) __syncthreads();
+  pdl_wait();  // everything below reads what the previous kernel of the stream wrote
   const TileOrder order{gx, zb_shift};
   int bx, by;
   order(s, bx, by);
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(K::THREADS, MINB)
       ns = s + gridDim.x;
     }
     const bool has_next = ns < ntile;
+    if (!has_next) pdl_launch_dependents();  // last tile of this CTA: the next kernel may start filling the tail
     K::template phase<0>(p, bx, by, it, threadIdx.x, p2_smem, stage);
     group_sync<K>();
     if (has_next) {
@@ -142,7 +144,8 @@ int launch_variant(const typename K::Params& p, dim3 grid, const char* label, cu
   if (g > ntile) g = ntile;
   SOPHT_PROF(label, st);
   while (zb_shift > 0 && (grid.y & ((1u << zb_shift) - 1))) --zb_shift;
-  p2_kernel<K, MINB, STAGED><<<(unsigned)g, K::THREADS, smem, st>>>(p, (int)grid.x, (int)grid.y, zb_shift);
+  SOPHT_CUDA(launch_pdl(p2_kernel<K, MINB, STAGED>, dim3((unsigned)g), dim3(K::THREADS), smem, st, p, (int)grid.x,
+                        (int)grid.y, zb_shift));
   SOPHT_CHECK_LAUNCH();
   return SOPHT_OK;
 }
@@ -399,7 +402,7 @@ int launch_zrow_L(const p2::ZRowParams& p, int nunits, cudaStream_t st) {
   }
   const int g = nunits < num_sm ? nunits : num_sm;
   SOPHT_PROF("poisson.z_conv", st);
-  p2::zrow_kernel<L><<<g, K::THREADS, K::SMEM_BYTES, st>>>(p, nunits);
+  SOPHT_CUDA(launch_pdl(p2::zrow_kernel<L>, dim3(g), dim3(K::THREADS), K::SMEM_BYTES, st, p, nunits));
   SOPHT_CHECK_LAUNCH();
   return SOPHT_OK;
 }

@@ -21,7 +21,7 @@ int launch_zquad(const p2::ZRowParams& p, int nunits, cudaStream_t st) {
   }
   const int g = nunits < num_sm ? nunits : num_sm;
   SOPHT_PROF("poisson.z_conv", st);
-  p2::zquad_kernel<1024><<<g, K::THREADS, K::SMEM_BYTES, st>>>(p, nunits);
+  SOPHT_CUDA(launch_pdl(p2::zquad_kernel<1024>, dim3(g), dim3(K::THREADS), K::SMEM_BYTES, st, p, nunits));
   SOPHT_CHECK_LAUNCH();
   return SOPHT_OK;
 }

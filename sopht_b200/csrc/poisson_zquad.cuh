@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(ZQuad<L>::THREADS, 1) zquad_kernel(const ZRowP
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();  // the rows are the previous kernel's output
 
   if (warp >= K::CWARPS) {
     // ---- producer warps: rows and G tiles, global -> shared, two units ahead ----
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(ZQuad<L>::THREADS, 1) zquad_kernel(const ZRowP
 #pragma unroll 1
     for (int n = 0; n < cnt; ++n) {
       const int b = n & 1;
+      if (n == cnt - 1) pdl_launch_dependents();  // last unit: the next kernel may start filling the tail
       // opaque copy: keeps the compiler from hoisting the loop-invariant twiddle powers of both passes out of the loop,
       // where they would live in local memory (16 reloads per pass through the very pipe that bounds this kernel)
       float2 wl = wj;

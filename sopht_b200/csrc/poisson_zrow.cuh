@@ -211,6 +211,7 @@ __global__ void __launch_bounds__(ZRow<L>::THREADS, 1) zrow_kernel(const ZRowPar
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pdl_wait();  // the rows are the previous kernel's output
 
   if (warp >= K::CWARPS) {
     // ---- producer warps: all global memory traffic, one component (= one group of four consumer warps) at a time ----

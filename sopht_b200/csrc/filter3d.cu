@@ -27,6 +27,7 @@ __device__ __forceinline__ T filter_point(T minus, T centre, T plus) {
 // offsets +-j. Cells within `order` of a line end see the zeroed ring of the intermediate passes and keep the
 // pass-by-pass evaluation.
 constexpr int FIR_MAX_ORDER = 8;
+constexpr int XPAD = 8;  // >= FIR_MAX_ORDER, a multiple of 4
 struct FirTaps {
   double c[FIR_MAX_ORDER + 1];
 };
@@ -52,14 +53,20 @@ inline FirTaps fir_taps(int order) {
 template <typename T, int K>  // K = the order when the one-pass filter applies (1..FIR_MAX_ORDER), 0 = pass by pass only
 __global__ void __launch_bounds__(256)
     filter_rows_x_kernel(T* f, int64_t sc, int64_t sz, int64_t sy, int ncomp, int nz, int ny, int nx, int order,
-                         int rb, FirTaps taps) {
-  extern __shared__ unsigned char filter_smem_raw[];
+                         int rb, int vec4, FirTaps taps) {
+  extern __shared__ __align__(16) unsigned char filter_smem_raw[];
   T* smem = reinterpret_cast<T*>(filter_smem_raw);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, warps = blockDim.x >> 5;
   const int span = rb * nx;
-  T* orig = smem + (size_t)w * 3 * span;
-  T* a = orig + span;
-  T* b = a + span;
+  constexpr bool fir = K > 0;  // the host picks K > 0 only when nx >= 4 K
+  // one-pass form: the originals of the batch + the K corrected cells at either end of every row; pass by pass: the
+  // originals and two ping-pong copies
+  // XPAD cells in front of and behind the originals: the 16-byte window reads of the first / last quads of the batch
+  // stay inside the warp's block (what they fetch there is never used)
+  const int per_warp = fir ? ((span + 2 * K * rb + 2 * XPAD + 3) & ~3) : 3 * span;
+  T* orig = smem + (size_t)w * per_warp + (fir ? XPAD : 0);
+  T* a = orig + span;   // fir: ends[(2 rr + right) K + t]
+  T* b = a + span;      // pass by pass only
   T c[K + 1];
 #pragma unroll
   for (int j = 0; j <= K; ++j) c[j] = T(taps.c[j]);
@@ -77,16 +84,20 @@ __global__ void __launch_bounds__(256)
     const unsigned long long my_row = lane < nrow ? (unsigned long long)row_ptr(r0 + lane) : 0ull;
     for (int rr = 0; rr < nrow; ++rr) {  // all loads of the batch are issued before anything waits on them
       const T* row = reinterpret_cast<const T*>(__shfl_sync(0xffffffffu, my_row, rr));
+      if (fir && vec4) {  // float rows, nx a multiple of 4, 16-byte aligned: a lane moves quads
+        for (int q = lane; q < nx / 4; q += 32)
+          reinterpret_cast<float4*>(orig + rr * nx)[q] = reinterpret_cast<const float4*>(row)[q];
+        continue;
+      }
       for (int i = lane; i < nx; i += 32) {
         const T v = row[i];
         orig[rr * nx + i] = v;
-        a[rr * nx + i] = v;
+        if (!fir) a[rr * nx + i] = v;
       }
     }
     __syncwarp();
     // pass by pass only where the line ends are felt: the first and last 2 K columns (what is computed there is
     // right for the outer K columns after K passes); everything else is one (2 K + 1)-tap filter of the originals
-    constexpr bool fir = K > 0;  // the host picks K > 0 only when nx >= 4 K
     if constexpr (fir) {
       // one lane per (row, line end): the 2 K cells next to the end live in registers, index 0 = the end cell (both
       // ends are the same problem mirrored, the stencil is symmetric); no shared-memory traffic, no barriers
@@ -109,9 +120,9 @@ __global__ void __launch_bounds__(256)
             prev = cur;
           }
         }
-        T* fl = a + rr * nx;
+        T* fl = a + job * K;
 #pragma unroll
-        for (int t = 0; t < K; ++t) fl[right ? nx - 1 - t : t] = u[t];
+        for (int t = 0; t < K; ++t) fl[t] = u[t];
       }
       __syncwarp();
     } else {
@@ -130,12 +141,42 @@ __global__ void __launch_bounds__(256)
     for (int rr = 0; rr < nrow; ++rr) {
       T* row = reinterpret_cast<T*>(__shfl_sync(0xffffffffu, my_row, rr));
       const T* o = orig + rr * nx;
+      if (fir && vec4) {
+        // a lane owns four consecutive cells: the 20-cell window [i0 - 8, i0 + 12) comes in as five 16-byte loads and
+        // the (2 K + 1)-tap sums run on registers (12 instead of 22 instructions per cell), one 16-byte store
+        for (int q = lane; q < nx / 4; q += 32) {
+          const int i0 = 4 * q;
+          float wv[20];
+#pragma unroll
+          for (int t = 0; t < 5; ++t) {
+            const float4 v = reinterpret_cast<const float4*>(o + i0 - 8)[t];
+            wv[4 * t] = v.x, wv[4 * t + 1] = v.y, wv[4 * t + 2] = v.z, wv[4 * t + 3] = v.w;
+          }
+          float r[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = i0 + e;
+            float flux = (float)c[0] * wv[8 + e];
+#pragma unroll
+            for (int j = 1; j <= K; ++j) flux += (float)c[j] * (wv[8 + e - j] + wv[8 + e + j]);
+            if (i < K)
+              flux = (float)a[(2 * rr) * K + i];
+            else if (i > nx - 1 - K)
+              flux = (float)a[(2 * rr + 1) * K + (nx - 1 - i)];
+            r[e] = wv[8 + e] - flux;
+          }
+          reinterpret_cast<float4*>(row)[q] = make_float4(r[0], r[1], r[2], r[3]);
+        }
+        continue;
+      }
       for (int i = lane; i < nx; i += 32) {
         T flux;
         if (fir && i >= K && i <= nx - 1 - K) {
           flux = c[0] * o[i];
 #pragma unroll
           for (int j = 1; j <= K; ++j) flux += c[j] * (o[i - j] + o[i + j]);
+        } else if (fir) {
+          flux = i < K ? a[(2 * rr) * K + i] : a[(2 * rr + 1) * K + (nx - 1 - i)];
         } else {
           flux = a[rr * nx + i];
         }
@@ -221,7 +262,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
     filter_lines_kernel(const T* __restrict__ src, T* __restrict__ dst, int64_t src_ls, int64_t src_os, int64_t dst_ls,
                         int64_t dst_os, int line_len, int n_other, int nx, int order) {
-  extern __shared__ unsigned char filter_smem_raw[];
+  extern __shared__ __align__(16) unsigned char filter_smem_raw[];
   const int H = FILTER_SEG + 2 * order;
   T* orig = reinterpret_cast<T*>(filter_smem_raw);
   T* a = orig + (size_t)H * 32;
@@ -266,7 +307,15 @@ int filter_rows_x(T* f, int64_t sc, int64_t sz, int64_t sy, int ncomp, int nz, i
   int rb = 512 / nx;
   if (rb < 1) rb = 1;
   if (rb > 32) rb = 32;  // one lane per row of the batch holds its address
-  const size_t per_warp = sizeof(T) * 3 * (size_t)nx * rb;
+  const int k = (order <= FIR_MAX_ORDER && nx >= 4 * order) ? order : 0;
+  // one-pass form: the originals + the corrected end cells (a third of the pass-by-pass footprint: three times the
+  // resident warps, which is what this latency-bound kernel is short of - 43 % occupancy, 8.8 long-scoreboard stalls
+  // per issue with the full footprint)
+  const size_t per_warp =
+      sizeof(T) * (k > 0 ? (((size_t)nx * rb + 2 * (size_t)k * rb + 2 * XPAD + 3) & ~(size_t)3) : 3 * (size_t)nx * rb);
+  // quads: float rows whose length, base and strides keep every row 16-byte aligned
+  const int vec4 = sizeof(T) == 4 && k > 0 && nx % 4 == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0 && sc % 4 == 0 &&
+                   sz % 4 == 0 && sy % 4 == 0;
   int warps = (int)((96 * 1024) / per_warp);
   if (warps > 8) warps = 8;
   if (warps < 1) SOPHT_FAIL(SOPHT_ERR_SHAPE, "laplacian filter (fused): rows of %d cells do not fit in shared memory", nx);
@@ -274,7 +323,6 @@ int filter_rows_x(T* f, int64_t sc, int64_t sz, int64_t sy, int ncomp, int nz, i
   const int64_t batches = ((int64_t)(nz - 2) * (ny - 2) * ncomp + rb - 1) / rb;
   int64_t blocks = (batches + warps - 1) / warps;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  const int k = (order <= FIR_MAX_ORDER && nx >= 4 * order) ? order : 0;
   SOPHT_PROF("laplacian_filter.x", st);
 #define ROWS_X(KK)                                                                                              \
   case KK: {                                                                                                    \
@@ -285,7 +333,7 @@ int filter_rows_x(T* f, int64_t sc, int64_t sz, int64_t sy, int ncomp, int nz, i
       attr_set = true;                                                                                          \
     }                                                                                                           \
     filter_rows_x_kernel<T, KK><<<(int)blocks, 32 * warps, smem, st>>>(f, sc, sz, sy, ncomp, nz, ny, nx, order, rb, \
-                                                                      fir_taps(KK));                            \
+                                                                      vec4, fir_taps(KK));                            \
     break;                                                                                                      \
   }
   switch (k) {

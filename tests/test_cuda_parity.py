@@ -70,6 +70,22 @@ def test_cuda_poisson_pow2_path_vs_oracle(grid):
     assert rel_l2(out[..., ::2].cpu().numpy(), want[0]) < 1e-5
 
 
+# the z pass of the 2 nz = 1024 solve has three implementations (warp-quartet kernel: default; SOPHT_P2_ZQUAD=0: row-mode
+# kernel; SOPHT_P2_ZROW=0: round-1 column kernel) and the chain has an opt-in programmatic-dependent-launch mode; the
+# library reads these switches once per process, so every variant runs in its own interpreter
+@pytest.mark.parametrize("env", [{}, {"SOPHT_P2_ZQUAD": "0"}, {"SOPHT_P2_ZROW": "0"}, {"SOPHT_PDL": "1"}],
+                         ids=["zquad", "zrow", "zconv", "zquad-pdl"])
+def test_cuda_poisson_z_pass_variants_vs_oracle(env):
+    import os
+    import subprocess
+    import sys
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, os.path.join(here, "poisson_variant_check.py"), "512", "16", "32"],
+                         env={**os.environ, **env}, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "POISSON VARIANT OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
 @pytest.mark.parametrize("precision", ["single", "double"])
 @pytest.mark.parametrize("grid", [(16, 16, 16), (9, 21, 70), (40, 24, 130)])
 def test_cuda_fused_ns3d_passes_vs_oracle(precision, grid):

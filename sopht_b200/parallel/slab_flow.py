@@ -81,6 +81,23 @@ class SlabUnboundedNavierStokesFlowSimulator3D:
             if world > 1 and self.part.nz_local < w:
                 msg = "fewer planes per rank than the penalisation width"
                 raise ValueError(msg)
+        # width 2: the penalisation is a per-axis factor and rides in the diffusion pass (like the single-GPU
+        # simulator, navier_stokes_flow_simulators.py: _penalty_ramps); the z factors are this rank's planes of the
+        # stencil view (halo planes of real neighbours: 1, global boundary planes: 0 / sin(pi / 4))
+        self._fused_ramps = None
+        if (w == 2 and (nx * 4) % 16 == 0 and min(nz, ny, nx) >= 4
+                and os.environ.get("SOPHT_FUSE_PENALISE", "1") != "0"):
+            def factors(axis_coords, n):
+                r = _sine_ramps(axis_coords, 2, self.dx, real_t)
+                f = np.ones(n, dtype=real_t)
+                f[:2], f[-2:] = r[:2], r[2:]
+                return f
+            fz = factors(coords[0], nz)
+            lo = self.part.z_start - (0 if self.part.is_first else 1)
+            hi = self.part.z_start + self.part.nz_local + (0 if self.part.is_last else 1)
+            self._fused_ramps = [torch.from_numpy(factors(coords[2], nx)).to(self.device),
+                                 torch.from_numpy(factors(coords[1], ny)).to(self.device),
+                                 torch.from_numpy(np.ascontiguousarray(fz[lo:hi])).to(self.device)]
         shape = (3, *self.part.local_shape)
         # Fields live in a peer-memory arena when there are neighbours: the halo exchange is then one kernel of
         # direct NVLink stores into the neighbours' halo planes (SOPHT_SLAB_PEER=0: torch tensors + NCCL send/recv)
@@ -143,13 +160,18 @@ class SlabUnboundedNavierStokesFlowSimulator3D:
             dc, ctypes.byref(fb), ctypes.byref(fw), ctypes.byref(fu), float(rt(dt / (2 * self.dx))), st))
         self._halos(self.buffer_vector_field)
         ff = fd(sv(self.eul_grid_forcing_field), dc) if self.with_forcing else None  # f <- 0 in the same pass
-        _lib.check(lib.sopht_ns3d_diffuse(
-            dc, ctypes.byref(fw), ctypes.byref(fb),
-            float(rt(self.kinematic_viscosity * dt / self.dx / self.dx)),
-            ctypes.byref(ff) if ff is not None else None, st))
-        if self.penalty_zone_width:
-            _lib.call("sopht_penalise_field_boundary_3d_slab", dc, self.owned(self.vorticity_field),
-                      self.penalty_zone_width, self._ramps[0], self._ramps[1], self._ramps[2], part.z_faces)
+        nu_dt_by_dx2 = float(rt(self.kinematic_viscosity * dt / self.dx / self.dx))
+        if self._fused_ramps is not None:
+            rx, ry, rz = self._fused_ramps
+            _lib.check(lib.sopht_ns3d_diffuse_penalise(
+                dc, ctypes.byref(fw), ctypes.byref(fb), nu_dt_by_dx2, ctypes.byref(ff) if ff is not None else None,
+                ctypes.c_void_p(rx.data_ptr()), ctypes.c_void_p(ry.data_ptr()), ctypes.c_void_p(rz.data_ptr()), st))
+        else:
+            _lib.check(lib.sopht_ns3d_diffuse(
+                dc, ctypes.byref(fw), ctypes.byref(fb), nu_dt_by_dx2, ctypes.byref(ff) if ff is not None else None, st))
+            if self.penalty_zone_width:
+                _lib.call("sopht_penalise_field_boundary_3d_slab", dc, self.owned(self.vorticity_field),
+                          self.penalty_zone_width, self._ramps[0], self._ramps[1], self._ramps[2], part.z_faces)
         self._unbounded_poisson_solver.vector_field_solve(
             solution_vector_field=self.owned(self.stream_func_field),
             rhs_vector_field=self.owned(self.vorticity_field))

@@ -1,8 +1,8 @@
 #!/bin/bash
 N=${1:-2}
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_slab_gpu.py tests/test_cuda_parity.py -q -m gpu -x -k "slab or z_pass_variants" 2>&1 | tail -3
-for args in "512 32 64 2" "32 16 64 3" "128 64 128 2"; do
+
+for args in "512 32 64 2" "128 64 128 2"; do
   timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541 \
     tests/mgpu_slab_check.py $args 2>&1 | grep -E "slab check|SLAB CHECK|rror" | tee -a gpurun_out/r2b_slab_check_fused_n$N.log
 done

@@ -353,6 +353,11 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// SOPHT_P2_ZQUAD (default 1): 2 nz = 1024 runs the warp-quartet form (poisson_zquad.cuh) instead of zrow_kernel
+bool zquad_enabled() {
+  static const int v = env_int("SOPHT_P2_ZQUAD", 1);
+  return v != 0;
+}
 bool zrow_enabled() {
   static const int v = env_int("SOPHT_P2_ZROW", 1);
   return v != 0;
@@ -367,6 +372,12 @@ int zrow_tx(int LZ, int ncomp, int nxl) {
   if (LZ == 1024) tx = p2::ZRow<1024>::TX;
   if (LZ == 512 && allow512) tx = p2::ZRow<512>::TX;
   return tx && nxl % tx == 0 && nxl % 8 == 0 ? tx : 0;
+}
+// the warp-quartet kernel writes, and the y inverse pass then reads, the z-blocked form of the tile-major spectrum
+// (poisson_pow2_phases.cuh: slab_y_params); SOPHT_P2_B2_Z8=0 keeps the plain form
+bool b2_z_blocked(int LZ, int ncomp, int nxl) {
+  static const int want = env_int("SOPHT_P2_B2_Z8", 1);
+  return want && LZ == 1024 && zquad_enabled() && zrow_tx(LZ, ncomp, nxl) != 0;
 }
 int zrow_gp(int LZ) { return LZ == 1024 ? p2::ZRow<1024>::GP : p2::ZRow<512>::GP; }
 
@@ -383,11 +394,6 @@ int build_green_tiles(float** gt, const float* gm, int nz, int ny, int g_row, cu
   return SOPHT_OK;
 }
 
-// SOPHT_P2_ZQUAD (default 1): 2 nz = 1024 runs the warp-quartet form (poisson_zquad.cuh) instead of zrow_kernel
-bool zquad_enabled() {
-  static const int v = env_int("SOPHT_P2_ZQUAD", 1);
-  return v != 0;
-}
 template <int L>
 int launch_zrow_L(const p2::ZRowParams& p, int nunits, cudaStream_t st) {
   using K = p2::ZRow<L>;
@@ -414,7 +420,8 @@ int launch_zrow(const p2::SlabDims& d, float2* b, float2* b2, const float* gt, c
   p.in = b;
   p.rs = LY * nxl, p.d_c = (int64_t)d.nz * LY * nxl, p.d_by = nxl;
   p.out = b2;
-  p.o_by = (int64_t)d.nz * 8, p.o_bx8 = LY * p.o_by, p.o_c = LY * d.nz * nxl;
+  p.o_by = (int64_t)d.nz * 8, p.o_bx8 = LY * p.o_by, p.o_c = LY * d.nz * nxl, p.o_bz8 = 64;
+  if (b2_z_blocked(LZ, d.C, (int)nxl)) p.o_by = 64, p.o_bz8 = LY * 64;  // (C, nxl/8, nz/8, 2ny, 8 z, 8 kx)
   p.gt = gt;
   p.ntx = (int)(nxl / tx);
   p.n2y = (int)LY;
@@ -552,7 +559,7 @@ struct Pow2Poisson : PoissonImpl {
     } else if ((rc = launch_zconv(LZ, p2::slab_z_params(d, TX, B, B2, gm, nx, 0, twz), dim3(nx / TX, LY, 1), st))) {
       return rc;
     }
-    if ((rc = launch_yinv(LY, p2::slab_y_params(d, TX, B2, A, false, twy), dim3(nx / TX, C * nz, 1), st)))
+    if ((rc = launch_yinv(LY, p2::slab_y_params(d, TX, B2, A, false, twy, gt && b2_z_blocked(LZ, C, nx)), dim3(nx / TX, C * nz, 1), st)))
       return rc;
     if (use_side) SOPHT_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
     xp = p2::slab_x_params(d, nullptr, reinterpret_cast<float*>(sol->data), vec ? sol->stride[0] : 0,
@@ -828,7 +835,8 @@ struct SlabPow2Poisson {
     }
     if ((rc = launch_zconv(LZ, p2::nyquist_z_params(d, TX, nyq_work, gn, twz), dim3(LY / TX, 1, 1), st)))
       return rc;
-    const p2::ColParams yi = p2::slab_y_params(d, TX, work2, peer ? xsend : recv, false, twy);
+    const p2::ColParams yi =
+        p2::slab_y_params(d, TX, work2, peer ? xsend : recv, false, twy, gt && b2_z_blocked(LZ, d.C, nxl));
     if ((rc = launch_yinv(LY, yi, dim3(nxl / TX, d.C * d.nz, 1), st))) return rc;
     return launch_yinv(LY, p2::nyquist_y_params(d, TX, nyq_work, nyq_all, false, twy),
                        dim3(d.C * d.nz / TX, 1, 1), st);

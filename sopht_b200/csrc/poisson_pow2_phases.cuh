@@ -74,9 +74,14 @@ struct ColParams {
   // (two terms because the tile-major spectrum the y inverse reads is not linear in by); output: out + bx*out_bx + by*out_by
   int64_t in_bx, in_by, in_bc, out_bx, out_by, out_bc;
   int log2_bz;
+  // in_by8 != 0: the input is blocked in z (planes z / 8 are in_by8 apart, planes z % 8 in_by apart inside a block): the
+  // z-blocked tile-major spectrum the warp-quartet z pass writes
+  int64_t in_by8;
   const float2* tw;                              // forward twiddles, length L
   FFT_HD const float2* in_plane(int by) const {
-    return in + (by >> log2_bz) * in_bc + (by & ((1 << log2_bz) - 1)) * in_by;
+    const int z = by & ((1 << log2_bz) - 1);
+    const int64_t zoff = in_by8 ? (z >> 3) * in_by8 + (z & 7) * in_by : z * in_by;
+    return in + (by >> log2_bz) * in_bc + zoff;
   }
   FFT_HD float2* out_plane(int by) const {
     return out + (by >> log2_bz) * out_bc + (by & ((1 << log2_bz) - 1)) * out_by;
@@ -712,8 +717,11 @@ inline XParams slab_x_params_peer(XParams xp, const SlabDims& d, float2* const* 
 // each other (its L2 prefetch hides that stride). The y forward pass keeps writing the x-major B: its 64-byte
 // stores lose more in the tile-major layout than the z pass gains (profiles/r01_poisson_layout_experiments.txt).
 // y passes on this rank's kx-slab: a = (C, nz, ny, nxl); forward a -> B, inverse B2 -> a; grid (nxl / TX, C * nz)
+// z8 (inverse only): the input is the z-blocked tile-major spectrum (C, nxl/8, nz/8, 2ny, 8 z, 8 kx) - a ky row of a
+// tile is 64 bytes, ky rows 512 bytes apart, and the eight z planes of a block (eight neighbouring CTAs of the y inverse
+// pass) read one contiguous 512 KB region together - instead of (C, nxl/8, 2ny, nz, 8 kx) with ky rows nz * 64 bytes apart
 inline ColParams slab_y_params(const SlabDims& d, int TX, const float2* in, float2* out, bool forward,
-                               const float2* tw) {
+                               const float2* tw, bool z8 = false) {
   const int64_t nxl = d.nxl(), LY = 2 * d.ny;
   ColParams yp{};
   yp.in = in;
@@ -725,6 +733,7 @@ inline ColParams slab_y_params(const SlabDims& d, int TX, const float2* in, floa
     yp.out_rs = nxl, yp.out_bx = TX, yp.out_by = LY * nxl, yp.out_bc = (int64_t)d.nz * LY * nxl;
   } else {
     yp.in_rs = (int64_t)d.nz * TX, yp.in_bx = LY * d.nz * TX, yp.in_by = TX, yp.in_bc = LY * d.nz * nxl;
+    if (z8) yp.in_rs = 8 * TX, yp.in_by8 = LY * 8 * TX;  // tile and component strides are the same in both layouts
     yp.out_rs = nxl, yp.out_bx = TX, yp.out_by = (int64_t)d.ny * nxl, yp.out_bc = (int64_t)d.nz * d.ny * nxl;
   }
   yp.tw = tw;

@@ -31,10 +31,11 @@ struct QuadLoad {
   const float2* p;
   __device__ __forceinline__ float2 operator()(int e) const { return p[e * 4]; }
 };
-// element z of a column of the kx-tile(8)-major spectrum: 8 complex apart
+// element z of a column of the kx-tile(8)-major spectrum: planes z % 8 are 8 complex apart, blocks z / 8 bz8 apart
 struct TileStore {
   float2* p;
-  __device__ __forceinline__ void operator()(int z, float2 v) const { p[(int64_t)z * 8] = v; }
+  int64_t bz8;
+  __device__ __forceinline__ void operator()(int z, float2 v) const { p[(z >> 3) * bz8 + (z & 7) * 8] = v; }
 };
 __device__ __forceinline__ void quartet_sync(int g) {
   asm volatile("bar.sync %0, 128;" ::"r"(g + 1) : "memory");
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(ZQuad<L>::THREADS, 1) zquad_kernel(const ZRowP
       const int kxt = (int)(s % p.ntx), ky = (int)(s / p.ntx);
       const int kx = kxt * K::TX + c;
       asm volatile("" : "+f"(wl.x), "+f"(wl.y));
-      zrow_inv_last<L>(sm, t, wl, TileStore{p.out + g * p.o_c + (kx >> 3) * p.o_bx8 + ky * p.o_by + (kx & 7)});
+      zrow_inv_last<L>(sm, t, wl, TileStore{p.out + g * p.o_c + (kx >> 3) * p.o_bx8 + ky * p.o_by + (kx & 7), p.o_bz8});
       // no barrier here: the next first pass of THIS thread overwrites exactly the positions (k S + t of column c) it has
       // just read, nobody else's
       if (++j == 3) j = 0, jpar ^= 1;

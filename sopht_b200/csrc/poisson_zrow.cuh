@@ -37,6 +37,7 @@ struct ZRowParams {
   int64_t rs, d_c, d_by;
   float2* out;             // kx-tile(8)-major spectrum B2: (c, z, ky, kx) at c*o_c + (kx/8)*o_bx8 + ky*o_by + z*8 + kx%8
   int64_t o_c, o_bx8, o_by;
+  int64_t o_bz8;           // warp-quartet kernel: distance of the z / 8 blocks (64 = the plain layout above; 2ny * 64: z-blocked)
   const float* gt;         // tile-major folded G_hat: block (fy * ntx + kxt) of TX * GP floats, [col][kq][r][4]:
                            // element (kq, r, i) = G_hat(fz = r + NBLK * (4 kq + i)), r <= NBLK (see ZRow::GP)
   int ntx;                 // kx tiles of TX columns (this rank's kx range)

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 ( time timeout 900 python -m pytest tests -q -m gpu -x --durations=5 ) > gpurun_out/r2b_pytest_gpu.log 2>&1
 tail -9 gpurun_out/r2b_pytest_gpu.log
-for wl in u512 c1 c2 c3 tg512 u256; do
+for wl in u512 c2; do
   timeout 400 python bench.py --workload $wl > gpurun_out/r2b_bench_$wl.json 2> gpurun_out/r2b_bench_$wl.err
   python tools/show_bench.py gpurun_out/r2b_bench_$wl.json 2>/dev/null | head -1 | cut -c1-110
 done

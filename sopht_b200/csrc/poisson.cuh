@@ -36,6 +36,9 @@ PoissonImpl* make_pow2_poisson(int nz, int ny, int nx, double dx, const double* 
 // Homogeneous Neumann walls on the cell-centred grid (the reference's FastDiagPoissonSolver{2,3}D): mirror
 // extension + periodic three-point symbol (poisson_neumann.cu)
 PoissonImpl* make_neumann_poisson(int dtype, int dim, int nz, int ny, int nx, double dx, cudaStream_t st, int* rc);
+// the same solve through same-length DCT-II transforms (poisson_neumann_dct.cu): 3-D grids with even extents
+bool neumann_dct_eligible(int dim, int nz, int ny, int nx);
+PoissonImpl* make_neumann_dct_poisson(int dtype, int nz, int ny, int nx, double dx, cudaStream_t st, int* rc);
 // Periodic in every direction (an extension, BASELINE config 4): same pipeline without the mirror step
 PoissonImpl* make_periodic_poisson(int dtype, int three_point_symbol, int dim, int nz, int ny, int nx, double dx,
                                    cudaStream_t st, int* rc);

@@ -269,6 +269,7 @@ PoissonImpl* make_neumann(int kind, int dim, int nz, int ny, int nx, double dx, 
 }  // namespace
 
 PoissonImpl* make_neumann_poisson(int dtype, int dim, int nz, int ny, int nx, double dx, cudaStream_t st, int* rc) {
+  if (neumann_dct_eligible(dim, nz, ny, nx)) return make_neumann_dct_poisson(dtype, nz, ny, nx, dx, st, rc);
   return dtype == SOPHT_F32 ? make_neumann<float>(0, dim, nz, ny, nx, dx, st, rc)
                             : make_neumann<double>(0, dim, nz, ny, nx, dx, st, rc);
 }

@@ -1,8 +1,8 @@
 """Neumann (fast-diagonalisation) Poisson solver.
 
 Fixtures: the reference's own FastDiagPoissonSolver{2,3}D run in the build container (tests/golden/make_golden.py ->
-fastdiag_*.npz). CPU: the oracle restatement against them, and a numpy emulation of the algorithm the CUDA path uses
-(mirror extension + periodic three-point symbol) against them. GPU: the CUDA classes through the C ABI against the
+fastdiag_*.npz). CPU: the oracle restatement against them, and numpy emulations of the two algorithms the CUDA path uses
+(same-length Makhoul DCTs on even 3-D grids; mirror extension + periodic three-point symbol otherwise) against them. GPU: the CUDA classes through the C ABI against the
 fixtures, against the oracle on other sizes, and residual / mean properties at a BASELINE-size grid."""
 
 import os
@@ -39,6 +39,50 @@ def _mirror_fft_solve(rhs, dx):
     return sol[tuple(slice(0, n) for n in rhs.shape)]
 
 
+def _dct_solve(rhs, dx):
+    """numpy emulation of csrc/poisson_neumann_dct.cu (float64): same-length transforms. DCT-II of length n from one
+    real FFT of the even / odd reordered sequence (Makhoul): X[k] = Re(w^k V[k]), X[n-k] = -Im(w^k V[k]),
+    w = exp(-i pi / 2n); (y, x) through a 2-D real FFT, z through a 1-D one, the pair (kz, nz - kz) scaled in place."""
+    nz, ny, nx = rhs.shape
+    nkx, nkz = nx // 2 + 1, nz // 2 + 1
+
+    def src(n):
+        d = np.arange(n)
+        return np.where(d < n // 2, 2 * d, 2 * (n - 1 - d) + 1)
+
+    def dst(n):
+        s = np.arange(n)
+        return np.where(s % 2 == 1, n - 1 - s // 2, s // 2)
+
+    lam = [4.0 * np.sin(np.pi * np.arange(n) / (2 * n)) ** 2 / (dx * dx) for n in (nz, ny, nx)]
+    wz, wy, wx = (np.exp(-1j * np.pi * np.arange(m) / (2 * n)) for n, m in ((nz, nkz), (ny, ny), (nx, nkx)))
+    s1 = np.fft.rfft2(rhs.astype(np.float64)[:, src(ny)][:, :, src(nx)], axes=(1, 2))
+    kyc = (ny - np.arange(ny)) % ny
+    p = s1 * wx
+    q = np.conj(s1[:, kyc, :]) * np.conj(wx)
+    r2 = np.zeros((nz, ny, nx))
+    dz = dst(nz)
+    r2[dz, :, :nkx] = np.real(wy[:, None] * 0.5 * (p + q))
+    r2[dz, :, nx - 1:nx // 2:-1] = np.real(wy[:, None] * 0.5j * (p - q))[:, :, 1:nx // 2]  # X[ky, nx - kx], 0 < kx < nx/2
+    s2 = np.fft.rfft(r2, axis=0)
+    lyx = lam[1][:, None] + lam[2][None, :]
+    for k in range(nkz):
+        t = s2[k] * wz[k]
+        with np.errstate(divide="ignore"):
+            s0 = 1.0 / (lam[0][k] + lyx)
+        if k == 0:
+            s0[0, 0] = 0.0  # the mean mode is dropped
+        s1k = 1.0 / (lam[0][nz - k] + lyx) if k else 0.0
+        s2[k] = (t.real * s0 + 1j * t.imag * s1k) * np.conj(wz[k])
+    x = np.fft.irfft(s2, n=nz, axis=0)[dz]
+    pad = np.zeros((nz, ny + 1, nx + 1))  # X[ny, .] = X[., nx] = 0
+    pad[:, :ny, :nx] = x
+    ky, kx = np.arange(ny)[:, None], np.arange(nkx)[None, :]
+    v = (pad[:, ky, kx] - pad[:, ny - ky, nx - kx]) - 1j * (pad[:, ky, nx - kx] + pad[:, ny - ky, kx])
+    r1 = np.fft.irfft2(v * np.conj(wy[:, None] * wx[None, :]), s=(ny, nx), axes=(1, 2))
+    return r1[:, dst(ny)][:, :, dst(nx)]
+
+
 @pytest.mark.parametrize("precision", ["single", "double"])
 def test_oracle_matches_reference_fixtures(precision):
     from oracle.poisson import FastDiagPoissonSolver
@@ -69,6 +113,26 @@ def test_mirror_fft_algorithm_matches_reference_fixtures():
     assert abs(sol2.mean()) < 1e-13  # the null (mean) mode is dropped
 
 
+def test_dct_algorithm_matches_reference_fixtures_and_oracle():
+    """The same-length (Makhoul) form the CUDA path uses on even 3-D grids is the reference's dense eigen-solve."""
+    from oracle.poisson import FastDiagPoissonSolver
+
+    g = _golden("double")
+    if all(n % 2 == 0 for n in g["neumann3d/rhs"].shape[1:]):
+        for c in range(3):
+            sol = _dct_solve(g["neumann3d/rhs"][c], float(g["neumann3d/dx"]))
+            assert _rel_l2(sol, g["neumann3d/solution"][c]) < 1e-11
+    rng = np.random.default_rng(5)
+    for grid in [(8, 6, 10), (4, 4, 4), (16, 8, 12), (2, 2, 2), (2, 12, 4)]:
+        dx = 1.0 / grid[-1]
+        rhs = rng.standard_normal(grid)
+        ref = np.zeros(grid)
+        FastDiagPoissonSolver(grid, dx, np.float64).solve(ref, rhs)
+        sol = _dct_solve(rhs, dx)
+        assert _rel_l2(sol, ref) < 1e-12
+        assert abs(sol.mean()) < 1e-13
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["single", "double"])
 def test_cuda_fastdiag_matches_reference_fixtures(precision):
@@ -85,7 +149,7 @@ def test_cuda_fastdiag_matches_reference_fixtures(precision):
     nz, ny, nx = rhs.shape[1:]
     solver = spne.FastDiagPoissonSolver3D(grid_size_z=nz, grid_size_y=ny, grid_size_x=nx,
                                           dx=real_t(g["neumann3d/dx"]), real_t=real_t)
-    assert solver.path == "neumann_mirror_fft"
+    assert solver.path == "neumann_dct"  # even 3-D grid: same-length transforms (odd extents: "neumann_mirror_fft")
     sol = torch.zeros_like(rhs)
     solver.vector_field_solve(solution_vector_field=sol, rhs_vector_field=rhs)
     assert _rel_l2(sol.cpu().numpy(), g["neumann3d/solution"]) < tol

@@ -19,7 +19,7 @@ int launch_zquad(const p2::ZRowParams& p, int nunits, cudaStream_t st) {
     SOPHT_CUDA(cudaGetDevice(&dev));
     SOPHT_CUDA(cudaDeviceGetAttribute(&num_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-  const int g = nunits < num_sm ? nunits : num_sm;
+  const int g = nunits / 2 < num_sm ? nunits / 2 : num_sm;  // a CTA owns pairs of units
   SOPHT_PROF("poisson.z_conv", st);
   SOPHT_CUDA(launch_pdl(p2::zquad_kernel<1024>, dim3(g), dim3(K::THREADS), K::SMEM_BYTES, st, p, nunits));
   SOPHT_CHECK_LAUNCH();

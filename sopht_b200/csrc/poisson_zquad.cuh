@@ -72,8 +72,13 @@ __global__ void __launch_bounds__(ZQuad<L>::THREADS, 1) zquad_kernel(const ZRowP
   // (the quartet of component g has read buffer b), gfull[j] = bars[12 + j] (G tile buffer j has landed)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if ((int)blockIdx.x >= nunits) return;
-  const int cnt = (nunits - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;  // units of this CTA
+  // Units are handed out in PAIRS of neighbouring kx quads (pair P = units 2P, 2P + 1; CTA b owns pairs b, b + gridDim.x,
+  // ...): the two 32-byte rows of a pair are the halves of one 64-byte L2 fetch, so the second unit's rows are L2 hits
+  // instead of a second DRAM fetch by another CTA (DRAM reads of the launch 10.2 -> 8.8 GB at 512^3; same time). nunits is even
+  // (the kx range is a multiple of 8).
+  const int npairs = nunits / 2;
+  if ((int)blockIdx.x >= npairs) return;
+  const int cnt = 2 * ((npairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);  // units of this CTA
   if (tid == 0) {
     for (int i = 0; i < 6; ++i) mbar_init(bars + i, K::PTHREADS);
     for (int i = 6; i < 12; ++i) mbar_init(bars + i, 4);
@@ -88,7 +93,7 @@ __global__ void __launch_bounds__(ZQuad<L>::THREADS, 1) zquad_kernel(const ZRowP
     const int pt = tid - K::CTHREADS;
     const int half = pt & 1, z0 = pt >> 1;           // 16-byte half of a row, rows z0 + 64 i
     auto refill = [&](int g, int n, int b) {
-      const int64_t s = (int64_t)blockIdx.x + (int64_t)n * gridDim.x;
+      const int64_t s = 2 * ((int64_t)blockIdx.x + (int64_t)(n >> 1) * gridDim.x) + (n & 1);
       const int kxt = (int)(s % p.ntx), ky = (int)(s / p.ntx);
       const float2* src = p.in + g * p.d_c + ky * p.d_by + kxt * K::TX + 2 * half + (int64_t)z0 * p.rs;
       float2* dst = stage + (b * 3 + g) * K::TILE + z0 * K::TX + 2 * half;
@@ -105,7 +110,7 @@ __global__ void __launch_bounds__(ZQuad<L>::THREADS, 1) zquad_kernel(const ZRowP
       mbar_arrive_on_copies(bars + 2 * g + b);
     };
     auto load_green = [&](int n, int j) {  // G tile of the n-th unit -> G buffer j (column pitch GP -> GPQ)
-      const int64_t s = (int64_t)blockIdx.x + (int64_t)n * gridDim.x;
+      const int64_t s = 2 * ((int64_t)blockIdx.x + (int64_t)(n >> 1) * gridDim.x) + (n & 1);
       const int kxt = (int)(s % p.ntx), ky = (int)(s / p.ntx);
       const int fy = ky <= p.n2y / 2 ? ky : p.n2y - ky;
       const float* gsrc = p.gt + ((int64_t)fy * p.ntx + kxt) * (K::TX * K::GP);
@@ -156,7 +161,7 @@ __global__ void __launch_bounds__(ZQuad<L>::THREADS, 1) zquad_kernel(const ZRowP
       mbar_wait(bars + 12 + j, jpar);                    // G tile
       zrow_mid<L>(sm, t, gbuf + j * (K::TX * K::GPQ) + c * K::GPQ);
       quartet_sync(g);
-      const int64_t s = (int64_t)blockIdx.x + (int64_t)n * gridDim.x;
+      const int64_t s = 2 * ((int64_t)blockIdx.x + (int64_t)(n >> 1) * gridDim.x) + (n & 1);
       const int kxt = (int)(s % p.ntx), ky = (int)(s / p.ntx);
       const int kx = kxt * K::TX + c;
       asm volatile("" : "+f"(wl.x), "+f"(wl.y));

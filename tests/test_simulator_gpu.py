@@ -85,9 +85,9 @@ def test_navier_stokes_2d_step(rng, precision, with_forcing, grid):
 
 
 # ---- BASELINE.json sizes: size-independent properties (the oracle takes minutes there) ------------------------------
-@pytest.mark.parametrize("grid", [(128, 128, 256), (256, 256, 256)])
+@pytest.mark.parametrize("grid", [(128, 128, 256), (256, 256, 256), (512, 512, 512)])
 def test_poisson_full_size_pow2_vs_cufft_path_and_linearity(grid):
-    """C2 / 256^3: the hand-written pruned FFT pipeline against the cuFFT-based generic path of the same library
+    """C2 / 256^3 / 512^3 (the bench default: the warp-quartet z pass at full size): the hand-written pruned FFT pipeline against the cuFFT-based generic path of the same library
     (independent code: padded doubled domain, cuFFT transforms), plus linearity of the solve."""
     import torch
 

@@ -483,7 +483,10 @@ __global__ void __launch_bounds__(32 * VBY, sizeof(T) == 4 ? 4 : 1)  // fp32: 64
 // ACCUM = true : out += p * curl_c(psi) on the interior, ring cells untouched (the forcing update
 //                w += p curl(f), update_vorticity_from_velocity_forcing_3d.py:12-132). 24 B read + 12 B written.
 template <typename T, bool ACCUM, bool PXY = false>
-__global__ void __launch_bounds__(32 * VBY)
+// fp32 curl(psi): three CTAs per SM (80 registers, a few spilled words) instead of two (106): 0.637 -> 0.556 ms at 512^3
+// (5.8 TB/s); the accumulating form and fp64 keep their register budget. Measured the same way: advect at three CTAs
+// spills 300 bytes (0.91 -> 2.66 ms), diffuse at five / six CTAs loses 2 - 9 %.
+__global__ void __launch_bounds__(32 * VBY, (sizeof(T) == 4 && !ACCUM) ? 3 : 1)
     velocity_vec_kernel(Vec3Out<T> out, Vec3View<T> psi, T p, T fx, T fy, T fz, T* max_out, int nz, int ny,
                         int nx, int kchunk) {
   constexpr int W = Vec<T>::W;
